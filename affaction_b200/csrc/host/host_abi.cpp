@@ -1,0 +1,247 @@
+// extern "C" surface of the host shim: scene loading, candidate generation
+// from text commands, batch prediction with message strings.  This is what a
+// non-C++ front end (the ctypes binding in affaction_b200/__init__.py, the
+// pybind module of the reference's python/module.cpp) binds.
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <sstream>
+#include <string>
+
+#include "ActionBase.h"
+#include "ActionGet.h"
+#include "TrajectoryPredictor.h"
+#include "affpredict_host.h"
+
+using namespace aff;
+
+struct aff_host_scene
+{
+  Graph graph;
+  ActionScene domain;
+  aff_scene* device = nullptr;
+};
+
+struct aff_host_batch
+{
+  CandidateBatch batch;
+  std::vector<std::string> commands;   // per candidate
+};
+
+static thread_local std::string g_hostError;
+
+extern "C" {
+
+const char* aff_host_last_error(void) { return g_hostError.c_str(); }
+
+aff_host_scene* aff_host_scene_load(const char* path)
+{
+  try {
+    std::unique_ptr<aff_host_scene> s(new aff_host_scene);
+    std::vector<std::string> tail;
+    s->graph = Graph::load(path, &tail);
+    s->domain.parse(tail);
+    s->graph.toDesc();
+    return s.release();
+  } catch (const std::exception& e) {
+    g_hostError = e.what();
+    return nullptr;
+  }
+}
+
+void aff_host_scene_destroy(aff_host_scene* s)
+{
+  if (!s) return;
+  if (s->device) aff_scene_destroy(s->device);
+  delete s;
+}
+
+const aff_scene_desc* aff_host_scene_desc(aff_host_scene* s) { return s->graph.toDesc(); }
+int aff_host_num_bodies(const aff_host_scene* s) { return (int)s->graph.bodies.size(); }
+int aff_host_num_ik_joints(const aff_host_scene* s) { return s->graph.nJ; }
+int aff_host_body_id(const aff_host_scene* s, const char* name) { return s->graph.getBodyByName(name); }
+const char* aff_host_body_name(const aff_host_scene* s, int id)
+{
+  return (id >= 0 && id < (int)s->graph.bodies.size()) ? s->graph.bodies[id].name.c_str() : "NULL";
+}
+const char* aff_host_ik_joint_name(const aff_host_scene* s, int jacobiIndex)
+{
+  for (const Joint& j : s->graph.joints) if (j.jacobiIndex == jacobiIndex) return j.name.c_str();
+  return "NULL";
+}
+
+int aff_host_scene_connect(aff_host_scene* s, const char* child, const char* parent)
+{
+  try {
+    const int c = s->graph.getBodyByName(child), p = s->graph.getBodyByName(parent);
+    if (c < 0 || p < 0) { g_hostError = "unknown body"; return AFF_ERR_INVALID; }
+    s->graph.connectBody(c, p);
+    s->graph.toDesc();
+    if (s->device) { aff_scene_destroy(s->device); s->device = nullptr; }
+    return AFF_OK;
+  } catch (const std::exception& e) { g_hostError = e.what(); return AFF_ERR_INVALID; }
+}
+
+aff_scene* aff_host_scene_device(aff_host_scene* s, int device)
+{
+  if (!s->device) {
+    if (aff_scene_create(s->graph.toDesc(), device, &s->device) != AFF_OK) { g_hostError = aff_last_error(); return nullptr; }
+  }
+  return s->device;
+}
+
+aff_host_batch* aff_host_batch_create(void) { return new aff_host_batch; }
+void aff_host_batch_destroy(aff_host_batch* b) { delete b; }
+void aff_host_batch_clear(aff_host_batch* b) { b->batch = CandidateBatch(); b->commands.clear(); }
+
+size_t aff_host_batch_num_tasks(const aff_host_batch* b) { return b->batch.tasks.size(); }
+size_t aff_host_batch_num_constraints(const aff_host_batch* b) { return b->batch.constraints.size(); }
+size_t aff_host_batch_num_candidates(const aff_host_batch* b) { return b->batch.candidates.size(); }
+const aff_task_desc* aff_host_batch_tasks(const aff_host_batch* b) { return b->batch.tasks.data(); }
+const aff_constraint* aff_host_batch_constraints(const aff_host_batch* b) { return b->batch.constraints.data(); }
+const aff_candidate* aff_host_batch_candidates(const aff_host_batch* b) { return b->batch.candidates.data(); }
+const char* aff_host_batch_task_name(const aff_host_batch* b, size_t cand, int task)
+{
+  if (cand >= b->batch.taskNames.size() || task < 0 || task >= (int)b->batch.taskNames[cand].size()) return "";
+  return b->batch.taskNames[cand][task].c_str();
+}
+
+// The predict block of ActionComponent::actionThread (reference
+// src/ActionComponent.cpp:145-199): create the action, then one candidate per
+// solution: clone, initialize(i), describe.
+int aff_host_batch_add_action(aff_host_batch* b, aff_host_scene* s, const char* text, double durationScale, double dt)
+{
+  try {
+    auto action = ActionFactory::create(s->domain, s->graph, text);
+    const size_t n = action->getNumSolutions();
+    for (size_t i = 0; i < n; ++i) {
+      auto local = action->clone();
+      if (!local->initialize(s->domain, s->graph, i)) { g_hostError = "initialize failed"; return AFF_ERR_INVALID; }
+      local->appendTo(b->batch, s->graph, durationScale * local->getDurationHint(), dt);
+      b->commands.push_back(local->getActionCommand());
+    }
+    return (int)n;
+  } catch (const std::exception& e) {
+    g_hostError = e.what();
+    return AFF_ERR_INVALID;
+  }
+}
+
+// splitmix64: one independent stream per rollout index
+static inline uint64_t splitmix(uint64_t& x)
+{
+  uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static inline double uni(uint64_t& st, double lo, double hi)
+{
+  return lo + (hi - lo) * ((double)(splitmix(st) >> 11) * (1.0 / 9007199254740992.0));
+}
+
+// Synthetic perturbed-goal sweep: rollout i uses hand
+// i mod nSolutions, RNG seed seed0 + i, object position +U(-5,5) cm in x/y,
+// +U(0,2) cm in z, yaw +U(-30,30) deg, preGraspDist x U(0.8,1.2), liftHeight
+// +U(-3,3) cm.  The duration stays at the action's hint so every rollout runs
+// the same, full number of steps.
+int aff_host_batch_add_perturbed(aff_host_batch* b, aff_host_scene* s, const char* text, size_t n, uint64_t seed0, double dt)
+{
+  try {
+    auto action = ActionFactory::create(s->domain, s->graph, text);
+    ActionGet* get = dynamic_cast<ActionGet*>(action.get());
+    if (!get) { g_hostError = "perturbed sweeps are defined for get actions"; return AFF_ERR_UNSUPPORTED; }
+    const size_t nSol = action->getNumSolutions();
+    std::vector<std::unique_ptr<ActionBase>> sols;
+    for (size_t r = 0; r < nSol; ++r) { sols.push_back(action->clone()); sols.back()->initialize(s->domain, s->graph, r); }
+    const int obj = s->graph.getBodyByName(get->objectName);
+    const Body& ob = s->graph.bodies[obj];
+    if (!ob.rigid_body_joints) { g_hostError = "object has no rigid body joints"; return AFF_ERR_INVALID; }
+    double q6[6];
+    for (int k = 0; k < 6; ++k) q6[k] = s->graph.joints[ob.firstJoint + k].q_init;
+    b->batch.candidates.reserve(b->batch.candidates.size() + n);
+    for (size_t i = 0; i < n; ++i) {
+      uint64_t st = seed0 + i;
+      ActionGet local(*static_cast<ActionGet*>(sols[i % nSol].get()));
+      double p6[6];
+      for (int k = 0; k < 6; ++k) p6[k] = q6[k];
+      p6[0] += uni(st, -0.05, 0.05);
+      p6[1] += uni(st, -0.05, 0.05);
+      const double dz = uni(st, 0.0, 0.02);
+      p6[2] += dz;
+      p6[5] += uni(st, -30.0, 30.0) * (M_PI / 180.0);
+      local.preGraspDist *= uni(st, 0.8, 1.2);
+      local.liftHeight += dz + uni(st, -0.03, 0.03);
+      const double delay = 5.0 * dt;
+      b->batch.append(s->graph, local.createTasks(), local.createTrajectory(delay, local.getDurationHint() + delay), obj, p6);
+      b->commands.push_back(local.getActionCommand());
+    }
+    return (int)n;
+  } catch (const std::exception& e) {
+    g_hostError = e.what();
+    return AFF_ERR_INVALID;
+  }
+}
+
+// Predict all candidates on the GPU, optionally sorted with
+// PredictionResult::lesser; messages are written as NUL-terminated strings of
+// at most msgStride-1 characters each.
+int aff_host_predict(aff_host_scene* s, aff_host_batch* b, double dt, int sortResults, int device,
+                     aff_result* rawOut, char* messages, size_t msgStride)
+{
+  try {
+    aff_scene* dev = aff_host_scene_device(s, device);
+    if (!dev) return AFF_ERR_CUDA;
+    auto res = TrajectoryPredictor::predictBatch(dev, s->graph, b->batch, dt, sortResults != 0);
+    for (size_t i = 0; i < res.size(); ++i) {
+      if (rawOut) rawOut[i] = res[i].raw;
+      if (messages && msgStride > 0) {
+        std::string m = res[i].message;
+        // multi-candidate path appends the command (reference src/ActionComponent.cpp:193)
+        if (res[i].idx >= 0 && (size_t)res[i].idx < b->commands.size()) m += " command: " + b->commands[res[i].idx];
+        std::strncpy(messages + i * msgStride, m.c_str(), msgStride - 1);
+        messages[i * msgStride + msgStride - 1] = '\0';
+      }
+    }
+    return (int)res.size();
+  } catch (const std::exception& e) {
+    g_hostError = e.what();
+    return AFF_ERR_CUDA;
+  }
+}
+
+// Message for a raw record (used by tests to compare oracle and GPU wording).
+int aff_host_format_message(aff_host_scene* s, aff_host_batch* b, const aff_result* r, double dt, char* out, size_t n)
+{
+  static const std::vector<std::string> none;
+  const auto& names = (r->idx >= 0 && (size_t)r->idx < b->batch.taskNames.size()) ? b->batch.taskNames[r->idx] : none;
+  const auto p = TrajectoryPredictor::convert(*r, s->graph, names, dt);
+  std::strncpy(out, p.message.c_str(), n - 1);
+  out[n - 1] = '\0';
+  return (int)p.message.size();
+}
+
+}   // extern "C"
+
+namespace aff
+{
+
+std::unique_ptr<ActionBase> ActionFactory::create(const ActionScene& domain, const Graph& graph, const std::string& text)
+{
+  std::istringstream is(text);
+  std::vector<std::string> words;
+  for (std::string w; is >> w;) words.push_back(w);
+  if (words.empty()) throw ActionException("ERROR: empty action command", ActionException::ParamNotFound);
+  const std::string name = words[0];
+  std::vector<std::string> params(words.begin() + 1, words.end());
+  std::unique_ptr<ActionBase> a;
+  if (name == "get") a.reset(new ActionGet(domain, graph, params));
+  else
+    throw ActionException("ERROR: REASON: Action '" + name + "' is not part of the GPU predict path" +
+                          " SUGGESTION: Use one of: get", ActionException::ParamNotFound);
+  a->setName(name);
+  a->setActionParams(params);
+  return a;
+}
+
+}   // namespace aff

@@ -1,0 +1,66 @@
+/*
+ * affpredict_host.h — C view of the host shim that sits above affpredict.h.
+ *
+ * The reference's front ends reach the predict step through C++ objects
+ * (ActionFactory::create -> ActionBase -> predict, reference
+ * src/ActionComponent.cpp:145-244) and through the pybind module
+ * python/module.cpp.  These functions expose the same steps to C / ctypes:
+ * load a scene, turn a text command into its Capability x Affordance
+ * candidates, predict them all on the GPU and read back results + messages.
+ */
+#ifndef AFFPREDICT_HOST_H
+#define AFFPREDICT_HOST_H
+
+#include "affpredict.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct aff_host_scene aff_host_scene;
+typedef struct aff_host_batch aff_host_batch;
+
+const char* aff_host_last_error(void);
+
+/* Scene = kinematic graph + affordance model, from a flattened .affscene file
+ * (tools/flatten_scene.py output of the reference's XML scene). NULL on error. */
+aff_host_scene* aff_host_scene_load(const char* path);
+void aff_host_scene_destroy(aff_host_scene* s);
+const aff_scene_desc* aff_host_scene_desc(aff_host_scene* s);
+int aff_host_num_bodies(const aff_host_scene* s);
+int aff_host_num_ik_joints(const aff_host_scene* s);
+int aff_host_body_id(const aff_host_scene* s, const char* name);
+const char* aff_host_body_name(const aff_host_scene* s, int id);
+const char* aff_host_ik_joint_name(const aff_host_scene* s, int jacobi_index);
+/* Re-parent a body keeping its world pose (state left by a finished get). */
+int aff_host_scene_connect(aff_host_scene* s, const char* child, const char* parent);
+/* Device-side scene handle (created on first use). NULL on CUDA failure. */
+aff_scene* aff_host_scene_device(aff_host_scene* s, int device);
+
+aff_host_batch* aff_host_batch_create(void);
+void aff_host_batch_destroy(aff_host_batch* b);
+void aff_host_batch_clear(aff_host_batch* b);
+/* ActionFactory::create(text) + one candidate per solution. Returns the
+ * number of candidates appended, or <0 (message in aff_host_last_error —
+ * the text of the reference's ActionException). */
+int aff_host_batch_add_action(aff_host_batch* b, aff_host_scene* s, const char* text, double duration_scale, double dt);
+/* n synthetic perturbed candidates of a get command, seeds seed0 + i. */
+int aff_host_batch_add_perturbed(aff_host_batch* b, aff_host_scene* s, const char* text, size_t n, uint64_t seed0, double dt);
+
+size_t aff_host_batch_num_tasks(const aff_host_batch* b);
+size_t aff_host_batch_num_constraints(const aff_host_batch* b);
+size_t aff_host_batch_num_candidates(const aff_host_batch* b);
+const aff_task_desc* aff_host_batch_tasks(const aff_host_batch* b);
+const aff_constraint* aff_host_batch_constraints(const aff_host_batch* b);
+const aff_candidate* aff_host_batch_candidates(const aff_host_batch* b);
+const char* aff_host_batch_task_name(const aff_host_batch* b, size_t cand, int task);
+
+/* Predict every candidate of the batch on `device`; returns the count or <0. */
+int aff_host_predict(aff_host_scene* s, aff_host_batch* b, double dt, int sort_results, int device,
+                     aff_result* raw_out, char* messages, size_t msg_stride);
+int aff_host_format_message(aff_host_scene* s, aff_host_batch* b, const aff_result* r, double dt, char* out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
