@@ -1,0 +1,311 @@
+// C ABI of the B200 predictor (include/affpredict.h): device memory, uploads,
+// kernel launches.  There is no CPU fallback: every entry point that computes
+// returns AFF_ERR_CUDA if the CUDA runtime / a B200 is not usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "affpredict.h"
+#include "kernel/plan_build.h"
+#include "kernel/rollout.cuh"
+
+#define AFF_WARPS_PER_BLOCK 4
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(AFF_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+// ------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(32) aff_prologue_kernel(const KPlan P)
+{
+  k_prologue(P);
+}
+
+// Persistent rollout kernel: one warp per candidate, warps stride over the batch.
+__global__ void __launch_bounds__(32 * AFF_WARPS_PER_BLOCK) aff_rollout_kernel(const KPlan P)
+{
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5;
+  double* sm = smem + (size_t)warp * P.warp_doubles;
+  const int warpsTotal = gridDim.x * AFF_WARPS_PER_BLOCK;
+  for (int cand = blockIdx.x * AFF_WARPS_PER_BLOCK + warp; cand < P.nCands; cand += warpsTotal) {
+    k_rollout(P, cand, sm);
+    __syncwarp();
+  }
+}
+
+// Register-resident DFMA chains: the FP64 roofline denominator.
+__global__ void aff_dfma_peak_kernel(double* out, int iters)
+{
+  double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 0.1, a2 = a0 + 0.2, a3 = a0 + 0.3, a4 = a0 + 0.4, a5 = a0 + 0.5, a6 = a0 + 0.6, a7 = a0 + 0.7;
+  const double b = 0.999999, cc = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, cc); a1 = fma(a1, b, cc); a2 = fma(a2, b, cc); a3 = fma(a3, b, cc);
+    a4 = fma(a4, b, cc); a5 = fma(a5, b, cc); a6 = fma(a6, b, cc); a7 = fma(a7, b, cc);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+// ------------------------------------------------------------------ handles
+struct aff_scene
+{
+  int device = 0;
+  affk::SceneModel model;
+};
+
+template <class T> struct DevBuf
+{
+  T* p = nullptr; size_t n = 0;
+  cudaError_t upload(const std::vector<T>& v, cudaStream_t s)
+  {
+    n = v.size();
+    cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(1, n) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (n) e = cudaMemcpyAsync(p, v.data(), n * sizeof(T), cudaMemcpyHostToDevice, s);
+    return e;
+  }
+  cudaError_t alloc(size_t count)
+  {
+    n = count;
+    return cudaMalloc((void**)&p, std::max<size_t>(1, n) * sizeof(T));
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; }
+};
+
+struct aff_batch
+{
+  aff_scene* scene = nullptr;
+  affk::HostPlan host;
+  KPlan plan{};
+  DevBuf<double> jq_init, jq0, jq_min, jq_max, jspeed, jacc, jwjl, jwmetric, obj_q6, statA, statSC, dynSC, sshapeA, sbodyAABB, qlog;
+  DevBuf<int32_t> j_node, j_type, rounds, always, obj_node, obj_body;
+  DevBuf<KNode> dyn, stat;
+  DevBuf<KShape> dshape, sshape;
+  DevBuf<KShapeBody> dbody, sbody;
+  DevBuf<KTask> tasks; DevBuf<KVia> vias; DevBuf<KAct> acts; DevBuf<KGraphCon> gcons; DevBuf<KCand> cands;
+  DevBuf<aff_result> results;
+  int grid = 0; size_t smemBytes = 0; int launches = 0;
+  size_t h2dBytes = 0;
+  bool prologueDone = false;
+  void release()
+  {
+    jq_init.release(); jq0.release(); jq_min.release(); jq_max.release(); jspeed.release(); jacc.release(); jwjl.release();
+    jwmetric.release(); obj_q6.release(); statA.release(); statSC.release(); dynSC.release(); sshapeA.release();
+    sbodyAABB.release(); qlog.release(); j_node.release(); j_type.release(); rounds.release(); always.release();
+    obj_node.release(); obj_body.release(); dyn.release(); stat.release(); dshape.release(); sshape.release();
+    dbody.release(); sbody.release(); tasks.release(); vias.release(); acts.release(); gcons.release(); cands.release();
+    results.release();
+  }
+};
+
+extern "C" {
+
+int aff_abi_version(void) { return AFF_ABI_VERSION; }
+const char* aff_last_error(void) { return g_err.c_str(); }
+
+void aff_default_opts(aff_opts* o)
+{
+  if (!o) return;
+  o->dt = 0.01; o->alpha = 0.05; o->lambda = 1.0e-6; o->q_filt_decay = 0.1; o->n_after_steps = 500; o->log_q = 0;
+}
+
+int aff_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { g_err = "cudaGetDeviceCount failed: no usable CUDA device"; return AFF_ERR_CUDA; }
+  return n;
+}
+
+int aff_scene_create(const aff_scene_desc* desc, int device, aff_scene** out)
+{
+  if (!desc || !out) return fail(AFF_ERR_INVALID, "aff_scene_create: null argument");
+  int n = 0;
+  CUDA_TRY(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) return fail(AFF_ERR_CUDA, "aff_scene_create: CUDA device " + std::to_string(device) + " not present (no CPU fallback)");
+  aff_scene* s = new aff_scene;
+  s->device = device;
+  const std::string e = s->model.init(desc);
+  if (!e.empty()) { delete s; return fail(AFF_ERR_INVALID, "aff_scene_create: " + e); }
+  *out = s;
+  return AFF_OK;
+}
+
+void aff_scene_destroy(aff_scene* s) { delete s; }
+int aff_scene_num_ik_joints(const aff_scene* s) { return s ? s->model.nJ : 0; }
+
+static int uploadBatch(aff_batch* b, cudaStream_t st)
+{
+  affk::HostPlan& H = b->host;
+  KPlan& P = b->plan;
+  P = H.plan;
+#define UP(name) do { CUDA_TRY(b->name.upload(H.name, st)); b->h2dBytes += H.name.size() * sizeof(H.name[0]); } while (0)
+  UP(jq_init); UP(jq0); UP(jq_min); UP(jq_max); UP(jspeed); UP(jacc); UP(jwjl); UP(jwmetric); UP(obj_q6);
+  UP(j_node); UP(j_type); UP(rounds); UP(always); UP(obj_node); UP(obj_body);
+  UP(dyn); UP(stat); UP(dshape); UP(sshape); UP(dbody); UP(sbody);
+  UP(tasks); UP(vias); UP(acts); UP(gcons); UP(cands);
+#undef UP
+  CUDA_TRY(b->statA.alloc(12 * (size_t)(P.nStatic + 1)));
+  CUDA_TRY(b->statSC.alloc(2 * (size_t)std::max(P.nStatic, 1)));
+  CUDA_TRY(b->dynSC.alloc(2 * (size_t)std::max(P.nDyn, 1)));
+  CUDA_TRY(b->sshapeA.alloc(12 * (size_t)std::max(P.nStatShapes, 1)));
+  CUDA_TRY(b->sbodyAABB.alloc(6 * (size_t)std::max(P.nStatBodies, 1)));
+  CUDA_TRY(b->results.alloc((size_t)P.nCands));
+  P.qlog = nullptr; P.qlog_rows = 0;
+  if (P.opts.log_q) {
+    P.qlog_rows = H.maxSteps + 1;
+    CUDA_TRY(b->qlog.alloc((size_t)P.nCands * P.qlog_rows * P.nJ));
+    P.qlog = b->qlog.p;
+  }
+  P.jq_init = b->jq_init.p; P.jq0 = b->jq0.p; P.jq_min = b->jq_min.p; P.jq_max = b->jq_max.p; P.jspeed = b->jspeed.p;
+  P.jacc = b->jacc.p; P.jwjl = b->jwjl.p; P.jwmetric = b->jwmetric.p; P.j_node = b->j_node.p; P.j_type = b->j_type.p;
+  P.dyn = b->dyn.p; P.stat = b->stat.p; P.statA = b->statA.p; P.statSC = b->statSC.p; P.dynSC = b->dynSC.p; P.rounds = b->rounds.p;
+  P.dshape = b->dshape.p; P.dbody = b->dbody.p; P.sshape = b->sshape.p; P.sbody = b->sbody.p; P.sshapeA = b->sshapeA.p;
+  P.sbodyAABB = b->sbodyAABB.p; P.always = b->always.p; P.obj_node = b->obj_node.p; P.obj_body = b->obj_body.p; P.obj_q6 = b->obj_q6.p;
+  P.tasks = b->tasks.p; P.vias = b->vias.p; P.acts = b->acts.p; P.gcons = b->gcons.p; P.cands = b->cands.p;
+  P.results = b->results.p;
+  return AFF_OK;
+}
+
+int aff_batch_create(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, const aff_constraint* cons, size_t n_cons,
+                     const aff_candidate* cands, size_t n_cands, const aff_opts* opts, aff_batch** out)
+{
+  if (!s || !out || !cands || (!tasks && n_tasks) || (!cons && n_cons)) return fail(AFF_ERR_INVALID, "aff_batch_create: null argument");
+  aff_opts o;
+  if (opts) o = *opts; else aff_default_opts(&o);
+  if (!(o.dt > 0.0)) return fail(AFF_ERR_INVALID, "aff_batch_create: dt must be positive");
+  CUDA_TRY(cudaSetDevice(s->device));
+  aff_batch* b = new aff_batch;
+  b->scene = s;
+  std::string e;
+  int rc = affk::buildPlan(s->model, tasks, n_tasks, cons, n_cons, cands, n_cands, o, b->host, e);
+  if (rc != AFF_OK) { delete b; return fail(rc, "aff_batch_create: " + e); }
+  rc = uploadBatch(b, 0);
+  if (rc != AFF_OK) { b->release(); delete b; return rc; }
+  // launch geometry: persistent blocks, as many as fit per SM
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
+  b->smemBytes = b->host.smemBytesPerWarp * AFF_WARPS_PER_BLOCK;
+  if (b->smemBytes > (size_t)prop.sharedMemPerBlockOptin) { b->release(); delete b; return fail(AFF_ERR_CAPACITY, "aff_batch_create: rollout state does not fit in shared memory"); }
+  CUDA_TRY(cudaFuncSetAttribute(aff_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smemBytes));
+  int perSM = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, aff_rollout_kernel, 32 * AFF_WARPS_PER_BLOCK, b->smemBytes));
+  if (perSM < 1) perSM = 1;
+  const int blocksNeeded = (int)((n_cands + AFF_WARPS_PER_BLOCK - 1) / AFF_WARPS_PER_BLOCK);
+  b->grid = std::max(1, std::min(blocksNeeded, perSM * prop.multiProcessorCount));
+  CUDA_TRY(cudaStreamSynchronize(0));
+  *out = b;
+  return AFF_OK;
+}
+
+void aff_batch_destroy(aff_batch* b)
+{
+  if (!b) return;
+  b->release();
+  delete b;
+}
+
+int aff_batch_launch(aff_batch* b, void* stream)
+{
+  if (!b) return fail(AFF_ERR_INVALID, "aff_batch_launch: null batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(b->scene->device));
+  b->launches = 0;
+  if (!b->prologueDone) {
+    aff_prologue_kernel<<<1, 32, 0, st>>>(b->plan);
+    CUDA_TRY(cudaGetLastError());
+    b->prologueDone = true;
+    b->launches++;
+  }
+  aff_rollout_kernel<<<b->grid, 32 * AFF_WARPS_PER_BLOCK, b->smemBytes, st>>>(b->plan);
+  CUDA_TRY(cudaGetLastError());
+  b->launches++;
+  return AFF_OK;
+}
+
+void* aff_batch_results_device(aff_batch* b) { return b ? (void*)b->results.p : nullptr; }
+
+int aff_batch_results(aff_batch* b, void* stream, aff_result* out, size_t n)
+{
+  if (!b || !out) return fail(AFF_ERR_INVALID, "aff_batch_results: null argument");
+  if (n > (size_t)b->plan.nCands) n = (size_t)b->plan.nCands;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpyAsync(out, b->results.p, n * sizeof(aff_result), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return AFF_OK;
+}
+
+int aff_batch_last_launch_count(const aff_batch* b) { return b ? b->launches : 0; }
+int aff_batch_num_steps(const aff_batch* b, size_t cand) { return (b && cand < b->host.cands.size()) ? b->host.cands[cand].n_steps : -1; }
+size_t aff_batch_h2d_bytes(const aff_batch* b) { return b ? b->h2dBytes : 0; }
+size_t aff_batch_smem_bytes_per_warp(const aff_batch* b) { return b ? b->host.smemBytesPerWarp : 0; }
+int aff_batch_grid_blocks(const aff_batch* b) { return b ? b->grid : 0; }
+
+int aff_batch_fetch_q(aff_batch* b, size_t cand, double* out, size_t max_rows)
+{
+  if (!b || !out) return fail(AFF_ERR_INVALID, "aff_batch_fetch_q: null argument");
+  if (!b->plan.qlog) return fail(AFF_ERR_INVALID, "aff_batch_fetch_q: batch was created without opts.log_q");
+  if (cand >= (size_t)b->plan.nCands) return fail(AFF_ERR_INVALID, "aff_batch_fetch_q: candidate out of range");
+  const size_t rows = std::min<size_t>(max_rows, (size_t)b->host.cands[cand].n_steps + 1);
+  CUDA_TRY(cudaMemcpy(out, b->qlog.p + cand * (size_t)b->plan.qlog_rows * b->plan.nJ, rows * b->plan.nJ * sizeof(double), cudaMemcpyDeviceToHost));
+  return (int)rows;
+}
+
+int aff_predict_batch(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, const aff_constraint* cons, size_t n_cons,
+                      const aff_candidate* cands, size_t n_cands, const aff_opts* opts, aff_result* out)
+{
+  aff_batch* b = nullptr;
+  int rc = aff_batch_create(s, tasks, n_tasks, cons, n_cons, cands, n_cands, opts, &b);
+  if (rc != AFF_OK) return rc;
+  rc = aff_batch_launch(b, nullptr);
+  if (rc == AFF_OK) rc = aff_batch_results(b, nullptr, out, n_cands);
+  aff_batch_destroy(b);
+  return rc;
+}
+
+void aff_rank_results(const aff_result* res, size_t n, int32_t* order)
+{
+  for (size_t i = 0; i < n; ++i) order[i] = (int32_t)i;
+  std::stable_sort(order, order + n, [&](int32_t a, int32_t b) {
+    const aff_result& x = res[a]; const aff_result& y = res[b];
+    if ((x.success != 0) != (y.success != 0)) return x.success != 0;
+    const double qx = x.jl_cost + x.coll_cost, qy = y.jl_cost + y.coll_cost;
+    if (qx != qy) return qx < qy;
+    return x.idx < y.idx;
+  });
+}
+
+double aff_measure_fp64_peak(int device, double seconds)
+{
+  if (cudaSetDevice(device) != cudaSuccess) { g_err = "aff_measure_fp64_peak: no CUDA device"; return -1.0; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+  const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
+  double* d = nullptr;
+  if (cudaMalloc((void**)&d, sizeof(double) * threads * blocks) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  aff_dfma_peak_kernel<<<blocks, threads>>>(d, 1024);   // warm-up
+  cudaDeviceSynchronize();
+  double best = 0.0, spent = 0.0;
+  while (spent < seconds) {
+    cudaEventRecord(e0);
+    aff_dfma_peak_kernel<<<blocks, threads>>>(d, iters);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 8.0 * (double)iters * threads * blocks;
+    best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+    spent += ms * 1e-3 + 1e-4;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  return best;
+}
+
+}   // extern "C"

@@ -1,0 +1,152 @@
+// Device-side "plan": the flattened, index-only form of (scene, tasks,
+// constraints, candidates) that the rollout kernel walks.  Built on the host by
+// plan.cpp (structure only: no floating-point arithmetic happens there, so
+// every rounded number the verdicts depend on is produced by the kernels).
+//
+// One warp runs one candidate rollout.  Bodies whose world pose can change
+// during a rollout become "dynamic nodes" kept in shared memory; everything
+// else is a "static node" whose world pose is computed once per batch by the
+// prologue kernel and read from HBM/L2 through the read-only path.
+#ifndef AFF_KERNEL_PLAN_H
+#define AFF_KERNEL_PLAN_H
+
+#include <stdint.h>
+
+#include "affpredict.h"
+
+#define AFFK_MAX_NJ 32        // IK joints: one lane each
+#define AFFK_MAX_DYN 40       // dynamic nodes
+#define AFFK_MAX_XDIM 24      // stacked task dimensions of one candidate
+#define AFFK_MAX_TASKS 12     // tasks of one candidate
+#define AFFK_MAX_M 16         // task rows active at the same time
+#define AFFK_MAX_OBJ 2        // re-parentable objects per candidate
+#define AFFK_MAX_DSHAPE 20    // shapes on dynamic nodes
+#define AFFK_MAX_DBODY 16     // shape bodies on dynamic nodes
+#define AFFK_MAX_LIVE 192     // body pairs in the collision model of one step
+#define AFFK_MAX_VIA_UNK 6    // unknown polynomial coefficients per 1-D window
+#define AFFK_MAX_ROUNDS 40    // FK schedule rounds
+#define AFFK_VIA_STRIDE 49    // doubles of solver scratch per trajectory lane (6*7 matrix + 6 solution, odd stride)
+
+// node reference: >= 0 dynamic node, -1 world, <= -2 static node (-2 - idx)
+#define AFFK_WORLD (-1)
+#define AFFK_STATIC_REF(i) (-2 - (i))
+#define AFFK_STATIC_IDX(r) (-2 - (r))
+
+enum { AFFK_NODE_FIXED = 0, AFFK_NODE_JOINT_IK = 1, AFFK_NODE_JOINT_CONST = 2, AFFK_NODE_OBJECT = 3 };
+
+struct KNode
+{
+  int32_t parent;      // node reference
+  int32_t kind;        // AFFK_NODE_*
+  int32_t jtype;       // AFF_JNT_* for joint kinds
+  int32_t qidx;        // JOINT_IK: jacobi index; OBJECT: object slot
+  int32_t identityT;   // T is the identity: copy the parent
+  int32_t under_obj;   // slot+1 if this node is a re-parentable object or below one
+  int32_t tree;        // broad-phase tree the node belongs to by construction, -1 none
+  uint32_t chain;      // IK joints (bit = jacobi index) that move this node by construction
+  double qconst;       // JOINT_CONST value
+  double T[12];        // A_JP (joints) or A_BP (fixed)
+};
+
+struct KShape
+{
+  int32_t type;        // AFF_SHAPE_*
+  int32_t active0;     // RCSSHAPE_COMPUTE_DISTANCE at start
+  int32_t node;        // node reference of the owning body
+  int32_t pad;
+  double ext[3];
+  double A_CB[12];
+};
+
+// A body owning primitive shapes.
+struct KShapeBody
+{
+  int32_t body;        // scene body id (result reporting, pair ordering)
+  int32_t node;        // node reference
+  int32_t first_shape, n_shapes;   // into the dynamic or static shape table
+  int32_t explicit_bp; // listed as <Body> in the broad phase
+  int32_t tree;        // static tree id or -1 (dynamic bodies not under an object)
+  int32_t obj_slot;    // slot+1 if the body is a re-parentable object or below one (tree membership)
+  int32_t toggle_slot; // slot+1 if the body IS the object (CollisionModelConstraint target)
+  int32_t any_active0; // has an initially active shape
+  int32_t pad;
+};
+
+struct KTask
+{
+  int32_t kind;
+  int32_t eff, ref, frame;   // node references (frame already resolved: AFFK_WORLD = world)
+  int32_t axis;
+  int32_t n_joints;
+  int32_t jidx[AFF_MAX_TASK_JOINTS];  // jacobi index, or -1 - (static value slot) for constrained joints
+  double jconst[AFF_MAX_TASK_JOINTS]; // value of constrained joints
+  int32_t has_region;
+  int32_t xoff;              // offset in the candidate's stacked x
+  double region_min, region_max, region_dx_scaling;
+};
+
+struct KVia { double t, x, xd, xdd; int32_t flag; int32_t pad; };
+struct KAct { double t, horizon; int32_t on; int32_t pad; };
+struct KGraphCon { double t; int32_t kind; int32_t on; int32_t slot; int32_t parent; };  // parent: node reference
+
+struct KCand
+{
+  int32_t first_task, n_tasks, xdim;
+  int32_t first_via;               // vias sorted by (dimension, time)
+  int32_t via_off[AFFK_MAX_XDIM + 1]; // per-dimension slice, relative to first_via
+  int32_t first_act;               // activations sorted by (task, time)
+  int32_t act_off[AFFK_MAX_TASKS + 1];
+  int32_t first_gcon, n_gcon;
+  int32_t n_steps;
+  int32_t pose_slot;               // object slot whose q6 is overridden, -1 none
+  double pose_q6[6];
+  double end_abs, start_abs;
+};
+
+// Everything the kernels need, passed by value.
+struct KPlan
+{
+  int32_t nJ, nDyn, nStatic, nRounds, nObj;
+  int32_t nDynShapes, nDynBodies, nStatShapes, nStatBodies, nTrees;
+  int32_t nAlways;                 // always-live body pairs (tree x tree, tree x explicit)
+  int32_t ns_base, ns_upperarm[2], ns_forearm[2], ns_hand[2];   // node references, AFFK_WORLD = absent
+  uint32_t rbj_static_chain;       // IK joints moving some non-object rigid-body-joint body
+  double bp_threshold;
+
+  // joints (jacobi order)
+  const double* jq_init; const double* jq0; const double* jq_min; const double* jq_max;
+  const double* jspeed; const double* jacc; const double* jwjl; const double* jwmetric;
+  const int32_t* j_node;           // dynamic node of the joint frame
+  const int32_t* j_type;
+
+  const KNode* dyn;                // [nDyn], parents first
+  const KNode* stat;               // [nStatic], parents first
+  double* statA;                   // [nStatic*12] world transforms   (written by the prologue)
+  double* statSC;                  // [nStatic*2]  sin/cos of constant joints
+  double* dynSC;                   // [nDyn*2]     sin/cos of constant joints on dynamic nodes
+  const int32_t* rounds;           // [nRounds*2] FK schedule: two dynamic nodes per round, -1 = none
+
+  const KShape* dshape; const KShapeBody* dbody;   // dynamic
+  const KShape* sshape; const KShapeBody* sbody;   // static
+  double* sshapeA;                 // [nStatShapes*12] world shape frames (prologue)
+  double* sbodyAABB;               // [nStatBodies*6]                      (prologue)
+  const int32_t* always;           // [nAlways*2]: dynamic body index, other body (>=0 dynamic, <0: -1-static index)
+  const int32_t* obj_node;         // [nObj] dynamic node of each object slot
+  const int32_t* obj_body;         // [nObj] scene body id
+  const double* obj_q6;            // [nObj*6] scene values of the six rigid-body dofs
+
+  const KTask* tasks; const KVia* vias; const KAct* acts; const KGraphCon* gcons; const KCand* cands;
+  int32_t nCands;
+
+  // shared-memory layout of one warp, in doubles from the warp base
+  int32_t o_node, o_q, o_qdot, o_dH, o_dq, o_sn, o_cs, o_J, o_L, o_rhs, o_dx, o_st, o_xdes, o_xcur, o_geo,
+          o_objrel, o_objq6, o_shp, o_baabb, o_taabb, o_scratch, o_live, warp_doubles;
+  int32_t JS, LS;                  // row strides of J and L (odd: conflict-free column access)
+
+  aff_opts opts;
+  aff_result* results;             // [nCands]
+  double* qlog;                    // [nCands * (maxSteps+1) * nJ] or NULL
+  int32_t qlog_rows;
+};
+
+#endif

@@ -1,0 +1,450 @@
+#include "plan_build.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace affk
+{
+
+static bool isIdentity12(const double* T)
+{
+  static const double I[12] = {0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < 12; ++i) if (T[i] != I[i]) return false;
+  return true;
+}
+
+std::string SceneModel::init(const aff_scene_desc* d)
+{
+  if (!d || d->n_bodies <= 0) return "empty scene description";
+  nB = d->n_bodies; nQ = d->n_joints; nS = d->n_shapes;
+  parent.assign(d->body_parent, d->body_parent + nB);
+  firstJoint.assign(d->body_first_joint, d->body_first_joint + nB);
+  nJoints.assign(d->body_n_joints, d->body_n_joints + nB);
+  firstShape.assign(d->body_first_shape, d->body_first_shape + nB);
+  nShapes.assign(d->body_n_shapes, d->body_n_shapes + nB);
+  rbj.assign(d->body_rbj, d->body_rbj + nB);
+  A_BP.assign(d->body_A_BP, d->body_A_BP + 12 * (size_t)nB);
+  jtype.assign(d->joint_type, d->joint_type + nQ);
+  jcon.assign(d->joint_constrained, d->joint_constrained + nQ);
+  A_JP.assign(d->joint_A_JP, d->joint_A_JP + 12 * (size_t)nQ);
+  qInit.assign(d->joint_q_init, d->joint_q_init + nQ);
+  q0.assign(d->joint_q0, d->joint_q0 + nQ);
+  qMin.assign(d->joint_q_min, d->joint_q_min + nQ);
+  qMax.assign(d->joint_q_max, d->joint_q_max + nQ);
+  speed.assign(d->joint_speed_limit, d->joint_speed_limit + nQ);
+  acc.assign(d->joint_acc_limit, d->joint_acc_limit + nQ);
+  wjl.assign(d->joint_weight_jl, d->joint_weight_jl + nQ);
+  wmetric.assign(d->joint_weight_metric, d->joint_weight_metric + nQ);
+  stype.assign(d->shape_type, d->shape_type + nS);
+  sdist.assign(d->shape_distance, d->shape_distance + nS);
+  A_CB.assign(d->shape_A_CB, d->shape_A_CB + 12 * (size_t)nS);
+  ext.assign(d->shape_extents, d->shape_extents + 3 * (size_t)nS);
+  bpThreshold = d->bp_threshold;
+  bpTree.assign(d->bp_tree_root, d->bp_tree_root + d->n_bp_trees);
+  bpBody.assign(d->bp_body, d->bp_body + d->n_bp_bodies);
+  ns_base = d->ns_base;
+  for (int k = 0; k < 2; ++k) { ns_upperarm[k] = d->ns_upperarm[k]; ns_forearm[k] = d->ns_forearm[k]; ns_hand[k] = d->ns_hand[k]; }
+  jacobi.assign(nQ, -1); jointBody.assign(nQ, -1);
+  nJ = 0;
+  for (int j = 0; j < nQ; ++j) if (!jcon[j]) { jacobi[j] = nJ++; ikJoint.push_back(j); }
+  for (int b = 0; b < nB; ++b) {
+    if (parent[b] >= b) return "scene bodies must list parents before children";
+    for (int k = 0; k < nJoints[b]; ++k) jointBody[firstJoint[b] + k] = b;
+  }
+  explicitBp.assign(nB, 0);
+  for (int b : bpBody) { if (b < 0 || b >= nB) return "broad phase body out of range"; explicitBp[b] = 1; }
+  for (int b : bpTree) if (b < 0 || b >= nB) return "broad phase tree root out of range";
+  if (nJ > AFFK_MAX_NJ) return "more than 32 unconstrained joints";
+  if ((int)bpTree.size() > 14) return "more than 14 broad phase trees";
+  return "";
+}
+
+static int popcount3(int flag) { return (flag & 1) + ((flag >> 1) & 1) + ((flag >> 2) & 1); }
+
+int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn, const aff_constraint* consIn, size_t nConsIn,
+              const aff_candidate* candsIn, size_t nCands, const aff_opts& opts, HostPlan& H, std::string& err)
+{
+  H = HostPlan();
+  KPlan& P = H.plan;
+  const int nB = S.nB;
+  if (nCands == 0) { err = "empty batch"; return AFF_ERR_INVALID; }
+
+  // ---- objects: bodies that can be re-parented, posed per candidate or toggled
+  std::vector<int> objSlotOfBody(nB, -1);
+  std::vector<int> objBodies;
+  auto addObject = [&](int b) -> bool {
+    if (b < 0 || b >= nB) { err = "constraint names a body outside the scene"; return false; }
+    if (objSlotOfBody[b] >= 0) return true;
+    if (!S.rbj[b] || S.nJoints[b] != 6) { err = "re-parentable / posed / toggled bodies need rigid_body_joints"; return false; }
+    if (!isIdentity12(&S.A_BP[12 * b])) { err = "rigid-body-joint objects with an extra body transform are not supported"; return false; }
+    if ((int)objBodies.size() >= AFFK_MAX_OBJ) { err = "more than AFFK_MAX_OBJ objects in one batch"; return false; }
+    objSlotOfBody[b] = (int)objBodies.size();
+    objBodies.push_back(b);
+    return true;
+  };
+  for (size_t i = 0; i < nCands; ++i) {
+    const aff_candidate& c = candsIn[i];
+    if (c.first_task < 0 || c.n_tasks < 0 || (size_t)(c.first_task + c.n_tasks) > nTasksIn ||
+        c.first_constraint < 0 || c.n_constraints < 0 || (size_t)(c.first_constraint + c.n_constraints) > nConsIn) {
+      err = "candidate slices outside the task / constraint tables"; return AFF_ERR_INVALID;
+    }
+    if (c.pose_body >= 0 && !addObject(c.pose_body)) return AFF_ERR_UNSUPPORTED;
+    for (int k = 0; k < c.n_constraints; ++k) {
+      const aff_constraint& cc = consIn[c.first_constraint + k];
+      if ((cc.kind == AFF_CON_CONNECT || cc.kind == AFF_CON_COLLISION) && !addObject(cc.body_a)) return AFF_ERR_UNSUPPORTED;
+      if (cc.kind == AFF_CON_CONNECT && (cc.body_b < 0 || cc.body_b >= nB)) { err = "connect parent outside the scene"; return AFF_ERR_INVALID; }
+    }
+  }
+  const int nObj = (int)objBodies.size();
+
+  // ---- dynamic bodies: moved by an IK joint, or an object / below one
+  std::vector<char> dynamicB(nB, 0), underObj(nB, 0);
+  std::vector<uint32_t> chainB(nB, 0u);
+  std::vector<int> treeB(nB, -1);
+  for (int b = 0; b < nB; ++b) {
+    const int p = S.parent[b];
+    uint32_t ch = p >= 0 ? chainB[p] : 0u;
+    for (int k = 0; k < S.nJoints[b]; ++k) { const int c = S.jacobi[S.firstJoint[b] + k]; if (c >= 0) ch |= 1u << c; }
+    chainB[b] = ch;
+    underObj[b] = (objSlotOfBody[b] >= 0) ? (char)(objSlotOfBody[b] + 1) : (p >= 0 ? underObj[p] : 0);
+    dynamicB[b] = (ch != 0u) || underObj[b];
+    int tr = p >= 0 ? treeB[p] : -1;
+    for (size_t t = 0; t < S.bpTree.size(); ++t) if (S.bpTree[t] == b) tr = (int)t;
+    treeB[b] = tr;
+  }
+  // rbj bodies that are not objects: their chains are masked out of the null space for good
+  uint32_t rbjStatic = 0u;
+  for (int b = 0; b < nB; ++b) if (S.rbj[b] && !underObj[b]) rbjStatic |= chainB[b];
+
+  // ---- which dynamic bodies are needed
+  std::vector<char> needed(nB, 0);
+  auto need = [&](int b) { for (int a = b; a >= 0 && !needed[a]; a = S.parent[a]) needed[a] = 1; };
+  for (int j : S.ikJoint) need(S.jointBody[j]);
+  for (int b : objBodies) need(b);
+  for (int b : {S.ns_base, S.ns_upperarm[0], S.ns_upperarm[1], S.ns_forearm[0], S.ns_forearm[1], S.ns_hand[0], S.ns_hand[1]}) if (b >= 0) need(b);
+  for (size_t i = 0; i < nTasksIn; ++i) {
+    const aff_task_desc& t = tasksIn[i];
+    for (int b : {t.effector, t.ref_body, t.ref_frame}) {
+      if (b >= nB) { err = "task names a body outside the scene"; return AFF_ERR_INVALID; }
+      if (b >= 0) need(b);
+    }
+  }
+  for (size_t i = 0; i < nConsIn; ++i) if (consIn[i].kind == AFF_CON_CONNECT && consIn[i].body_b >= 0 && consIn[i].body_b < nB) need(consIn[i].body_b);
+  std::vector<char> shapeBody(nB, 0);
+  for (int b = 0; b < nB; ++b) {
+    bool any = false;
+    for (int k = 0; k < S.nShapes[b]; ++k) any = any || S.sdist[S.firstShape[b] + k];
+    if (objSlotOfBody[b] >= 0 && S.nShapes[b] > 0) any = true;
+    if (any) { shapeBody[b] = 1; need(b); }
+  }
+
+  // ---- nodes
+  std::vector<int> bodyRef(nB, AFFK_WORLD), jointRef(S.nQ, AFFK_WORLD);
+  H.j_node.assign(S.nJ, -1); H.j_type.assign(S.nJ, 0);
+  auto mkNode = [](int parentRef, int kind, const double* T) {
+    KNode n; std::memset(&n, 0, sizeof(n));
+    n.parent = parentRef; n.kind = kind; n.tree = -1;
+    std::memcpy(n.T, T, sizeof(double) * 12);
+    n.identityT = isIdentity12(T) ? 1 : 0;
+    return n;
+  };
+  for (int b = 0; b < nB; ++b) {
+    const int pRef = S.parent[b] >= 0 ? bodyRef[S.parent[b]] : AFFK_WORLD;
+    if (!dynamicB[b]) {
+      int cur = pRef;
+      for (int k = 0; k < S.nJoints[b]; ++k) {
+        const int j = S.firstJoint[b] + k;
+        KNode n = mkNode(cur, AFFK_NODE_JOINT_CONST, &S.A_JP[12 * j]);
+        n.jtype = S.jtype[j]; n.qconst = S.qInit[j];
+        H.stat.push_back(n);
+        cur = AFFK_STATIC_REF((int)H.stat.size() - 1);
+        jointRef[j] = cur;
+      }
+      if (!isIdentity12(&S.A_BP[12 * b]) || cur == AFFK_WORLD) {
+        H.stat.push_back(mkNode(cur, AFFK_NODE_FIXED, &S.A_BP[12 * b]));
+        cur = AFFK_STATIC_REF((int)H.stat.size() - 1);
+      }
+      bodyRef[b] = cur;
+      continue;
+    }
+    if (!needed[b]) continue;
+    const int uo = underObj[b];
+    if (objSlotOfBody[b] >= 0) {
+      static const double I[12] = {0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1};
+      KNode n = mkNode(pRef, AFFK_NODE_OBJECT, I);
+      n.qidx = objSlotOfBody[b]; n.under_obj = uo; n.chain = 0u; n.tree = -1;
+      H.dyn.push_back(n);
+      bodyRef[b] = (int)H.dyn.size() - 1;
+      continue;
+    }
+    int cur = pRef;
+    for (int k = 0; k < S.nJoints[b]; ++k) {
+      const int j = S.firstJoint[b] + k;
+      const int c = S.jacobi[j];
+      KNode n = mkNode(cur, c >= 0 ? AFFK_NODE_JOINT_IK : AFFK_NODE_JOINT_CONST, &S.A_JP[12 * j]);
+      n.jtype = S.jtype[j]; n.qconst = S.qInit[j]; n.qidx = c >= 0 ? c : 0; n.under_obj = uo;
+      // chain up to and including this joint
+      uint32_t ch = S.parent[b] >= 0 ? chainB[S.parent[b]] : 0u;
+      for (int kk = 0; kk <= k; ++kk) { const int cc = S.jacobi[S.firstJoint[b] + kk]; if (cc >= 0) ch |= 1u << cc; }
+      n.chain = uo ? 0u : ch;
+      n.tree = uo ? -1 : treeB[b];
+      H.dyn.push_back(n);
+      cur = (int)H.dyn.size() - 1;
+      jointRef[j] = cur;
+      if (c >= 0) { H.j_node[c] = cur; H.j_type[c] = S.jtype[j]; }
+    }
+    bool isTreeRoot = false;
+    for (int r : S.bpTree) isTreeRoot = isTreeRoot || (r == b);
+    // The body frame aliases its last joint frame (or its parent) when A_BP is the identity.
+    const bool alias = isIdentity12(&S.A_BP[12 * b]) && cur >= 0 && !(isTreeRoot && S.nJoints[b] == 0);
+    if (!alias) {
+      KNode n = mkNode(cur, AFFK_NODE_FIXED, &S.A_BP[12 * b]);
+      n.under_obj = uo; n.chain = uo ? 0u : chainB[b]; n.tree = uo ? -1 : treeB[b];
+      H.dyn.push_back(n);
+      cur = (int)H.dyn.size() - 1;
+    }
+    bodyRef[b] = cur;
+  }
+  if ((int)H.dyn.size() > AFFK_MAX_DYN) { err = "too many dynamic nodes (" + std::to_string(H.dyn.size()) + ")"; return AFF_ERR_CAPACITY; }
+  for (int c = 0; c < S.nJ; ++c) if (H.j_node[c] < 0) { err = "internal: IK joint without a node"; return AFF_ERR_INVALID; }
+
+  // ---- FK schedule: two nodes per round, parents in earlier rounds
+  {
+    const int nD = (int)H.dyn.size();
+    std::vector<int> roundOf(nD, 0), fill;
+    for (int n = 0; n < nD; ++n) {
+      int r = 0;
+      const int p = H.dyn[n].parent;
+      if (p >= 0) r = roundOf[p] + 1;
+      // an object may later hang on any dynamic node: schedule it after everything that is not below it
+      if (H.dyn[n].kind == AFFK_NODE_OBJECT) for (int k = 0; k < n; ++k) if (!H.dyn[k].under_obj) r = std::max(r, roundOf[k] + 1);
+      while (true) {
+        if ((int)fill.size() <= r) fill.resize(r + 1, 0);
+        if (fill[r] < 2) break;
+        ++r;
+      }
+      roundOf[n] = r; fill[r]++;
+    }
+    const int nR = (int)fill.size();
+    if (nR > AFFK_MAX_ROUNDS) { err = "FK schedule too deep"; return AFF_ERR_CAPACITY; }
+    H.rounds.assign(2 * (size_t)nR, -1);
+    std::vector<int> used(nR, 0);
+    for (int n = 0; n < nD; ++n) { const int r = roundOf[n]; H.rounds[2 * r + used[r]++] = n; }
+    P.nRounds = nR;
+  }
+  // objects below objects (a connect parent under another object) would need a dynamic schedule
+  for (int b : objBodies) if (S.parent[b] >= 0 && underObj[S.parent[b]]) { err = "objects nested in objects are not supported"; return AFF_ERR_UNSUPPORTED; }
+
+  // ---- shapes
+  auto addShapes = [&](int b, bool dynamicSide) {
+    KShapeBody sb; std::memset(&sb, 0, sizeof(sb));
+    sb.body = b; sb.node = bodyRef[b]; sb.explicit_bp = S.explicitBp[b];
+    sb.obj_slot = underObj[b]; sb.toggle_slot = objSlotOfBody[b] >= 0 ? objSlotOfBody[b] + 1 : 0;
+    sb.tree = underObj[b] ? -1 : treeB[b];
+    std::vector<KShape>& dst = dynamicSide ? H.dshape : H.sshape;
+    sb.first_shape = (int)dst.size();
+    for (int k = 0; k < S.nShapes[b]; ++k) {
+      const int s = S.firstShape[b] + k;
+      if (!S.sdist[s] && !sb.toggle_slot) continue;   // can never become active
+      KShape sh; std::memset(&sh, 0, sizeof(sh));
+      sh.type = S.stype[s]; sh.active0 = S.sdist[s]; sh.node = bodyRef[b];
+      std::memcpy(sh.ext, &S.ext[3 * s], sizeof(double) * 3);
+      std::memcpy(sh.A_CB, &S.A_CB[12 * s], sizeof(double) * 12);
+      if (sh.active0) sb.any_active0 = 1;
+      dst.push_back(sh);
+    }
+    sb.n_shapes = (int)dst.size() - sb.first_shape;
+    if (sb.n_shapes > 0) (dynamicSide ? H.dbody : H.sbody).push_back(sb);
+  };
+  for (int b = 0; b < nB; ++b) if (shapeBody[b]) addShapes(b, dynamicB[b] != 0);
+  if ((int)H.dshape.size() > AFFK_MAX_DSHAPE || (int)H.dbody.size() > AFFK_MAX_DBODY) { err = "too many dynamic shapes"; return AFF_ERR_CAPACITY; }
+  for (size_t i = 0; i < H.dbody.size(); ++i) {
+    const KShapeBody& a = H.dbody[i];
+    const bool aTree = a.tree >= 0 || a.obj_slot;
+    for (size_t j = i + 1; j < H.dbody.size(); ++j) {
+      const KShapeBody& b = H.dbody[j];
+      const bool bTree = b.tree >= 0 || b.obj_slot;
+      if (!aTree && !bTree) continue;
+      if (a.tree >= 0 && b.tree >= 0 && a.tree == b.tree && !a.obj_slot && !b.obj_slot) continue;
+      H.always.push_back((int)i); H.always.push_back((int)j);
+    }
+    if (aTree) for (size_t j = 0; j < H.sbody.size(); ++j) if (H.sbody[j].explicit_bp) { H.always.push_back((int)i); H.always.push_back(-1 - (int)j); }
+  }
+
+  // ---- joints (jacobi order)
+  for (int c = 0; c < S.nJ; ++c) {
+    const int j = S.ikJoint[c];
+    H.jq_init.push_back(S.qInit[j]); H.jq0.push_back(S.q0[j]); H.jq_min.push_back(S.qMin[j]); H.jq_max.push_back(S.qMax[j]);
+    H.jspeed.push_back(S.speed[j]); H.jacc.push_back(S.acc[j]); H.jwjl.push_back(S.wjl[j]); H.jwmetric.push_back(S.wmetric[j]);
+  }
+  for (int s = 0; s < nObj; ++s) {
+    const int b = objBodies[s];
+    H.obj_node.push_back(bodyRef[b]); H.obj_body.push_back(b);
+    for (int k = 0; k < 6; ++k) H.obj_q6.push_back(S.qInit[S.firstJoint[b] + k]);
+  }
+
+  // ---- tasks
+  H.tasks.resize(nTasksIn);
+  for (size_t i = 0; i < nTasksIn; ++i) {
+    const aff_task_desc& t = tasksIn[i];
+    KTask& k = H.tasks[i];
+    std::memset(&k, 0, sizeof(k));
+    if (t.kind < AFF_TASK_XYZ || t.kind > AFF_TASK_JOINTS) { err = "unsupported task kind"; return AFF_ERR_UNSUPPORTED; }
+    k.kind = t.kind; k.axis = (t.axis >= 0 && t.axis < 3) ? t.axis : 2;
+    k.eff = t.effector >= 0 ? bodyRef[t.effector] : AFFK_WORLD;
+    k.ref = t.ref_body >= 0 ? bodyRef[t.ref_body] : AFFK_WORLD;
+    k.frame = (t.ref_frame == -2) ? AFFK_WORLD : (t.ref_frame >= 0 ? bodyRef[t.ref_frame] : k.ref);
+    if (t.kind != AFF_TASK_JOINTS && t.effector < 0) { err = "task without effector"; return AFF_ERR_INVALID; }
+    // a reference to the world origin itself cannot be told apart from "no reference": forbid bodies aliased to world
+    if (t.kind == AFF_TASK_JOINTS) {
+      if (t.n_joints < 0 || t.n_joints > AFF_MAX_TASK_JOINTS) { err = "bad joint count in Joints task"; return AFF_ERR_INVALID; }
+      k.n_joints = t.n_joints;
+      for (int q = 0; q < t.n_joints; ++q) {
+        const int j = t.joints[q];
+        if (j < 0 || j >= S.nQ) { err = "Joints task names a joint outside the scene"; return AFF_ERR_INVALID; }
+        k.jidx[q] = S.jacobi[j] >= 0 ? S.jacobi[j] : -1;
+        k.jconst[q] = S.qInit[j];
+      }
+    }
+    k.has_region = t.has_region; k.region_min = t.region_min; k.region_max = t.region_max; k.region_dx_scaling = t.region_dx_scaling;
+  }
+
+  // ---- candidates
+  H.cands.resize(nCands);
+  H.vias.reserve(nConsIn); H.acts.reserve(nConsIn);
+  std::vector<std::pair<int, int>> order;   // (sort key, constraint index)
+  for (size_t i = 0; i < nCands; ++i) {
+    const aff_candidate& c = candsIn[i];
+    KCand& kc = H.cands[i];
+    std::memset(&kc, 0, sizeof(kc));
+    if (c.n_tasks > AFFK_MAX_TASKS) { err = "too many tasks in one candidate"; return AFF_ERR_CAPACITY; }
+    kc.first_task = c.first_task; kc.n_tasks = c.n_tasks;
+    int xdim = 0;
+    int toff[AFFK_MAX_TASKS + 1];
+    for (int t = 0; t < c.n_tasks; ++t) {
+      KTask& k = H.tasks[c.first_task + t];
+      k.xoff = xdim; toff[t] = xdim;
+      xdim += (k.kind == AFF_TASK_XYZ) ? 3 : (k.kind == AFF_TASK_POLAR ? 2 : (k.kind == AFF_TASK_JOINTS ? k.n_joints : 1));
+    }
+    toff[c.n_tasks] = xdim;
+    if (xdim > AFFK_MAX_XDIM) { err = "candidate has more than AFFK_MAX_XDIM task dimensions"; return AFF_ERR_CAPACITY; }
+    kc.xdim = xdim;
+    H.maxXdim = std::max(H.maxXdim, xdim);
+    const aff_constraint* cc = consIn + c.first_constraint;
+    double endT = 0.0, startT = 1.0e308;
+    for (int k = 0; k < c.n_constraints; ++k) { if (cc[k].t > endT) endT = cc[k].t; if (cc[k].t < startT) startT = cc[k].t; }
+    kc.end_abs = endT;
+    kc.start_abs = (c.n_constraints == 0) ? 0.0 : (startT < 0.0 ? 0.0 : startT);
+    kc.n_steps = (int)std::lround(endT / opts.dt) + opts.n_after_steps;
+    H.maxSteps = std::max(H.maxSteps, kc.n_steps);
+    // vias by (dimension, time), stable in insertion order
+    kc.first_via = (int)H.vias.size();
+    int unknowns[AFFK_MAX_XDIM];
+    for (int d = 0; d < xdim; ++d) unknowns[d] = 0;
+    order.clear();
+    for (int k = 0; k < c.n_constraints; ++k) {
+      if (cc[k].kind != AFF_CON_VIA) continue;
+      if (cc[k].task < 0 || cc[k].task >= c.n_tasks || cc[k].dim < 0 || toff[cc[k].task] + cc[k].dim >= toff[cc[k].task + 1]) {
+        err = "via point outside its task"; return AFF_ERR_INVALID;
+      }
+      order.emplace_back(toff[cc[k].task] + cc[k].dim, k);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+      if (a.first != b.first) return a.first < b.first;
+      return cc[a.second].t < cc[b.second].t;
+    });
+    {
+      size_t oi = 0;
+      for (int d = 0; d <= xdim; ++d) {
+        kc.via_off[d] = (int)(H.vias.size() - kc.first_via);
+        while (d < xdim && oi < order.size() && order[oi].first == d) {
+          const aff_constraint& v = cc[order[oi].second];
+          KVia kv; kv.t = v.t; kv.x = v.x; kv.xd = v.xd; kv.xdd = v.xdd; kv.flag = v.flag & 7; kv.pad = 0;
+          unknowns[d] += popcount3(kv.flag);
+          H.vias.push_back(kv);
+          ++oi;
+        }
+      }
+    }
+    for (int d = 0; d < xdim; ++d) if (unknowns[d] > AFFK_MAX_VIA_UNK) { err = "a trajectory has more than 6 constrained values"; return AFF_ERR_CAPACITY; }
+    // activations by (task, time)
+    kc.first_act = (int)H.acts.size();
+    order.clear();
+    for (int k = 0; k < c.n_constraints; ++k) {
+      if (cc[k].kind != AFF_CON_ACTIVATION) continue;
+      if (cc[k].task < 0 || cc[k].task >= c.n_tasks) { err = "activation outside the task list"; return AFF_ERR_INVALID; }
+      order.emplace_back(cc[k].task, k);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+      if (a.first != b.first) return a.first < b.first;
+      return cc[a.second].t < cc[b.second].t;
+    });
+    {
+      size_t oi = 0;
+      for (int t = 0; t <= c.n_tasks; ++t) {
+        kc.act_off[t] = (int)(H.acts.size() - kc.first_act);
+        while (t < c.n_tasks && oi < order.size() && order[oi].first == t) {
+          const aff_constraint& a = cc[order[oi].second];
+          KAct ka; ka.t = a.t; ka.horizon = a.horizon; ka.on = a.flag ? 1 : 0; ka.pad = 0;
+          H.acts.push_back(ka);
+          ++oi;
+        }
+      }
+    }
+    // graph constraints in list order
+    kc.first_gcon = (int)H.gcons.size();
+    for (int k = 0; k < c.n_constraints; ++k) {
+      if (cc[k].kind != AFF_CON_CONNECT && cc[k].kind != AFF_CON_COLLISION) continue;
+      KGraphCon g; g.t = cc[k].t; g.kind = cc[k].kind; g.on = cc[k].flag ? 1 : 0; g.slot = objSlotOfBody[cc[k].body_a];
+      g.parent = (cc[k].kind == AFF_CON_CONNECT) ? bodyRef[cc[k].body_b] : AFFK_WORLD;
+      if (cc[k].kind == AFF_CON_CONNECT && cc[k].body_b >= 0 && underObj[cc[k].body_b] == g.slot + 1) { err = "connect onto the object's own subtree"; return AFF_ERR_INVALID; }
+      H.gcons.push_back(g);
+    }
+    kc.n_gcon = (int)H.gcons.size() - kc.first_gcon;
+    if (kc.n_gcon > 32) { err = "more than 32 graph constraints in one candidate"; return AFF_ERR_CAPACITY; }
+    kc.pose_slot = c.pose_body >= 0 ? objSlotOfBody[c.pose_body] : -1;
+    for (int k = 0; k < 6; ++k) kc.pose_q6[k] = c.pose_q6[k];
+  }
+
+  // ---- scalars
+  P.nJ = S.nJ; P.nDyn = (int)H.dyn.size(); P.nStatic = (int)H.stat.size(); P.nObj = nObj;
+  P.nDynShapes = (int)H.dshape.size(); P.nDynBodies = (int)H.dbody.size();
+  P.nStatShapes = (int)H.sshape.size(); P.nStatBodies = (int)H.sbody.size();
+  P.nTrees = (int)S.bpTree.size(); P.nAlways = (int)H.always.size() / 2;
+  auto refOf = [&](int b) { return b >= 0 ? bodyRef[b] : AFFK_WORLD; };
+  P.ns_base = refOf(S.ns_base);
+  for (int k = 0; k < 2; ++k) { P.ns_upperarm[k] = refOf(S.ns_upperarm[k]); P.ns_forearm[k] = refOf(S.ns_forearm[k]); P.ns_hand[k] = refOf(S.ns_hand[k]); }
+  P.rbj_static_chain = rbjStatic;
+  P.bp_threshold = S.bpThreshold;
+  P.nCands = (int)nCands;
+  P.opts = opts;
+
+  // ---- shared-memory layout (doubles)
+  int o = 0;
+  auto take = [&](int n) { const int at = o; o += n; return at; };
+  P.o_node = take(12 * std::max(P.nDyn, 1));
+  P.o_q = take(32); P.o_qdot = take(32); P.o_dH = take(32); P.o_dq = take(32); P.o_sn = take(32); P.o_cs = take(32);
+  P.o_dx = take(AFFK_MAX_XDIM);
+  P.o_st = take(3 * std::max(H.maxXdim, 1));
+  P.o_xdes = take(AFFK_MAX_XDIM); P.o_xcur = take(AFFK_MAX_XDIM);
+  P.o_geo = take(12 * AFFK_MAX_TASKS);
+  P.o_objrel = take(12 * AFFK_MAX_OBJ); P.o_objq6 = take(6 * AFFK_MAX_OBJ);
+  // union region: trajectory solver scratch | J, L, rhs | collision scratch
+  const int uBase = o;
+  P.JS = (S.nJ | 1); P.LS = (H.maxXdim | 1);
+  const int uTraj = AFFK_VIA_STRIDE * std::max(H.maxXdim, 1);
+  const int mRows = std::max(H.maxXdim, 1);
+  const int uIk = mRows * P.JS + mRows * P.LS + mRows;
+  const int uColl = 12 * std::max(P.nDynShapes, 1) + 6 * std::max(P.nDynBodies, 1) + 6 * std::max(P.nTrees, 1) + AFFK_MAX_LIVE;
+  P.o_scratch = uBase;
+  P.o_J = uBase; P.o_L = uBase + mRows * P.JS; P.o_rhs = P.o_L + mRows * P.LS;
+  P.o_shp = uBase; P.o_baabb = P.o_shp + 12 * std::max(P.nDynShapes, 1); P.o_taabb = P.o_baabb + 6 * std::max(P.nDynBodies, 1);
+  P.o_live = P.o_taabb + 6 * std::max(P.nTrees, 1);
+  o = uBase + std::max(uTraj, std::max(uIk, uColl));
+  P.warp_doubles = (o + 1) & ~1;
+  H.smemBytesPerWarp = sizeof(double) * (size_t)P.warp_doubles;
+  return AFF_OK;
+}
+
+}   // namespace affk

@@ -1,0 +1,1340 @@
+// One candidate rollout on one warp: the whole of
+//   TrajectoryPredictor::predict     (reference src/TrajectoryPredictor.cpp:79-406)
+//   TrajectoryPredictor::computeIK   (:573-753)
+//   TrajectoryPredictor::checkState  (:756-886)
+// fused into a single step loop whose state lives in shared memory.
+//
+// Lane mapping per phase (32 lanes):
+//   trajectories ...... one lane per task dimension (1-D via-point polynomial)
+//   task values / dx .. one lane per task
+//   Jacobians, dH, dq . one lane per IK joint (column of J)
+//   J W^-1 J^T ........ one lane per matrix entry; Cholesky one lane per row
+//   forward kinematics  12 lanes per node (one per HTr element), two nodes per round
+//   collision model ... one lane per shape / body pair
+// Every floating-point expression is written in the order the CPU checker uses
+// (explicit fma(), compiled with -fmad=false), and the few reductions over
+// lanes are order-independent (min / max / ballot) or use the fixed butterfly
+// order of w_tree_sum(), so results are reproducible bit for bit.
+#ifndef AFF_KERNEL_ROLLOUT_CUH
+#define AFF_KERNEL_ROLLOUT_CUH
+
+#include <float.h>
+#include <math.h>
+
+#include "aff_detmath.h"
+#include "plan.h"
+#include "warp.cuh"
+
+#define AFFK_TRACK_MAX 0.05      // MAX_TRACKING_ERROR, src/TrajectoryPredictor.cpp:50
+#define AFFK_TRAJ_EPS 1.0e-8
+#define AFFK_HORIZON 1.0         // src/ActionBase.cpp:137
+#define AFFK_NO_LIMIT 1.0e300
+#define AFFK_GOLDEN_ITERS 48
+
+// ------------------------------------------------------------ small algebra
+AFF_DEV void k_cross(double* o, const double* a, const double* b)
+{
+  o[0] = fma(a[1], b[2], -(a[2] * b[1]));
+  o[1] = fma(a[2], b[0], -(a[0] * b[2]));
+  o[2] = fma(a[0], b[1], -(a[1] * b[0]));
+}
+AFF_DEV double k_dot(const double* a, const double* b) { return fma(a[2], b[2], fma(a[1], b[1], a[0] * b[0])); }
+// o = R v, R = 9 doubles row-major
+AFF_DEV void k_mulv(double* o, const double* R, const double* v)
+{
+  for (int i = 0; i < 3; ++i) o[i] = fma(R[3 * i + 2], v[2], fma(R[3 * i + 1], v[1], R[3 * i] * v[0]));
+}
+AFF_DEV double k_clip(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+AFF_DEV double k_clamp01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
+
+// element e (0..2 org, 3..11 rot) of T o P
+AFF_DEV double k_compose_elem(const double* T, const double* P, int e)
+{
+  if (e < 3) return fma(P[3 + 6 + e], T[2], fma(P[3 + 3 + e], T[1], fma(P[3 + e], T[0], P[e])));
+  const int i = (e - 3) / 3, j = (e - 3) % 3;
+  return fma(T[3 + 3 * i + 2], P[3 + 6 + j], fma(T[3 + 3 * i + 1], P[3 + 3 + j], T[3 + 3 * i] * P[3 + j]));
+}
+
+// Serial versions used for rare per-node work (object nodes, prologue).
+AFF_DEV void k_compose(double* out, const double* T, const double* P)
+{
+  double r[12];
+  for (int e = 0; e < 12; ++e) r[e] = k_compose_elem(T, P, e);
+  for (int e = 0; e < 12; ++e) out[e] = r[e];
+}
+AFF_DEV void k_apply_joint(double* A, int type, double q)
+{
+  if (type < AFF_JNT_ROT_X) {
+    for (int k = 0; k < 3; ++k) A[k] = fma(q, A[3 + 3 * type + k], A[k]);
+  } else {
+    const int d = type - AFF_JNT_ROT_X, a = (d + 1) % 3, b = (d + 2) % 3;
+    double s, c;
+    aff_sincos(q, &s, &c);
+    for (int k = 0; k < 3; ++k) {
+      const double ra = A[3 + 3 * a + k], rb = A[3 + 3 * b + k];
+      A[3 + 3 * a + k] = fma(s, rb, c * ra);
+      A[3 + 3 * b + k] = fma(c, rb, -(s * ra));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ context
+struct KCtx
+{
+  const KPlan* P;
+  const KCand* C;
+  double* sm;        // warp base in shared memory
+  int lane;
+  // re-parentable objects (warp-uniform)
+  int objParent[AFFK_MAX_OBJ];
+  unsigned objChain[AFFK_MAX_OBJ];
+  int objTree[AFFK_MAX_OBJ];
+  int objMode[AFFK_MAX_OBJ];    // 0 per-shape flags, 1 all on, 2 all off
+  unsigned objHasRel;
+};
+
+AFF_DEV double* k_node(const KCtx& c, int n) { return c.sm + c.P->o_node + 12 * n; }
+AFF_DEV const double* k_ref(const KCtx& c, int ref)
+{
+  if (ref >= 0) return c.sm + c.P->o_node + 12 * ref;
+  if (ref == AFFK_WORLD) return c.P->statA + 12 * c.P->nStatic;   // identity slot
+  return c.P->statA + 12 * AFFK_STATIC_IDX(ref);
+}
+AFF_DEV unsigned k_chain(const KCtx& c, int ref)
+{
+  if (ref < 0) return 0u;
+  const KNode* n = c.P->dyn + ref;
+  unsigned m = ldg(&n->chain);
+  const int uo = ldg(&n->under_obj);
+  if (uo) m |= c.objChain[uo - 1];
+  return m;
+}
+AFF_DEV int k_tree_of_node(const KCtx& c, int ref)
+{
+  if (ref < 0) return -1;
+  const KNode* n = c.P->dyn + ref;
+  const int uo = ldg(&n->under_obj);
+  return uo ? c.objTree[uo - 1] : ldg(&n->tree);
+}
+
+// Jacobian columns of this lane's IK joint for a point p fixed to node `ref`.
+struct KJointFrame { double ax[3]; double org[3]; int type; int valid; };
+
+AFF_DEV void k_jac_cols(const KCtx& c, const KJointFrame& jf, int ref, const double* p, double* colT, double* colR)
+{
+  colT[0] = colT[1] = colT[2] = 0.0;
+  colR[0] = colR[1] = colR[2] = 0.0;
+  if (!jf.valid || !((k_chain(c, ref) >> c.lane) & 1u)) return;
+  if (jf.type < AFF_JNT_ROT_X) { colT[0] = jf.ax[0]; colT[1] = jf.ax[1]; colT[2] = jf.ax[2]; }
+  else {
+    double r[3];
+    for (int k = 0; k < 3; ++k) r[k] = p[k] - jf.org[k];
+    k_cross(colT, jf.ax, r);
+    colR[0] = jf.ax[0]; colR[1] = jf.ax[1]; colR[2] = jf.ax[2];
+  }
+}
+
+// ------------------------------------------------------- forward kinematics
+// Pose of an object node that still hangs on its six rigid-body joints.
+AFF_DEV void k_object_from_q6(const KCtx& c, int n, int slot)
+{
+  double A[12];
+  const double* Pp = k_ref(c, c.objParent[slot]);
+  for (int e = 0; e < 12; ++e) A[e] = Pp[e];
+  const double* q6 = c.sm + c.P->o_objq6 + 6 * slot;
+  for (int k = 0; k < 6; ++k) k_apply_joint(A, k, q6[k]);
+  double* out = k_node(c, n);
+  for (int e = 0; e < 12; ++e) out[e] = A[e];
+}
+
+// RcsGraph_setState for the dynamic nodes. `all` = also nodes that only change
+// at initialisation (objects resting on static parents).
+AFF_DEV void k_fk(const KCtx& c, bool init)
+{
+  const KPlan& P = *c.P;
+  double* sn = c.sm + P.o_sn; double* cs = c.sm + P.o_cs;
+  const double* q = c.sm + P.o_q;
+  if (c.lane < P.nJ) { double s, co; aff_sincos(q[c.lane], &s, &co); sn[c.lane] = s; cs[c.lane] = co; }
+  w_sync();
+  const int grp = c.lane / 12, e = c.lane % 12;
+  for (int r = 0; r < P.nRounds; ++r) {
+    const int n = (grp < 2) ? ldg(&P.rounds[2 * r + grp]) : -1;
+    double val = 0.0;
+    int kind = -1, jtype = 0, partner = c.lane, isA = 0, isB = 0;
+    double s = 0.0, co = 1.0, qv = 0.0;
+    bool skip = true;
+    if (n >= 0) {
+      const KNode* nd = P.dyn + n;
+      kind = ldg(&nd->kind);
+      if (kind == AFFK_NODE_OBJECT) {
+        const int slot = ldg(&nd->qidx);
+        if ((c.objHasRel >> slot) & 1u) {
+          val = k_compose_elem(c.sm + P.o_objrel + 12 * slot, k_ref(c, c.objParent[slot]), e);
+          skip = false;
+        } else if (init || c.objParent[slot] >= 0) {
+          if (e == 0) k_object_from_q6(c, n, slot);
+        }
+      } else {
+        const double* Pp = k_ref(c, ldg(&nd->parent));
+        val = ldg(&nd->identityT) ? Pp[e] : k_compose_elem(nd->T, Pp, e);
+        skip = false;
+        if (kind == AFFK_NODE_JOINT_IK || kind == AFFK_NODE_JOINT_CONST) {
+          jtype = ldg(&nd->jtype);
+          if (kind == AFFK_NODE_JOINT_IK) { const int qi = ldg(&nd->qidx); s = sn[qi]; co = cs[qi]; qv = q[qi]; }
+          else { s = ldg(&P.dynSC[2 * n]); co = ldg(&P.dynSC[2 * n + 1]); qv = ldg(&nd->qconst); }
+          if (jtype >= AFF_JNT_ROT_X && e >= 3) {
+            const int d = jtype - AFF_JNT_ROT_X, a = (d + 1) % 3, b = (d + 2) % 3;
+            const int row = (e - 3) / 3, col = (e - 3) % 3;
+            if (row == a) { isA = 1; partner = grp * 12 + 3 + 3 * b + col; }
+            else if (row == b) { isB = 1; partner = grp * 12 + 3 + 3 * a + col; }
+          } else if (jtype < AFF_JNT_ROT_X && e < 3) {
+            partner = grp * 12 + 3 + 3 * jtype + e;   // axis component for the translation
+          }
+        }
+      }
+    }
+    const double other = w_shfl(val, partner);
+    if (!skip) {
+      if (kind == AFFK_NODE_JOINT_IK || kind == AFFK_NODE_JOINT_CONST) {
+        if (jtype >= AFF_JNT_ROT_X) {
+          if (isA) val = fma(s, other, co * val);            // ra' = c ra + s rb
+          else if (isB) val = fma(co, val, -(s * other));    // rb' = c rb - s ra
+        } else if (e < 3) {
+          val = fma(qv, other, val);
+        }
+      }
+      k_node(c, n)[e] = val;
+    }
+    w_sync();
+  }
+}
+
+// ------------------------------------------------------------ via-point step
+// One receding-horizon step of a 1-D via-point trajectory (the oracle's
+// oracle_via_step): window selection, reduced polynomial system, evaluation.
+AFF_DEV void k_via_step(double* st, const KVia* vias, int n, double tnow, double dt, double* A)
+{
+  if (n <= 0) { st[1] = 0.0; st[2] = 0.0; return; }
+  int G = -1, lastFull = -1;
+  for (int i = 0; i < n; ++i) {
+    if (ldg(&vias[i].flag) == 7) { lastFull = i; if (ldg(&vias[i].t) - tnow >= AFFK_HORIZON) { G = i; break; } }
+  }
+  if (G < 0) G = (lastFull >= 0) ? lastFull : n - 1;
+  int K = 0, nwin = 0;
+  for (int i = 0; i <= G; ++i) {
+    const int flag = ldg(&vias[i].flag);
+    const int add = (flag & 1) + ((flag >> 1) & 1) + ((flag >> 2) & 1);
+    if (K + add > AFFK_MAX_VIA_UNK) break;
+    K += add; nwin = i + 1;
+  }
+  if (K == 0) { st[1] = 0.0; st[2] = 0.0; return; }
+  const double T = ldg(&vias[nwin - 1].t) - tnow;
+  const double c0 = st[0], c1 = st[1] * T, c2 = (0.5 * st[2]) * (T * T);
+  const int S = K + 1;
+  int row = 0;
+  for (int i = 0; i < nwin; ++i) {
+    const int flag = ldg(&vias[i].flag);
+    const double tau = (ldg(&vias[i].t) - tnow) / T;
+    const double pw1 = 1.0 * tau, pw2 = pw1 * tau;
+    if (flag & 1) {
+      double p = pw2;
+      for (int k = 0; k < K; ++k) { p = p * tau; A[row * S + k] = p; }
+      A[row * S + K] = ldg(&vias[i].x) - fma(c2, pw2, fma(c1, tau, c0));
+      ++row;
+    }
+    if (flag & 2) {
+      double p = pw1;
+      for (int k = 0; k < K; ++k) { p = p * tau; A[row * S + k] = (double)(k + 3) * p; }
+      A[row * S + K] = ldg(&vias[i].xd) * T - fma(2.0 * c2, tau, c1);
+      ++row;
+    }
+    if (flag & 4) {
+      double p = 1.0;
+      for (int k = 0; k < K; ++k) { p = p * tau; A[row * S + k] = (double)((k + 3) * (k + 2)) * p; }
+      A[row * S + K] = ldg(&vias[i].xdd) * (T * T) - 2.0 * c2;
+      ++row;
+    }
+  }
+  // Gaussian elimination, partial pivoting, first maximal pivot
+  for (int cI = 0; cI < K; ++cI) {
+    int piv = cI;
+    double best = fabs(A[cI * S + cI]);
+    for (int r = cI + 1; r < K; ++r) { const double v = fabs(A[r * S + cI]); if (v > best) { best = v; piv = r; } }
+    if (piv != cI) for (int k = cI; k < S; ++k) { const double tmp = A[cI * S + k]; A[cI * S + k] = A[piv * S + k]; A[piv * S + k] = tmp; }
+    const double p = A[cI * S + cI];
+    if (p == 0.0) continue;
+    for (int r = cI + 1; r < K; ++r) {
+      const double f = A[r * S + cI] / p;
+      for (int k = cI + 1; k < S; ++k) A[r * S + k] = fma(-f, A[cI * S + k], A[r * S + k]);
+    }
+  }
+  double* sol = A + AFFK_MAX_VIA_UNK * (AFFK_MAX_VIA_UNK + 1);   // AFFK_MAX_VIA_UNK doubles after the matrix
+  for (int r = K - 1; r >= 0; --r) {
+    double sacc = A[r * S + K];
+    for (int k = r + 1; k < K; ++k) sacc = fma(-A[r * S + k], sol[k], sacc);
+    const double p = A[r * S + r];
+    sol[r] = (p != 0.0) ? sacc / p : 0.0;
+  }
+  const double s = (dt < T) ? dt / T : 1.0;
+  double p = 0.0, pd = 0.0, pdd = 0.0;
+  for (int k = K - 1; k >= 0; --k) {
+    const int deg = k + 3;
+    p = fma(p, s, sol[k]);
+    pd = fma(pd, s, (double)deg * sol[k]);
+    pdd = fma(pdd, s, (double)(deg * (deg - 1)) * sol[k]);
+  }
+  const double s2 = s * s, s3 = s2 * s;
+  st[0] = fma(p, s3, fma(c2, s2, fma(c1, s, c0)));
+  st[1] = fma(pd, s2, fma(2.0 * c2, s, c1)) / T;
+  st[2] = fma(pdd, s, 2.0 * c2) / (T * T);
+}
+
+// ----------------------------------------------------------- task geometry
+// Per task t (one lane each), from the current node transforms:
+//   geo[t][0..11] kind-specific vectors, xcur[xoff..] = Task::computeX.
+// XYZ/X/Y/Z : 0-2 pe, 3-5 pr, 6-8 r12
+// POLAR     : 0-2 a (axis in ref frame), 3-5 e1, 6-8 e2, 9-11 pe
+// INCLINATION: 0-2 u, 3-5 v, 6-8 n (unit, or zero), 9-11 pe
+#define AFFK_GEO 12
+
+AFF_DEV void k_tangent_basis(const double* a, double* e1, double* e2)
+{
+  int k = 0;
+  double m = fabs(a[0]);
+  if (fabs(a[1]) < m) { k = 1; m = fabs(a[1]); }
+  if (fabs(a[2]) < m) { k = 2; }
+  double t[3];
+  for (int i = 0; i < 3; ++i) t[i] = -(a[k] * a[i]);
+  t[k] = t[k] + 1.0;
+  const double n = sqrt(k_dot(t, t));
+  for (int i = 0; i < 3; ++i) e1[i] = t[i] / n;
+  k_cross(e2, a, e1);
+}
+
+AFF_DEV void k_task_geo(const KCtx& c, const KTask* tk, double* geo, double* xcur)
+{
+  const int kind = ldg(&tk->kind), eff = ldg(&tk->eff), ref = ldg(&tk->ref), frame = ldg(&tk->frame), axis = ldg(&tk->axis);
+  const int xoff = ldg(&tk->xoff);
+  if (kind <= AFF_TASK_Z) {
+    const double* Ae = k_ref(c, eff);
+    double r[3], xr[3];
+    for (int k = 0; k < 3; ++k) {
+      geo[k] = Ae[k];
+      const double prk = (ref != AFFK_WORLD) ? k_ref(c, ref)[k] : 0.0;
+      geo[3 + k] = prk;
+      r[k] = (ref != AFFK_WORLD) ? Ae[k] - prk : Ae[k];
+      geo[6 + k] = r[k];
+    }
+    if (frame != AFFK_WORLD) k_mulv(xr, k_ref(c, frame) + 3, r);
+    else { xr[0] = r[0]; xr[1] = r[1]; xr[2] = r[2]; }
+    if (kind == AFF_TASK_XYZ) { xcur[xoff] = xr[0]; xcur[xoff + 1] = xr[1]; xcur[xoff + 2] = xr[2]; }
+    else xcur[xoff] = xr[kind - AFF_TASK_X];
+  } else if (kind == AFF_TASK_POLAR) {
+    const double* Ae = k_ref(c, eff);
+    const double* aI = Ae + 3 + 3 * axis;
+    double a[3], e1[3], e2[3];
+    if (ref != AFFK_WORLD) k_mulv(a, k_ref(c, ref) + 3, aI);
+    else { a[0] = aI[0]; a[1] = aI[1]; a[2] = aI[2]; }
+    k_tangent_basis(a, e1, e2);
+    for (int k = 0; k < 3; ++k) { geo[k] = a[k]; geo[3 + k] = e1[k]; geo[6 + k] = e2[k]; geo[9 + k] = Ae[k]; }
+    xcur[xoff] = aff_acos(a[2]);
+    xcur[xoff + 1] = aff_atan2(a[1], a[0]);
+  } else if (kind == AFF_TASK_INCLINATION) {
+    const double* Ae = k_ref(c, eff);
+    const double* aI = Ae + 3 + 3 * axis;
+    double u[3], v[3], n[3];
+    for (int k = 0; k < 3; ++k) u[k] = aI[k];
+    if (ref != AFFK_WORLD) { const double* z = k_ref(c, ref) + 3 + 6; v[0] = z[0]; v[1] = z[1]; v[2] = z[2]; }
+    else { v[0] = 0.0; v[1] = 0.0; v[2] = 1.0; }
+    k_cross(n, v, u);
+    const double sn = sqrt(k_dot(n, n));
+    if (sn > 1.0e-8) { for (int k = 0; k < 3; ++k) n[k] = n[k] / sn; }
+    else { n[0] = n[1] = n[2] = 0.0; }
+    for (int k = 0; k < 3; ++k) { geo[k] = u[k]; geo[3 + k] = v[k]; geo[6 + k] = n[k]; geo[9 + k] = Ae[k]; }
+    xcur[xoff] = aff_acos(k_dot(u, v));
+  } else {   // JOINTS
+    const int nj = ldg(&tk->n_joints);
+    const double* q = c.sm + c.P->o_q;
+    for (int i = 0; i < nj; ++i) {
+      const int ji = ldg(&tk->jidx[i]);
+      xcur[xoff + i] = (ji >= 0) ? q[ji] : ldg(&tk->jconst[i]);
+    }
+  }
+}
+
+AFF_DEV double k_region_dx(const KTask* tk, double e)
+{
+  if (!ldg(&tk->has_region)) return e;
+  const double off = -e;
+  const double rmax = ldg(&tk->region_max), rmin = ldg(&tk->region_min);
+  if (off > rmax) return e + rmax;
+  if (off < rmin) return e + rmin;
+  return ldg(&tk->region_dx_scaling) * e;
+}
+
+// Task::computeDX towards xdes, from geo / xcur of the current state.
+AFF_DEV void k_task_dx(const KTask* tk, const double* geo, const double* xcur, const double* xdes, double* dx)
+{
+  const int kind = ldg(&tk->kind), xoff = ldg(&tk->xoff);
+  if (kind == AFF_TASK_POLAR) {
+    const double* a = geo; const double* e1 = geo + 3; const double* e2 = geo + 6;
+    double ad[3], n[3], w[3], sp, cp, st, ct;
+    aff_sincos(xdes[xoff], &sp, &cp);
+    aff_sincos(xdes[xoff + 1], &st, &ct);
+    ad[0] = sp * ct; ad[1] = sp * st; ad[2] = cp;
+    k_cross(n, a, ad);
+    const double s = sqrt(k_dot(n, n));
+    const double cc = k_dot(a, ad);
+    const double ang = aff_atan2(s, cc);
+    if (s > 1.0e-12) { const double f = ang / s; for (int k = 0; k < 3; ++k) w[k] = n[k] * f; }
+    else { w[0] = w[1] = w[2] = 0.0; }
+    dx[0] = k_dot(e1, w);
+    dx[1] = k_dot(e2, w);
+    return;
+  }
+  const int dim = (kind == AFF_TASK_XYZ) ? 3 : ((kind == AFF_TASK_JOINTS) ? ldg(&tk->n_joints) : 1);
+  for (int i = 0; i < dim; ++i) dx[i] = k_region_dx(tk, xdes[xoff + i] - xcur[xoff + i]);
+}
+
+AFF_DEV int k_task_dim(const KTask* tk)
+{
+  const int kind = ldg(&tk->kind);
+  if (kind == AFF_TASK_XYZ) return 3;
+  if (kind == AFF_TASK_POLAR) return 2;
+  if (kind == AFF_TASK_JOINTS) return ldg(&tk->n_joints);
+  return 1;
+}
+
+// Rows of task tk in column `lane` of J (Task::computeJ).
+AFF_DEV void k_task_J(const KCtx& c, const KJointFrame& jf, const KTask* tk, const double* geo, double* Jrow0, int Jstride)
+{
+  const int kind = ldg(&tk->kind), eff = ldg(&tk->eff), ref = ldg(&tk->ref), frame = ldg(&tk->frame);
+  const int col = c.lane;
+  if (kind <= AFF_TASK_Z) {
+    double te[3], re[3], tr[3], rr[3], tf[3], rf[3], cr[3], cl[3], out[3];
+    const double zero[3] = {0.0, 0.0, 0.0};
+    k_jac_cols(c, jf, eff, geo, te, re);
+    k_jac_cols(c, jf, ref, geo + 3, tr, rr);
+    k_jac_cols(c, jf, frame, (frame != AFFK_WORLD) ? k_ref(c, frame) : zero, tf, rf);
+    k_cross(cr, geo + 6, rf);
+    for (int k = 0; k < 3; ++k) cl[k] = (te[k] - tr[k]) + cr[k];
+    if (frame != AFFK_WORLD) k_mulv(out, k_ref(c, frame) + 3, cl);
+    else { out[0] = cl[0]; out[1] = cl[1]; out[2] = cl[2]; }
+    if (kind == AFF_TASK_XYZ) { Jrow0[col] = out[0]; Jrow0[Jstride + col] = out[1]; Jrow0[2 * Jstride + col] = out[2]; }
+    else Jrow0[col] = out[kind - AFF_TASK_X];
+  } else if (kind == AFF_TASK_POLAR) {
+    double te[3], re[3], tr[3], rr[3], wI[3], w[3];
+    k_jac_cols(c, jf, eff, geo + 9, te, re);
+    k_jac_cols(c, jf, ref, geo + 9, tr, rr);
+    for (int k = 0; k < 3; ++k) wI[k] = re[k] - rr[k];
+    if (ref != AFFK_WORLD) k_mulv(w, k_ref(c, ref) + 3, wI);
+    else { w[0] = wI[0]; w[1] = wI[1]; w[2] = wI[2]; }
+    Jrow0[col] = k_dot(geo + 3, w);
+    Jrow0[Jstride + col] = k_dot(geo + 6, w);
+  } else if (kind == AFF_TASK_INCLINATION) {
+    double te[3], re[3], tr[3], rr[3], wI[3];
+    const double* n = geo + 6;
+    double v = 0.0;
+    if (n[0] != 0.0 || n[1] != 0.0 || n[2] != 0.0) {
+      k_jac_cols(c, jf, eff, geo + 9, te, re);
+      k_jac_cols(c, jf, ref, geo + 9, tr, rr);
+      for (int k = 0; k < 3; ++k) wI[k] = re[k] - rr[k];
+      v = k_dot(n, wI);
+    }
+    Jrow0[col] = v;
+  } else {
+    const int nj = ldg(&tk->n_joints);
+    for (int i = 0; i < nj; ++i) Jrow0[i * Jstride + col] = (ldg(&tk->jidx[i]) == col) ? 1.0 : 0.0;
+  }
+}
+
+// -------------------------------------------------------- shape distances
+AFF_DEV double k_seg_seg(const double* p1, const double* d1, const double* p2, const double* d2)
+{
+  const double EPS = 1.0e-18;
+  double r[3];
+  for (int k = 0; k < 3; ++k) r[k] = p1[k] - p2[k];
+  const double a = k_dot(d1, d1), e = k_dot(d2, d2), f = k_dot(d2, r);
+  double s, t;
+  if (a <= EPS && e <= EPS) { s = 0.0; t = 0.0; }
+  else if (a <= EPS) { s = 0.0; t = k_clamp01(f / e); }
+  else {
+    const double cc = k_dot(d1, r);
+    if (e <= EPS) { t = 0.0; s = k_clamp01(-cc / a); }
+    else {
+      const double b = k_dot(d1, d2);
+      const double denom = fma(a, e, -(b * b));
+      s = (denom > 0.0) ? k_clamp01(fma(b, f, -(cc * e)) / denom) : 0.0;
+      t = fma(b, s, f) / e;
+      if (t < 0.0) { t = 0.0; s = k_clamp01(-cc / a); }
+      else if (t > 1.0) { t = 1.0; s = k_clamp01((b - cc) / a); }
+    }
+  }
+  double dv[3];
+  for (int k = 0; k < 3; ++k) dv[k] = fma(s, d1[k], p1[k]) - fma(t, d2[k], p2[k]);
+  return sqrt(k_dot(dv, dv));
+}
+
+AFF_DEV double k_seg_box_g(const double* p, const double* d, const double* h, double s)
+{
+  double g = 0.0;
+  for (int i = 0; i < 3; ++i) {
+    const double cv = fma(s, d[i], p[i]);
+    const double e = (cv > h[i]) ? cv - h[i] : ((cv < -h[i]) ? cv + h[i] : 0.0);
+    g = fma(e, d[i], g);
+  }
+  return g;
+}
+AFF_DEV double k_seg_box_f(const double* p, const double* d, const double* h, double s)
+{
+  double f = 0.0;
+  for (int i = 0; i < 3; ++i) {
+    const double cv = fma(s, d[i], p[i]);
+    const double e = (cv > h[i]) ? cv - h[i] : ((cv < -h[i]) ? cv + h[i] : 0.0);
+    f = fma(e, e, f);
+  }
+  return f;
+}
+AFF_DEV double k_seg_box(const double* p, const double* d, const double* h)
+{
+  double lo = 0.0, hi = 1.0;
+  double glo = k_seg_box_g(p, d, h, 0.0), ghi = k_seg_box_g(p, d, h, 1.0);
+  double s;
+  if (glo >= 0.0) s = 0.0;
+  else if (ghi <= 0.0) s = 1.0;
+  else {
+    for (int i = 0; i < 3; ++i) {
+      if (d[i] == 0.0) continue;
+      for (int sg = 0; sg < 2; ++sg) {
+        const double b = ((sg ? h[i] : -h[i]) - p[i]) / d[i];
+        if (!(b > lo && b < hi)) continue;
+        const double gb = k_seg_box_g(p, d, h, b);
+        if (gb <= 0.0) { lo = b; glo = gb; } else { hi = b; ghi = gb; }
+      }
+    }
+    const double dg = ghi - glo;
+    s = (dg > 0.0) ? fma(hi - lo, (-glo) / dg, lo) : lo;
+  }
+  return sqrt(k_seg_box_f(p, d, h, s));
+}
+
+AFF_DEV double k_seg_cyl_D(const double* p, const double* d, double hl, double R, double s)
+{
+  const double x = fma(s, d[0], p[0]), y = fma(s, d[1], p[1]), z = fma(s, d[2], p[2]);
+  const double rho = sqrt(fma(y, y, x * x));
+  const double er = (rho > R) ? rho - R : 0.0;
+  const double az = fabs(z);
+  const double ez = (az > hl) ? az - hl : 0.0;
+  return sqrt(fma(ez, ez, er * er));
+}
+AFF_DEV double k_seg_cyl(const double* p, const double* d, double hl, double R)
+{
+  const double PHI = 0.6180339887498949;
+  double best = k_seg_cyl_D(p, d, hl, R, 0.0);
+  if (d[0] == 0.0 && d[1] == 0.0 && d[2] == 0.0) return best;
+  const double D1 = k_seg_cyl_D(p, d, hl, R, 1.0);
+  if (D1 < best) best = D1;
+  double a = 0.0, b = 1.0;
+  double x1 = b - PHI * (b - a), x2 = a + PHI * (b - a);
+  double f1 = k_seg_cyl_D(p, d, hl, R, x1), f2 = k_seg_cyl_D(p, d, hl, R, x2);
+  for (int it = 0; it < AFFK_GOLDEN_ITERS; ++it) {
+    if (f1 <= f2) { b = x2; x2 = x1; f2 = f1; x1 = b - PHI * (b - a); f1 = k_seg_cyl_D(p, d, hl, R, x1); }
+    else { a = x1; x1 = x2; f1 = f2; x2 = a + PHI * (b - a); f2 = k_seg_cyl_D(p, d, hl, R, x2); }
+  }
+  const double Dm = k_seg_cyl_D(p, d, hl, R, 0.5 * (a + b));
+  if (Dm < best) best = Dm;
+  return best;
+}
+
+AFF_DEV bool k_is_seg(int type) { return type == AFF_SHAPE_SSL || type == AFF_SHAPE_SPHERE; }
+
+AFF_DEV void k_shape_segment(int type, const double* ext, const double* A, double* p, double* d, double* r)
+{
+  for (int k = 0; k < 3; ++k) p[k] = A[k];
+  *r = ext[0];
+  if (type == AFF_SHAPE_SSL) for (int k = 0; k < 3; ++k) d[k] = ext[2] * A[3 + 6 + k];
+  else d[0] = d[1] = d[2] = 0.0;
+}
+
+// A1/A2: world shape frames (12 doubles); ext: 3 doubles each.
+AFF_DEV double k_shape_dist(int t1, const double* e1, const double* A1, int t2, const double* e2, const double* A2)
+{
+  if (!k_is_seg(t1) && k_is_seg(t2)) {
+    const int tt = t1; t1 = t2; t2 = tt;
+    const double* te = e1; e1 = e2; e2 = te;
+    const double* ta = A1; A1 = A2; A2 = ta;
+  }
+  if (!k_is_seg(t1)) return DBL_MAX;
+  double p1[3], d1[3], r1;
+  k_shape_segment(t1, e1, A1, p1, d1, &r1);
+  if (k_is_seg(t2)) {
+    double p2[3], d2[3], r2;
+    k_shape_segment(t2, e2, A2, p2, d2, &r2);
+    return (k_seg_seg(p1, d1, p2, d2) - r1) - r2;
+  }
+  double rel[3], pl[3], dl[3];
+  for (int k = 0; k < 3; ++k) rel[k] = p1[k] - A2[k];
+  k_mulv(pl, A2 + 3, rel);
+  k_mulv(dl, A2 + 3, d1);
+  if (t2 == AFF_SHAPE_BOX) {
+    const double h[3] = {0.5 * e2[0], 0.5 * e2[1], 0.5 * e2[2]};
+    return k_seg_box(pl, dl, h) - r1;
+  }
+  return k_seg_cyl(pl, dl, 0.5 * e2[2], e2[0]) - r1;
+}
+
+AFF_DEV void k_shape_aabb(int type, const double* ext, const double* A, double* mn, double* mx)
+{
+  if (type == AFF_SHAPE_SSL || type == AFF_SHAPE_SPHERE) {
+    double p[3], d[3], r;
+    k_shape_segment(type, ext, A, p, d, &r);
+    for (int k = 0; k < 3; ++k) {
+      const double q = p[k] + d[k];
+      mn[k] = ((p[k] < q) ? p[k] : q) - r;
+      mx[k] = ((p[k] > q) ? p[k] : q) + r;
+    }
+  } else if (type == AFF_SHAPE_BOX) {
+    for (int k = 0; k < 3; ++k) {
+      const double e = fma(fabs(A[3 + 6 + k]), 0.5 * ext[2], fma(fabs(A[3 + 3 + k]), 0.5 * ext[1], fabs(A[3 + k]) * (0.5 * ext[0])));
+      mn[k] = A[k] - e; mx[k] = A[k] + e;
+    }
+  } else {
+    for (int k = 0; k < 3; ++k) {
+      const double az = A[3 + 6 + k];
+      const double cc = 1.0 - az * az;
+      const double e = fma(fabs(az), 0.5 * ext[2], ext[0] * sqrt(cc > 0.0 ? cc : 0.0));
+      mn[k] = A[k] - e; mx[k] = A[k] + e;
+    }
+  }
+}
+
+AFF_DEV bool k_aabb_overlap(const double* A, const double* B, double thr)
+{
+  bool ov = true;
+  for (int cI = 0; cI < 3; ++cI) if (A[cI] - thr > B[3 + cI] || B[cI] - thr > A[3 + cI]) ov = false;
+  return ov;
+}
+
+// ------------------------------------------------------- collision model
+struct KCollResult { double minDist; int minB1, minB2; double cost; };
+
+// toggleSlotPlus1: slot+1 if the shape's body IS a re-parentable object (the
+// body a CollisionModelConstraint names), else 0.
+AFF_DEV bool k_dshape_active(const KCtx& c, const KShape* sh, int toggleSlotPlus1)
+{
+  if (toggleSlotPlus1) {
+    const int mode = c.objMode[toggleSlotPlus1 - 1];
+    if (mode == 1) return true;
+    if (mode == 2) return false;
+  }
+  return ldg(&sh->active0) != 0;
+}
+
+// Distance of a live body pair = min over active shape pairs.
+// ia: dynamic body index; ib >= 0 dynamic body index, ib < 0 static body (-1-ib).
+AFF_DEV double k_pair_distance(const KCtx& c, int ia, int ib)
+{
+  const KPlan& P = *c.P;
+  const KShapeBody* ba = P.dbody + ia;
+  const int fa = ldg(&ba->first_shape), na = ldg(&ba->n_shapes), sa = ldg(&ba->toggle_slot);
+  const double* shp = c.sm + P.o_shp;
+  double dmin = DBL_MAX;
+  for (int k1 = 0; k1 < na; ++k1) {
+    const KShape* s1 = P.dshape + fa + k1;
+    if (!k_dshape_active(c, s1, sa)) continue;
+    double e1[3] = {ldg(&s1->ext[0]), ldg(&s1->ext[1]), ldg(&s1->ext[2])};
+    const int t1 = ldg(&s1->type);
+    if (ib >= 0) {
+      const KShapeBody* bb = P.dbody + ib;
+      const int fb = ldg(&bb->first_shape), nb = ldg(&bb->n_shapes), sb = ldg(&bb->toggle_slot);
+      for (int k2 = 0; k2 < nb; ++k2) {
+        const KShape* s2 = P.dshape + fb + k2;
+        if (!k_dshape_active(c, s2, sb)) continue;
+        double e2[3] = {ldg(&s2->ext[0]), ldg(&s2->ext[1]), ldg(&s2->ext[2])};
+        const double dd = k_shape_dist(t1, e1, shp + 12 * (fa + k1), ldg(&s2->type), e2, shp + 12 * (fb + k2));
+        if (dd < dmin) dmin = dd;
+      }
+    } else {
+      const KShapeBody* bb = P.sbody + (-1 - ib);
+      const int fb = ldg(&bb->first_shape), nb = ldg(&bb->n_shapes);
+      for (int k2 = 0; k2 < nb; ++k2) {
+        const KShape* s2 = P.sshape + fb + k2;
+        if (!ldg(&s2->active0)) continue;
+        double e2[3] = {ldg(&s2->ext[0]), ldg(&s2->ext[1]), ldg(&s2->ext[2])};
+        double A2[12];
+        for (int e = 0; e < 12; ++e) A2[e] = ldg(&P.sshapeA[12 * (fb + k2) + e]);
+        const double dd = k_shape_dist(t1, e1, shp + 12 * (fa + k1), ldg(&s2->type), e2, A2);
+        if (dd < dmin) dmin = dd;
+      }
+    }
+  }
+  return dmin;
+}
+
+// ControllerBase::computeCollisionModel: broad phase + narrow phase
+// (see the rule list above collmdl_compute() in oracle/oracle.c).
+AFF_DEV KCollResult k_collision(const KCtx& c)
+{
+  const KPlan& P = *c.P;
+  const int lane = c.lane;
+  const double thr = P.bp_threshold;
+  double* shp = c.sm + P.o_shp;
+  double* baabb = c.sm + P.o_baabb;
+  double* taabb = c.sm + P.o_taabb;
+  int* live = (int*)(c.sm + P.o_live);             // pairs: [2*i] = dyn body a, [2*i+1] = other
+  // 1. world frames of the dynamic shapes
+  for (int s = lane; s < P.nDynShapes; s += 32) {
+    const KShape* sh = P.dshape + s;
+    const double* An = k_ref(c, ldg(&sh->node));
+    double W[12];
+    k_compose(W, sh->A_CB, An);
+    for (int e = 0; e < 12; ++e) shp[12 * s + e] = W[e];
+  }
+  w_sync();
+  // 2. per dynamic body: active flag, tree, AABB
+  int myActive = 0, myTree = -1;
+  if (lane < P.nDynBodies) {
+    const KShapeBody* b = P.dbody + lane;
+    const int f = ldg(&b->first_shape), n = ldg(&b->n_shapes), os = ldg(&b->obj_slot), ts = ldg(&b->toggle_slot);
+    double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    for (int k = 0; k < n; ++k) {
+      const KShape* sh = P.dshape + f + k;
+      if (!k_dshape_active(c, sh, ts)) continue;
+      myActive = 1;
+      double ext[3] = {ldg(&sh->ext[0]), ldg(&sh->ext[1]), ldg(&sh->ext[2])};
+      double smn[3], smx[3];
+      k_shape_aabb(ldg(&sh->type), ext, shp + 12 * (f + k), smn, smx);
+      for (int q = 0; q < 3; ++q) { if (smn[q] < mn[q]) mn[q] = smn[q]; if (smx[q] > mx[q]) mx[q] = smx[q]; }
+    }
+    for (int q = 0; q < 3; ++q) { baabb[6 * lane + q] = mn[q]; baabb[6 * lane + 3 + q] = mx[q]; }
+    myTree = os ? c.objTree[os - 1] : ldg(&b->tree);
+  }
+  const unsigned activeMask = w_ballot(myActive);
+  // tree id of every dynamic body, packed 4 bits each (tree+1), 16 bodies -> 64 bits in two words
+  unsigned treeLo = 0u, treeHi = 0u;
+  for (int b = 0; b < P.nDynBodies; ++b) {
+    const int t = w_shfl(myTree, b) + 1;
+    if (b < 8) treeLo |= (unsigned)(t & 15) << (4 * b); else treeHi |= (unsigned)(t & 15) << (4 * (b - 8));
+  }
+  w_sync();
+  // 3. tree AABBs
+  if (lane < P.nTrees) {
+    double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    for (int b = 0; b < P.nDynBodies; ++b) {
+      const int t = (int)(((b < 8 ? treeLo >> (4 * b) : treeHi >> (4 * (b - 8))) & 15u)) - 1;
+      if (t != lane || !((activeMask >> b) & 1u)) continue;
+      for (int q = 0; q < 3; ++q) {
+        const double lo = baabb[6 * b + q], hi = baabb[6 * b + 3 + q];
+        if (lo < mn[q]) mn[q] = lo;
+        if (hi > mx[q]) mx[q] = hi;
+      }
+    }
+    for (int q = 0; q < 3; ++q) { taabb[6 * lane + q] = mn[q]; taabb[6 * lane + 3 + q] = mx[q]; }
+  }
+  w_sync();
+  int nLive = 0;
+  // 4a. candidate pairs among dynamic bodies and against explicit static bodies
+  for (int base = 0; base < P.nAlways; base += 32) {
+    const int i = base + lane;
+    int isLive = 0, ia = 0, ib = 0;
+    if (i < P.nAlways) {
+      ia = ldg(&P.always[2 * i]); ib = ldg(&P.always[2 * i + 1]);
+      const int ta = (int)(((ia < 8 ? treeLo >> (4 * ia) : treeHi >> (4 * (ia - 8))) & 15u)) - 1;
+      const bool actA = (activeMask >> ia) & 1u;
+      if (ib >= 0) {
+        const int tb = (int)(((ib < 8 ? treeLo >> (4 * ib) : treeHi >> (4 * (ib - 8))) & 15u)) - 1;
+        const bool actB = (activeMask >> ib) & 1u;
+        if (actA && actB && !(ta < 0 && tb < 0)) {
+          if (ta >= 0 && tb >= 0) isLive = (ta != tb);
+          else {
+            const int other = (ta >= 0) ? ib : ia;
+            if (ldg(&P.dbody[other].explicit_bp)) isLive = 1;
+            else isLive = k_aabb_overlap(baabb + 6 * ia, baabb + 6 * ib, thr);
+          }
+        }
+      } else {
+        // static explicit body: live iff a is in a tree
+        const KShapeBody* sb = P.sbody + (-1 - ib);
+        isLive = actA && ta >= 0 && ldg(&sb->any_active0);
+      }
+    }
+    const unsigned m = w_ballot(isLive);
+    if (isLive) {
+      const int pos = nLive + w_popc(m & ((1u << lane) - 1u));
+      if (pos < AFFK_MAX_LIVE) { live[2 * pos] = ia; live[2 * pos + 1] = ib; }
+    }
+    nLive += w_popc(m);
+  }
+  // 4b. static bodies that are not explicit: two-level AABB test
+  for (int base = 0; base < P.nStatBodies; base += 32) {
+    const int i = base + lane;
+    int near = 0;
+    if (i < P.nStatBodies) {
+      const KShapeBody* sb = P.sbody + i;
+      if (!ldg(&sb->explicit_bp) && ldg(&sb->any_active0)) {
+        double bb[6];
+        for (int q = 0; q < 6; ++q) bb[q] = ldg(&P.sbodyAABB[6 * i + q]);
+        for (int t = 0; t < P.nTrees; ++t) if (k_aabb_overlap(taabb + 6 * t, bb, thr)) near = 1;
+      }
+    }
+    unsigned nm = w_ballot(near);
+    while (nm) {   // rare: a static body is close to a tree; test it against each tree body
+      const int src = w_ffs(nm) - 1;
+      nm &= nm - 1u;
+      const int sidx = base + src;
+      int isLive = 0;
+      if (lane < P.nDynBodies && ((activeMask >> lane) & 1u)) {
+        const int ta = (int)(((lane < 8 ? treeLo >> (4 * lane) : treeHi >> (4 * (lane - 8))) & 15u)) - 1;
+        if (ta >= 0) {
+          double bb[6];
+          for (int q = 0; q < 6; ++q) bb[q] = ldg(&P.sbodyAABB[6 * sidx + q]);
+          isLive = k_aabb_overlap(baabb + 6 * lane, bb, thr);
+        }
+      }
+      const unsigned m = w_ballot(isLive);
+      if (isLive) {
+        const int pos = nLive + w_popc(m & ((1u << lane) - 1u));
+        if (pos < AFFK_MAX_LIVE) { live[2 * pos] = lane; live[2 * pos + 1] = -1 - sidx; }
+      }
+      nLive += w_popc(m);
+    }
+  }
+  w_sync();
+  if (nLive > AFFK_MAX_LIVE) nLive = AFFK_MAX_LIVE;
+  // 5. narrow phase
+  double best = DBL_MAX; int bestKey = 0x7fffffff;
+  double myCost[AFFK_MAX_LIVE / 32]; int myKey[AFFK_MAX_LIVE / 32];
+  int nCostly = 0;
+  for (int r = 0; r < AFFK_MAX_LIVE / 32; ++r) { myCost[r] = 0.0; myKey[r] = 0x7fffffff; }
+#pragma unroll
+  for (int r = 0; r < AFFK_MAX_LIVE / 32; ++r) {
+    const int i = 32 * r + lane;
+    if (i < nLive) {
+      const int ia = live[2 * i], ib = live[2 * i + 1];
+      const double d = k_pair_distance(c, ia, ib);
+      const int bodyA = ldg(&P.dbody[ia].body);
+      const int bodyB = (ib >= 0) ? ldg(&P.dbody[ib].body) : ldg(&P.sbody[-1 - ib].body);
+      const int b1 = bodyA < bodyB ? bodyA : bodyB, b2 = bodyA < bodyB ? bodyB : bodyA;
+      const int key = (b1 << 15) | b2;
+      if (d < best || (d == best && key < bestKey)) { best = d; bestKey = key; }
+      if (thr > 0.0) {
+        if (d < 0.0) { myCost[r] = 1.0 - (2.0 * d) / thr; myKey[r] = key; nCostly++; }
+        else if (d < thr) { const double u = (d - thr) / thr; myCost[r] = u * u; myKey[r] = key; nCostly++; }
+      }
+    }
+  }
+  KCollResult res;
+  w_min_keyed(best, bestKey);
+  res.minDist = best;
+  if (nLive == 0 || !(best < DBL_MAX)) { res.minB1 = -1; res.minB2 = -1; }
+  else { res.minB1 = bestKey >> 15; res.minB2 = bestKey & 0x7fff; }
+  // cost: sum of the non-zero pair terms in ascending (b1, b2) order
+  res.cost = 0.0;
+  unsigned anyCost = w_ballot(nCostly > 0);
+  while (anyCost) {
+    double dummy = 0.0; int k = 0x7fffffff; double kc = 0.0;
+#pragma unroll
+    for (int r = 0; r < AFFK_MAX_LIVE / 32; ++r) if (myKey[r] < k) { k = myKey[r]; kc = myCost[r]; }
+    int kmin = k;
+    w_min_keyed(dummy, kmin);
+    const int owner = w_ffs(w_ballot(k == kmin && k != 0x7fffffff)) - 1;
+    double term = 0.0;
+    if (lane == owner) {
+      term = kc; nCostly--;
+#pragma unroll
+      for (int r = 0; r < AFFK_MAX_LIVE / 32; ++r) if (myKey[r] == k) myKey[r] = 0x7fffffff;
+    }
+    term = w_shfl(term, owner);
+    res.cost = res.cost + term;
+    anyCost = w_ballot(nCostly > 0);
+  }
+  return res;
+}
+
+// ----------------------------------------------------------- the rollout
+AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
+{
+  KCtx c;
+  c.P = &P; c.C = P.cands + cand; c.sm = sm; c.lane = w_lane();
+  const KCand& C = *c.C;
+  const int lane = c.lane, nJ = P.nJ;
+  const double dt = P.opts.dt;
+  const int nTasks = ldg(&C.n_tasks), xdim = ldg(&C.xdim);
+  const KTask* tasks = P.tasks + ldg(&C.first_task);
+  double* q = sm + P.o_q; double* qdot = sm + P.o_qdot; double* dH = sm + P.o_dH; double* dq = sm + P.o_dq;
+  double* J = sm + P.o_J; double* L = sm + P.o_L; double* rhs = sm + P.o_rhs; double* dxv = sm + P.o_dx;
+  double* st = sm + P.o_st; double* xdes = sm + P.o_xdes; double* xcur = sm + P.o_xcur; double* geo = sm + P.o_geo;
+  const int JS = P.JS, LS = P.LS;
+
+  // ---- per-lane constants
+  double jq0 = 0, jqmin = 0, jqmax = 0, jspeed = AFFK_NO_LIMIT, jacc = AFFK_NO_LIMIT, jwjl = 0, jw = 0;
+  int jnode = -1, jtype = 0;
+  if (lane < nJ) {
+    jq0 = ldg(&P.jq0[lane]); jqmin = ldg(&P.jq_min[lane]); jqmax = ldg(&P.jq_max[lane]);
+    jspeed = ldg(&P.jspeed[lane]); jacc = ldg(&P.jacc[lane]); jwjl = ldg(&P.jwjl[lane]); jw = ldg(&P.jwmetric[lane]);
+    jnode = ldg(&P.j_node[lane]); jtype = ldg(&P.j_type[lane]);
+    q[lane] = ldg(&P.jq_init[lane]); qdot[lane] = 0.0;
+  }
+  // task of this lane's dimension
+  int myTask = -1;
+  if (lane < xdim) for (int t = 0; t < nTasks; ++t) if (lane >= ldg(&tasks[t].xoff)) myTask = t;
+  int viaHead = 0, viaEnd = 0;
+  if (lane < xdim) { viaHead = ldg(&C.via_off[lane]); viaEnd = ldg(&C.via_off[lane + 1]); }
+  const KVia* vias = P.vias + ldg(&C.first_via);
+  int actHead = 0, actEnd = 0, myActive = 0;
+  double lastSwitchT = 0.0, lastSwitchH = -1.0;
+  if (lane < nTasks) { actHead = ldg(&C.act_off[lane]); actEnd = ldg(&C.act_off[lane + 1]); }
+  const KAct* acts = P.acts + ldg(&C.first_act);
+  const KGraphCon* gcons = P.gcons + ldg(&C.first_gcon);
+  const int nGcon = ldg(&C.n_gcon);
+  unsigned gfired = 0u;
+
+  // ---- objects
+  c.objHasRel = 0u;
+  for (int s = 0; s < AFFK_MAX_OBJ; ++s) { c.objParent[s] = AFFK_WORLD; c.objChain[s] = 0u; c.objTree[s] = -1; c.objMode[s] = 0; }
+  for (int s = 0; s < P.nObj; ++s) {
+    const int n = ldg(&P.obj_node[s]);
+    const int par = ldg(&P.dyn[n].parent);
+    c.objParent[s] = par;
+  }
+  // chains / trees of objects hanging on dynamic parents (e.g. held in a hand at start)
+  for (int s = 0; s < P.nObj; ++s) { c.objChain[s] = k_chain(c, c.objParent[s]); c.objTree[s] = k_tree_of_node(c, c.objParent[s]); }
+  if (lane < 6) {
+    for (int s = 0; s < P.nObj; ++s)
+      sm[P.o_objq6 + 6 * s + lane] = (ldg(&C.pose_slot) == s) ? ldg(&C.pose_q6[lane]) : ldg(&P.obj_q6[6 * s + lane]);
+  }
+  if (lane < xdim) { st[3 * lane] = 0.0; st[3 * lane + 1] = 0.0; st[3 * lane + 2] = 0.0; xdes[lane] = 0.0; }
+  w_sync();
+
+  // ---- initial state
+  k_fk(c, true);
+  const int nSteps = ldg(&C.n_steps);
+  const int qrows = P.qlog_rows;
+  double* qlog = P.qlog ? P.qlog + (size_t)cand * qrows * nJ : nullptr;
+  if (qlog && lane < nJ && qrows > 0) qlog[lane] = q[lane];
+
+  aff_result res;
+  res.idx = cand; res.success = 0; res.code = 0; res.first_code = 0; res.first_fail_step = -1; res.fail_step = -1;
+  res.fail_id0 = -1; res.fail_id1 = -1; res.min_dist_b1 = -1; res.min_dist_b2 = -1; res.n_steps = 0; res.reserved = 0;
+  res.jmask_bits = 0ull; res.min_dist = DBL_MAX; res.jl_cost = 0.0; res.coll_cost = 0.0; res.track_err = 0.0;
+
+  KCollResult cm = k_collision(c);
+  res.min_dist = cm.minDist; res.min_dist_b1 = cm.minB1; res.min_dist_b2 = cm.minB2;
+
+  // check(): checkLimits(jl, coll, speed, 0, 0, 0.01)  (src/TrajectoryPredictor.cpp:426-441)
+  {
+    const int viol = (lane < nJ) && (q[lane] < jqmin || q[lane] > jqmax);
+    bool ok0 = w_ballot(viol) == 0u;
+    if (cm.minB1 >= 0 && cm.minDist < 0.01) ok0 = false;
+    if (!ok0) {
+      res.code = AFF_CODE_INITIAL_STATE; res.first_code = AFF_CODE_INITIAL_STATE; res.first_fail_step = 0; res.fail_step = 0;
+      if (lane == 0) P.results[cand] = res;
+      return;
+    }
+  }
+
+  // geometry of the initial state (for the first re-initialisation of the trajectories)
+  if (lane < nTasks) k_task_geo(c, tasks + lane, geo + AFFK_GEO * lane, xcur);
+  w_sync();
+
+  unsigned activeMask = 0u, prevMask = 0u, jmaskBits = 0u;
+  unsigned emask = ~(P.rbj_static_chain);
+  for (int s = 0; s < P.nObj; ++s) emask &= ~c.objChain[s];
+  double tnow = 0.0, qFilt = 0.0, err = 0.0, jlSum = 0.0, collSum = 0.0, endTime = ldg(&C.end_abs);
+  const double motionDuration = ldg(&C.end_abs) - ldg(&C.start_abs);
+  const double alpha = P.opts.alpha, lambda = P.opts.lambda, qFiltDecay = P.opts.q_filt_decay;
+  int success = 1, rows = 1;
+
+  for (int iter = 0; iter < nSteps; ++iter) {
+    // ---- task switch / qFilt (:166-180)
+    if (prevMask != activeMask) qFilt = 1.0;
+    if (qFiltDecay <= 0.0) qFilt = 0.0;
+    else qFilt = k_clip(qFilt - (1.0 / qFiltDecay) * dt, 0.0, 1.0);
+
+    // ---- tc->step(dt): trajectories
+    if (lane < xdim) {
+      double s3[3];
+      if (!((activeMask >> myTask) & 1u)) { s3[0] = xcur[lane]; s3[1] = 0.0; s3[2] = 0.0; }
+      else { s3[0] = st[3 * lane]; s3[1] = st[3 * lane + 1]; s3[2] = st[3 * lane + 2]; }
+      k_via_step(s3, vias + viaHead, viaEnd - viaHead, tnow, dt, sm + P.o_scratch + AFFK_VIA_STRIDE * lane);
+      st[3 * lane] = s3[0]; st[3 * lane + 1] = s3[1]; st[3 * lane + 2] = s3[2];
+      xdes[lane] = s3[0];
+    }
+    tnow = tnow + dt;
+    // graph constraints
+    for (int k = 0; k < nGcon; ++k) {
+      if ((gfired >> k) & 1u) continue;
+      const double tc = ldg(&gcons[k].t);
+      const int kind = ldg(&gcons[k].kind), slot = ldg(&gcons[k].slot);
+      if (kind == AFF_CON_CONNECT) {
+        if (tc - tnow < AFFK_TRAJ_EPS) {
+          const int par = ldg(&gcons[k].parent);
+          const int on = ldg(&P.obj_node[slot]);
+          w_sync();
+          if (lane < 12) {
+            // HTr_invTransform: child relative to the new parent
+            const double* Cc = k_node(c, on); const double* Pp = k_ref(c, par);
+            double v;
+            if (lane < 3) {
+              const double d0 = Cc[0] - Pp[0], d1 = Cc[1] - Pp[1], d2 = Cc[2] - Pp[2];
+              v = fma(Pp[3 + 3 * lane + 2], d2, fma(Pp[3 + 3 * lane + 1], d1, Pp[3 + 3 * lane] * d0));
+            } else {
+              const int i = (lane - 3) / 3, j = (lane - 3) % 3;
+              v = fma(Cc[3 + 3 * i + 2], Pp[3 + 3 * j + 2], fma(Cc[3 + 3 * i + 1], Pp[3 + 3 * j + 1], Cc[3 + 3 * i] * Pp[3 + 3 * j]));
+            }
+            sm[P.o_objrel + 12 * slot + lane] = v;
+          }
+          w_sync();
+          c.objHasRel |= 1u << slot;
+          c.objParent[slot] = par;
+          c.objChain[slot] = k_chain(c, par);
+          c.objTree[slot] = k_tree_of_node(c, par);
+          emask = ~(P.rbj_static_chain);
+          for (int s = 0; s < P.nObj; ++s) emask &= ~c.objChain[s];
+          gfired |= 1u << k;
+        }
+      } else {
+        if (tc - tnow < 0.0) { c.objMode[slot] = ldg(&gcons[k].on) ? 1 : 2; gfired |= 1u << k; }
+      }
+    }
+    // activation points
+    if (lane < nTasks) {
+      while (actHead < actEnd && ldg(&acts[actHead].t) - tnow < AFFK_TRAJ_EPS) {
+        myActive = ldg(&acts[actHead].on); lastSwitchT = ldg(&acts[actHead].t); lastSwitchH = ldg(&acts[actHead].horizon);
+        ++actHead;
+      }
+    }
+    if (lane < xdim) while (viaHead < viaEnd && ldg(&vias[viaHead].t) - tnow < AFFK_TRAJ_EPS) ++viaHead;
+    prevMask = activeMask;
+    activeMask = w_ballot(lane < nTasks && myActive);
+    {
+      const double rem = ldg(&C.end_abs) - tnow;
+      endTime = rem > 0.0 ? rem : 0.0;
+    }
+    // blending
+    double bl = 1.0;
+    if (lane < nTasks) {
+      if (actHead < actEnd) { const double h = ldg(&acts[actHead].horizon); if (h > 0.0) bl = k_clip((ldg(&acts[actHead].t) - tnow) / h, 0.0, 1.0); }
+      if (lastSwitchH > 0.0) { const double up = k_clip((tnow - lastSwitchT) / lastSwitchH, 0.0, 1.0); if (up < bl) bl = up; }
+    }
+    double blending = w_min(bl);
+    if (activeMask == 0u) blending = 0.0;
+    const double phase = (motionDuration > 0.0) ? 1.0 - (endTime / motionDuration) : 0.0;
+    const double phaseScale = aff_sin(AFF_PI * phase);
+    const double alphaEff = blending * alpha;
+    w_sync();
+
+    // ================= computeIK =================
+    // row offsets of the active tasks
+    int m = 0, myRow = 0;
+    for (int t = 0; t < nTasks; ++t) {
+      if (t == lane) myRow = m;
+      if ((activeMask >> t) & 1u) m += k_task_dim(tasks + t);
+    }
+    if (lane < nTasks && ((activeMask >> lane) & 1u)) k_task_dx(tasks + lane, geo + AFFK_GEO * lane, xcur, xdes, dxv + myRow);
+    // joint frame of this lane's IK joint
+    KJointFrame jf;
+    jf.valid = (lane < nJ); jf.type = jtype;
+    if (jf.valid) {
+      const double* A = k_node(c, jnode);
+      const int ar = (jtype < AFF_JNT_ROT_X) ? jtype : jtype - AFF_JNT_ROT_X;
+      for (int k = 0; k < 3; ++k) { jf.ax[k] = A[3 + 3 * ar + k]; jf.org[k] = A[k]; }
+    } else { for (int k = 0; k < 3; ++k) { jf.ax[k] = 0.0; jf.org[k] = 0.0; } }
+    // J columns
+    {
+      int row = 0;
+      for (int t = 0; t < nTasks; ++t) {
+        if (!((activeMask >> t) & 1u)) continue;
+        if (lane < nJ) k_task_J(c, jf, tasks + t, geo + AFFK_GEO * t, J + row * JS, JS);
+        row += k_task_dim(tasks + t);
+      }
+    }
+    // dH: joint limit gradient + elbow / wrist terms (:589-625)
+    double dHv = 0.0;
+    if (lane < nJ) {
+      const double dqc = q[lane] - jq0;
+      const double r = (dqc > 0.0) ? jqmax - jq0 : jq0 - jqmin;
+      dHv = ((jwjl * dqc) / (r * r)) * alphaEff;
+    }
+    {
+      double ex = 0.0, tmp = 0.0;
+      if (P.ns_base != AFFK_WORLD) {   // AFFK_WORLD = base_footprint absent: no extra null space
+        const int base = P.ns_base;
+        const bool haveBase = true;
+        const double* Ab = k_ref(c, base);
+        // elbows, then hands (boundary 0.15 / 0.0)
+        for (int pass = 0; pass < 2 && haveBase; ++pass) {
+          const double boundary = pass ? 0.0 : 0.15;
+          for (int side = 0; side < 2; ++side) {
+            const int el = pass ? P.ns_hand[side] : P.ns_forearm[side];
+            const int sh = P.ns_upperarm[side];
+            if (el == AFFK_WORLD || sh == AFFK_WORLD) continue;
+            const double* Ae = k_ref(c, el); const double* As = k_ref(c, sh);
+            double dS[3], dE[3];
+            for (int k = 0; k < 3; ++k) { dS[k] = As[k] - Ab[k]; dE[k] = Ae[k] - Ab[k]; }
+            const double yS = fma(Ab[3 + 3 + 2], dS[2], fma(Ab[3 + 3 + 1], dS[1], Ab[3 + 3] * dS[0]));
+            const double yE = fma(Ab[3 + 3 + 2], dE[2], fma(Ab[3 + 3 + 1], dE[1], Ab[3 + 3] * dE[0]));
+            double f;
+            if (side == 0) f = k_clip((yE - yS) - boundary, -0.5, 0.0) * 5.0;
+            else f = -k_clip((-yE + yS) - boundary, -0.5, 0.0) * 5.0;
+            double te[3], re[3], tr[3], rr[3];
+            k_jac_cols(c, jf, el, Ae, te, re);
+            k_jac_cols(c, jf, base, Ab, tr, rr);
+            tmp = tmp + (te[1] - tr[1]) * f;
+          }
+        }
+        ex = ex + tmp;
+        tmp = 0.0;
+        for (int side = 0; side < 2 && haveBase; ++side) {
+          const int wr = P.ns_hand[side];
+          if (wr == AFFK_WORLD) continue;
+          const double* Aw = k_ref(c, wr);
+          double dW[3];
+          for (int k = 0; k < 3; ++k) dW[k] = Aw[k] - Ab[k];
+          const double x = fma(Ab[3 + 2], dW[2], fma(Ab[3 + 1], dW[1], Ab[3] * dW[0]));
+          const double z = fma(Ab[3 + 6 + 2], dW[2], fma(Ab[3 + 6 + 1], dW[1], Ab[3 + 6] * dW[0]));
+          const double dBound = (z > 1.0) ? 0.4 * (z - 1.0) : 0.0;
+          const double f = k_clip(x - (0.25 + dBound), -0.5, 0.0) * 5.0;
+          double te[3], re[3], tr[3], rr[3];
+          k_jac_cols(c, jf, wr, Aw, te, re);
+          k_jac_cols(c, jf, base, Ab, tr, rr);
+          tmp = tmp + (te[0] - tr[0]) * f;
+        }
+        ex = (ex + tmp) * alphaEff;
+      }
+      // RcsGraph_checkJointSpeeds(dH_extra, dt, IK)
+      double sc = 1.0;
+      if (lane < nJ && jspeed < AFFK_NO_LIMIT) { const double a = fabs(ex), mx = jspeed * dt; if (a > mx) sc = mx / a; }
+      const double scale = w_min(sc);
+      if (scale < 1.0) ex = ex * (0.99999 * scale);
+      dHv = dHv + ex * phaseScale;
+    }
+    w_sync();   // J complete
+    // joint masks (:636-675)
+    {
+      int on = 0;
+      if (lane < nJ) for (int r = 0; r < m; ++r) if (J[r * JS + lane] != 0.0) on = 1;
+      const unsigned aMask = w_ballot(on);
+      jmaskBits |= aMask;
+      if (lane < nJ && !(((aMask | emask) >> lane) & 1u)) dHv = dHv * 0.0;
+    }
+    // ---- solveRightInverse
+    const double vv = (lane < nJ) ? jw * dHv : 0.0;
+    if (lane < nJ) dH[lane] = vv;          // v = W^-1 dH
+    if (lane < nJ) dq[lane] = jw;          // w, read by the entry lanes below
+    w_sync();
+    if (lane < m) {
+      double acc = dxv[lane];
+      for (int j = 0; j < nJ; ++j) acc = fma(J[lane * JS + j], dH[j], acc);
+      rhs[lane] = acc;
+    }
+    {
+      const int nEnt = m * (m + 1) / 2;
+      for (int ebase = 0; ebase < nEnt; ebase += 32) {
+        const int e = ebase + lane;
+        if (e < nEnt) {
+          // e -> (i, k), k <= i
+          int i = 0;
+          while ((i + 1) * (i + 2) / 2 <= e) ++i;
+          const int k = e - i * (i + 1) / 2;
+          double acc = 0.0;
+          for (int j = 0; j < nJ; ++j) acc = fma(J[i * JS + j] * dq[j], J[k * JS + j], acc);
+          if (i == k) acc = acc + lambda;
+          L[i * LS + k] = acc;
+        }
+      }
+    }
+    w_sync();
+    int singular = 0;
+    for (int j = 0; j < m; ++j) {
+      // column j: lane i >= j computes L[i][j]
+      double sdiag = L[j * LS + j];
+      for (int k = 0; k < j; ++k) sdiag = fma(-L[j * LS + k], L[j * LS + k], sdiag);
+      if (!(sdiag > 0.0)) { singular = 1; break; }
+      const double ljj = sqrt(sdiag);
+      double t = 0.0;
+      if (lane > j && lane < m) {
+        t = L[lane * LS + j];
+        for (int k = 0; k < j; ++k) t = fma(-L[lane * LS + k], L[j * LS + k], t);
+        t = t / ljj;
+      }
+      w_sync();
+      if (lane == j) L[j * LS + j] = ljj;
+      if (lane > j && lane < m) L[lane * LS + j] = t;
+      w_sync();
+    }
+    int ikRes = 0, id0 = -1, id1 = -1;
+    if (singular) {
+      ikRes = AFF_CODE_SINGULAR;
+    } else {
+      // forward substitution L y = rhs (lane i owns y[i]); column oriented
+      double yi = (lane < m) ? rhs[lane] : 0.0;
+      for (int i = 0; i < m; ++i) {
+        double yfin = 0.0;
+        if (lane == i) { yi = yi / L[i * LS + i]; yfin = yi; }
+        yfin = w_shfl(yfin, i);
+        if (lane > i && lane < m) yi = fma(-L[lane * LS + i], yfin, yi);
+      }
+      // backward substitution L^T z = y
+      for (int i = m - 1; i >= 0; --i) {
+        double zfin = 0.0;
+        if (lane == i) { yi = yi / L[i * LS + i]; zfin = yi; }
+        zfin = w_shfl(zfin, i);
+        if (lane < i) yi = fma(-L[i * LS + lane], zfin, yi);
+      }
+      if (lane < m) rhs[lane] = yi;
+      w_sync();
+      double dqv = 0.0;
+      if (lane < nJ) {
+        double acc = 0.0;
+        for (int i = 0; i < m; ++i) acc = fma(J[i * JS + lane], rhs[i], acc);
+        dqv = fma(jw, acc, -vv);
+      }
+      // speed and acceleration limits (:696-723)
+      {
+        double sc = 1.0;
+        if (lane < nJ && jspeed < AFFK_NO_LIMIT) { const double a = fabs(dqv), mx = jspeed * dt; if (a > mx) sc = mx / a; }
+        const double scale = w_min(sc);
+        if (scale < 1.0) dqv = dqv * (0.99999 * scale);
+      }
+      const double dynLim = -0.99 * qFilt + 1.0;
+      const double invdt = 1.0 / dt;
+      double qd = 0.0;
+      if (lane < nJ) {
+        qd = dqv * invdt;
+        if (jacc < AFFK_NO_LIMIT) {
+          const double lim = (dynLim * jacc) * dt;
+          const double dv = qd - qdot[lane];
+          if (dv > lim) qd = qdot[lane] + lim;
+          else if (dv < -lim) qd = qdot[lane] - lim;
+        }
+      }
+      w_sync();
+      if (lane < nJ) { qdot[lane] = qd; q[lane] = q[lane] + dqv; }
+      w_sync();
+      // integration, FK, collision model, checkState (:730-752)
+      k_fk(c, false);
+      cm = k_collision(c);
+      const unsigned fast = w_ballot(lane < nJ && jspeed < AFFK_NO_LIMIT && fabs(qd) > jspeed * 1.0);
+      const unsigned viol = w_ballot(lane < nJ && (q[lane] < jqmin || q[lane] > jqmax));
+      if (fast) ikRes = AFF_CODE_SPEED;
+      else if (viol) { ikRes = AFF_CODE_JOINT_LIMIT; id0 = w_popc(viol); }
+      else if (cm.minB1 >= 0 && cm.minDist < 0.001) { ikRes = AFF_CODE_COLLISION; id0 = cm.minB1; id1 = cm.minB2; }
+    }
+    if (ikRes != 0) {
+      if (success) { res.first_code = ikRes; res.first_fail_step = iter; }
+      success = 0; res.code = ikRes; res.fail_step = iter; res.fail_id0 = id0; res.fail_id1 = id1;
+    }
+    // ---- costs (:226-227)
+    {
+      double term = 0.0;
+      if (lane < nJ) {
+        const double dqc = q[lane] - jq0;
+        const double r = (dqc > 0.0) ? jqmax - jq0 : jq0 - jqmin;
+        const double u = dqc / r;
+        term = (0.5 * jwjl) * (u * u);
+      }
+      jlSum = jlSum + w_tree_sum(term);
+      collSum = collSum + cm.cost;
+    }
+    // ---- geometry of the new state; tracking error (:297-337)
+    w_sync();
+    if (lane < nTasks) k_task_geo(c, tasks + lane, geo + AFFK_GEO * lane, xcur);
+    w_sync();
+    if (success) {
+      double* dxe = dxv;   // stacked over all dims here
+      if (lane < nTasks && ((activeMask >> lane) & 1u)) k_task_dx(tasks + lane, geo + AFFK_GEO * lane, xcur, xdes, dxe + ldg(&tasks[lane].xoff));
+      w_sync();
+      double ev = -1.0; int ek = 0x7fffffff;
+      if (lane < xdim && ((activeMask >> myTask) & 1u)) { ev = fabs(dxe[lane]); ek = lane; }
+      w_max_keyed(ev, ek);
+      if (ev > err) err = ev;
+      if (err > AFFK_TRACK_MAX) {
+        int etask = -1, edim = -1;
+        if (ev > 0.0) for (int t = 0; t < nTasks; ++t) if (ek >= ldg(&tasks[t].xoff)) { etask = t; edim = ek - ldg(&tasks[t].xoff); }
+        success = 0; res.code = AFF_CODE_TRACKING; res.first_code = AFF_CODE_TRACKING;
+        res.first_fail_step = iter; res.fail_step = iter; res.fail_id0 = etask; res.fail_id1 = edim;
+      }
+      w_sync();
+    }
+    if (cm.minDist < res.min_dist) { res.min_dist = cm.minDist; res.min_dist_b1 = cm.minB1; res.min_dist_b2 = cm.minB2; }
+    if (qlog && lane < nJ && rows < qrows) qlog[(size_t)rows * nJ + lane] = q[lane];
+    rows++;
+  }
+  res.jl_cost = jlSum / (double)rows;
+  res.coll_cost = collSum / (double)rows;
+  res.success = success;
+  res.n_steps = rows;
+  res.track_err = err;
+  res.jmask_bits = (uint64_t)jmaskBits;
+  if (lane == 0) P.results[cand] = res;
+}
+
+// ------------------------------------------------- prologue (once per batch)
+// World transforms of the static nodes, world frames / AABBs of the static
+// shapes, and sin/cos of the constant joints.  One warp.
+AFF_DEV void k_prologue(const KPlan& P)
+{
+  const int lane = w_lane();
+  // sin / cos of constant joints
+  for (int n = lane; n < P.nStatic; n += 32) {
+    double s = 0.0, co = 1.0;
+    if (ldg(&P.stat[n].kind) == AFFK_NODE_JOINT_CONST && ldg(&P.stat[n].jtype) >= AFF_JNT_ROT_X) aff_sincos(ldg(&P.stat[n].qconst), &s, &co);
+    P.statSC[2 * n] = s; P.statSC[2 * n + 1] = co;
+  }
+  for (int n = lane; n < P.nDyn; n += 32) {
+    double s = 0.0, co = 1.0;
+    if (ldg(&P.dyn[n].kind) == AFFK_NODE_JOINT_CONST && ldg(&P.dyn[n].jtype) >= AFF_JNT_ROT_X) aff_sincos(ldg(&P.dyn[n].qconst), &s, &co);
+    P.dynSC[2 * n] = s; P.dynSC[2 * n + 1] = co;
+  }
+  if (lane < 12) P.statA[12 * P.nStatic + lane] = (lane == 3 || lane == 7 || lane == 11) ? 1.0 : 0.0;
+  w_sync();
+  // static nodes, parents first; element-parallel like k_fk
+  const int e = lane % 12;
+  for (int n = 0; n < P.nStatic; ++n) {
+    const KNode* nd = P.stat + n;
+    const int par = nd->parent;
+    const double* Pp = (par == AFFK_WORLD) ? P.statA + 12 * P.nStatic : P.statA + 12 * AFFK_STATIC_IDX(par);
+    double val = nd->identityT ? Pp[e] : k_compose_elem(nd->T, Pp, e);
+    int partner = lane, isA = 0, isB = 0;
+    const int kind = nd->kind, jt = nd->jtype;
+    if (kind == AFFK_NODE_JOINT_CONST) {
+      if (jt >= AFF_JNT_ROT_X && e >= 3) {
+        const int d = jt - AFF_JNT_ROT_X, a = (d + 1) % 3, b = (d + 2) % 3, row = (e - 3) / 3, col = (e - 3) % 3;
+        if (row == a) { isA = 1; partner = 3 + 3 * b + col; } else if (row == b) { isB = 1; partner = 3 + 3 * a + col; }
+      } else if (jt < AFF_JNT_ROT_X && e < 3) partner = 3 + 3 * jt + e;
+    }
+    const double other = w_shfl(val, partner);
+    if (kind == AFFK_NODE_JOINT_CONST) {
+      const double s = P.statSC[2 * n], co = P.statSC[2 * n + 1];
+      if (jt >= AFF_JNT_ROT_X) { if (isA) val = fma(s, other, co * val); else if (isB) val = fma(co, val, -(s * other)); }
+      else if (e < 3) val = fma(nd->qconst, other, val);
+    }
+    if (lane < 12) P.statA[12 * n + e] = val;
+    w_sync();
+  }
+  // static shapes
+  for (int s = lane; s < P.nStatShapes; s += 32) {
+    const KShape* sh = P.sshape + s;
+    const int ref = sh->node;
+    const double* An = (ref == AFFK_WORLD) ? P.statA + 12 * P.nStatic : P.statA + 12 * AFFK_STATIC_IDX(ref);
+    double W[12];
+    k_compose(W, sh->A_CB, An);
+    for (int k = 0; k < 12; ++k) P.sshapeA[12 * s + k] = W[k];
+  }
+  w_sync();
+  for (int b = lane; b < P.nStatBodies; b += 32) {
+    const KShapeBody* sb = P.sbody + b;
+    double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    for (int k = 0; k < sb->n_shapes; ++k) {
+      const KShape* sh = P.sshape + sb->first_shape + k;
+      if (!sh->active0) continue;
+      double smn[3], smx[3];
+      k_shape_aabb(sh->type, sh->ext, P.sshapeA + 12 * (sb->first_shape + k), smn, smx);
+      for (int q = 0; q < 3; ++q) { if (smn[q] < mn[q]) mn[q] = smn[q]; if (smx[q] > mx[q]) mx[q] = smx[q]; }
+    }
+    for (int q = 0; q < 3; ++q) { P.sbodyAABB[6 * b + q] = mn[q]; P.sbodyAABB[6 * b + 3 + q] = mx[q]; }
+  }
+}
+
+#endif

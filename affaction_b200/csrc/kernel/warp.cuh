@@ -1,0 +1,82 @@
+// Warp primitives used by rollout.cuh.
+//
+// CUDA build (the product): thin wrappers over the sm_100a intrinsics.
+// AFF_EMULATE build (tests/emu only, never linked into libaffpredict.so): the
+// same names are provided by a fiber-based 32-lane emulator so the kernel
+// source can be stepped on a CPU next to the oracle while debugging.
+#ifndef AFF_KERNEL_WARP_CUH
+#define AFF_KERNEL_WARP_CUH
+
+#if defined(AFF_EMULATE)
+
+#define AFF_DEV static inline
+int w_lane();
+void w_sync();
+double w_shfl(double v, int src);
+int w_shfl(int v, int src);
+double w_shfl_xor(double v, int mask);
+int w_shfl_xor(int v, int mask);
+unsigned w_ballot(int pred);
+template <class T> static inline T ldg(const T* p) { return *p; }
+static inline int w_popc(unsigned v) { return __builtin_popcount(v); }
+static inline int w_ffs(unsigned v) { return __builtin_ffs((int)v); }
+
+#else
+
+#define AFF_DEV __device__ __forceinline__
+AFF_DEV int w_lane() { return (int)(threadIdx.x & 31u); }
+AFF_DEV void w_sync() { __syncwarp(); }
+AFF_DEV double w_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+AFF_DEV int w_shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+AFF_DEV double w_shfl_xor(double v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
+AFF_DEV int w_shfl_xor(int v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
+AFF_DEV unsigned w_ballot(int pred) { return __ballot_sync(0xffffffffu, pred); }
+template <class T> AFF_DEV T ldg(const T* p) { return __ldg(p); }
+AFF_DEV int w_popc(unsigned v) { return __popc(v); }
+AFF_DEV int w_ffs(unsigned v) { return __ffs((int)v); }
+
+#endif
+
+// ---- reductions built from the primitives (identical in both builds) ----
+
+// Sum in the fixed pairwise order of the xor butterfly (offsets 16,8,4,2,1);
+// the oracle's tree_sum() reproduces this order.
+AFF_DEV double w_tree_sum(double v)
+{
+  for (int off = 16; off >= 1; off >>= 1) v = v + w_shfl_xor(v, off);
+  return v;
+}
+
+AFF_DEV double w_min(double v)
+{
+  for (int off = 16; off >= 1; off >>= 1) { const double o = w_shfl_xor(v, off); v = (o < v) ? o : v; }
+  return v;
+}
+
+AFF_DEV double w_max(double v)
+{
+  for (int off = 16; off >= 1; off >>= 1) { const double o = w_shfl_xor(v, off); v = (o > v) ? o : v; }
+  return v;
+}
+
+// Lexicographic minimum of (value, key): smallest value, ties -> smallest key.
+AFF_DEV void w_min_keyed(double& v, int& key)
+{
+  for (int off = 16; off >= 1; off >>= 1) {
+    const double ov = w_shfl_xor(v, off);
+    const int ok = w_shfl_xor(key, off);
+    if (ov < v || (ov == v && ok < key)) { v = ov; key = ok; }
+  }
+}
+
+// Lexicographic maximum of (value, -key): largest value, ties -> smallest key.
+AFF_DEV void w_max_keyed(double& v, int& key)
+{
+  for (int off = 16; off >= 1; off >>= 1) {
+    const double ov = w_shfl_xor(v, off);
+    const int ok = w_shfl_xor(key, off);
+    if (ov > v || (ov == v && ok < key)) { v = ov; key = ok; }
+  }
+}
+
+#endif

@@ -250,6 +250,12 @@ int aff_batch_last_launch_count(const aff_batch* b);
 /* Steps a full-length rollout of candidate i runs (nSteps). */
 int aff_batch_num_steps(const aff_batch* b, size_t cand);
 
+/* Bytes copied host->device when the batch was created, shared-memory bytes one
+ * rollout (warp) uses, and the persistent grid size. */
+size_t aff_batch_h2d_bytes(const aff_batch* b);
+size_t aff_batch_smem_bytes_per_warp(const aff_batch* b);
+int aff_batch_grid_blocks(const aff_batch* b);
+
 /* q(t) log of one candidate: (n_steps+1) rows of nJ doubles, jacobi-index
  * order; requires opts.log_q.  Returns rows written or <0. */
 int aff_batch_fetch_q(aff_batch* b, size_t cand, double* out, size_t max_rows);

@@ -1,0 +1,116 @@
+// TEST-ONLY 32-lane warp emulator.  NEVER linked into libaffpredict.so and
+// never used by the product: it exists so the kernel source
+// (affaction_b200/csrc/kernel/rollout.cuh) can be stepped on a CPU next to the
+// oracle when debugging, and so the CPU test tier can exercise the plan
+// compiler + kernel logic without a GPU.  Results obtained through it are not
+// GPU results and are never reported as such.
+//
+// Each lane is a ucontext fiber; w_sync() yields to a round-robin scheduler, so
+// a barrier completes when all 32 lanes have reached it.  Shuffles and ballots
+// exchange values through a 32-entry array between two barriers.
+#define AFF_EMULATE 1
+#include <ucontext.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "kernel/plan_build.h"
+
+static ucontext_t g_main, g_ctx[32];
+static int g_cur = 0;
+static bool g_done[32];
+static std::function<void()>* g_body = nullptr;
+static double g_xd[32];
+static int g_xi[32];
+static std::vector<char> g_stacks;
+
+int w_lane() { return g_cur; }
+void w_sync() { swapcontext(&g_ctx[g_cur], &g_main); }
+double w_shfl(double v, int src) { g_xd[g_cur] = v; w_sync(); const double r = g_xd[src & 31]; w_sync(); return r; }
+int w_shfl(int v, int src) { g_xi[g_cur] = v; w_sync(); const int r = g_xi[src & 31]; w_sync(); return r; }
+double w_shfl_xor(double v, int mask) { return w_shfl(v, g_cur ^ mask); }
+int w_shfl_xor(int v, int mask) { return w_shfl(v, g_cur ^ mask); }
+unsigned w_ballot(int pred)
+{
+  g_xi[g_cur] = pred ? 1 : 0;
+  w_sync();
+  unsigned m = 0u;
+  for (int i = 0; i < 32; ++i) if (g_xi[i]) m |= 1u << i;
+  w_sync();
+  return m;
+}
+
+#include "kernel/rollout.cuh"
+
+static void fiberEntry()
+{
+  (*g_body)();
+  g_done[g_cur] = true;
+  swapcontext(&g_ctx[g_cur], &g_main);
+}
+
+static void runWarp(std::function<void()> body)
+{
+  const size_t stackSize = 512 * 1024;
+  if (g_stacks.size() < 32 * stackSize) g_stacks.resize(32 * stackSize);
+  g_body = &body;
+  for (int l = 0; l < 32; ++l) {
+    g_done[l] = false;
+    getcontext(&g_ctx[l]);
+    g_ctx[l].uc_stack.ss_sp = g_stacks.data() + l * stackSize;
+    g_ctx[l].uc_stack.ss_size = stackSize;
+    g_ctx[l].uc_link = &g_main;
+    makecontext(&g_ctx[l], fiberEntry, 0);
+  }
+  bool any = true;
+  while (any) {
+    any = false;
+    for (int l = 0; l < 32; ++l) {
+      if (g_done[l]) continue;
+      g_cur = l;
+      swapcontext(&g_main, &g_ctx[l]);
+      any = true;
+    }
+  }
+}
+
+extern "C" int emu_predict_batch(const aff_scene_desc* scene, const aff_task_desc* tasks, size_t nTasks,
+                                 const aff_constraint* cons, size_t nCons, const aff_candidate* cands, size_t nCands,
+                                 const aff_opts* opts, aff_result* out, double* qlog, size_t qlogRows, char* errbuf, size_t errlen)
+{
+  affk::SceneModel model;
+  std::string e = model.init(scene);
+  affk::HostPlan H;
+  int rc = e.empty() ? AFF_OK : AFF_ERR_INVALID;
+  if (rc == AFF_OK) rc = affk::buildPlan(model, tasks, nTasks, cons, nCons, cands, nCands, *opts, H, e);
+  if (rc != AFF_OK) { if (errbuf && errlen) { std::strncpy(errbuf, e.c_str(), errlen - 1); errbuf[errlen - 1] = 0; } return rc; }
+  KPlan P = H.plan;
+  std::vector<double> statA(12 * (size_t)(P.nStatic + 1)), statSC(2 * (size_t)P.nStatic + 2), dynSC(2 * (size_t)P.nDyn + 2),
+      sshapeA(12 * (size_t)P.nStatShapes + 12), sbodyAABB(6 * (size_t)P.nStatBodies + 6);
+  std::vector<aff_result> results(nCands);
+  P.jq_init = H.jq_init.data(); P.jq0 = H.jq0.data(); P.jq_min = H.jq_min.data(); P.jq_max = H.jq_max.data();
+  P.jspeed = H.jspeed.data(); P.jacc = H.jacc.data(); P.jwjl = H.jwjl.data(); P.jwmetric = H.jwmetric.data();
+  P.j_node = H.j_node.data(); P.j_type = H.j_type.data(); P.dyn = H.dyn.data(); P.stat = H.stat.data();
+  P.statA = statA.data(); P.statSC = statSC.data(); P.dynSC = dynSC.data(); P.rounds = H.rounds.data();
+  P.dshape = H.dshape.data(); P.dbody = H.dbody.data(); P.sshape = H.sshape.data(); P.sbody = H.sbody.data();
+  P.sshapeA = sshapeA.data(); P.sbodyAABB = sbodyAABB.data(); P.always = H.always.data();
+  P.obj_node = H.obj_node.data(); P.obj_body = H.obj_body.data(); P.obj_q6 = H.obj_q6.data();
+  P.tasks = H.tasks.data(); P.vias = H.vias.data(); P.acts = H.acts.data(); P.gcons = H.gcons.data(); P.cands = H.cands.data();
+  P.results = results.data();
+  P.qlog = qlog; P.qlog_rows = qlog ? (int)qlogRows : 0;
+  runWarp([&]() { k_prologue(P); });
+  std::vector<double> sm((size_t)P.warp_doubles + 64);
+  for (size_t i = 0; i < nCands; ++i) {
+    std::fill(sm.begin(), sm.end(), 0.0);
+    runWarp([&]() { k_rollout(P, (int)i, sm.data()); });
+    out[i] = results[i];
+  }
+  if (getenv("AFF_EMU_VERBOSE"))
+    std::fprintf(stderr, "emu: nDyn %d nStatic %d rounds %d dynShapes %d dynBodies %d statBodies %d always %d warp smem %zu B\n",
+                 P.nDyn, P.nStatic, P.nRounds, P.nDynShapes, P.nDynBodies, P.nStatBodies, P.nAlways, H.smemBytesPerWarp);
+  return AFF_OK;
+}

@@ -1,0 +1,42 @@
+"""Binding of the TEST-ONLY warp emulator (tests/emu/libaffemu.so): the kernel
+source compiled for the CPU, used to check the plan compiler and kernel logic
+in the CPU test tier.  Not a product path and not a GPU result."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from affaction_b200 import Result, REPO_ROOT
+
+_lib = None
+
+
+def emu_lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(REPO_ROOT, "tests", "emu", "libaffemu.so")
+        if not os.path.isfile(path):
+            raise RuntimeError("%s missing: run `make emu`" % path)
+        _lib = C.CDLL(path)
+        vp, sz = C.c_void_p, C.c_size_t
+        _lib.emu_predict_batch.restype = C.c_int
+        _lib.emu_predict_batch.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, vp, vp, sz, vp, sz]
+    return _lib
+
+
+def predict(scene, batch, opts, first=0, count=None, log_q=False, n_steps=None):
+    """Run candidates [first, first+count) through the emulated kernel."""
+    n = batch.n_candidates - first if count is None else count
+    res = (Result * n)()
+    q = None
+    rows = 0
+    if log_q:
+        rows = n_steps + 1
+        q = np.zeros((n, rows, scene.nJ))
+    err = C.create_string_buffer(512)
+    rc = emu_lib().emu_predict_batch(scene.desc, batch.tasks_ptr, batch.n_tasks, batch.constraints_ptr, batch.n_constraints,
+                                     batch.candidate_ptr(first), n, C.byref(opts), res,
+                                     q.ctypes.data_as(C.c_void_p) if q is not None else None, rows, err, 512)
+    if rc != 0:
+        raise RuntimeError("emu_predict_batch failed (%d): %s" % (rc, err.value.decode()))
+    return list(res), q
