@@ -73,7 +73,7 @@ ABI_SYMBOLS = [
     "aff_default_opts", "aff_abi_version", "aff_last_error", "aff_device_count", "aff_scene_create", "aff_scene_destroy",
     "aff_scene_num_ik_joints", "aff_batch_create", "aff_batch_destroy", "aff_batch_launch", "aff_batch_results_device",
     "aff_batch_results", "aff_batch_last_launch_count", "aff_batch_num_steps", "aff_batch_fetch_q", "aff_predict_batch",
-    "aff_rank_results", "aff_measure_fp64_peak", "aff_batch_h2d_bytes", "aff_batch_smem_bytes_per_warp", "aff_batch_grid_blocks",
+    "aff_rank_results", "aff_measure_fp64_peak", "aff_batch_set_results_buffer", "aff_batch_h2d_bytes", "aff_batch_smem_bytes_per_warp", "aff_batch_grid_blocks",
 ]
 HOST_SYMBOLS = [
     "aff_host_last_error", "aff_host_scene_load", "aff_host_scene_destroy", "aff_host_scene_desc", "aff_host_num_bodies",
@@ -101,7 +101,7 @@ def lib():
         "aff_scene_num_ik_joints": (i32, [vp]),
         "aff_batch_create": (i32, [vp, vp, sz, vp, sz, vp, sz, vp, C.POINTER(vp)]), "aff_batch_destroy": (None, [vp]),
         "aff_batch_launch": (i32, [vp, vp]), "aff_batch_results_device": (vp, [vp]),
-        "aff_batch_results": (i32, [vp, vp, vp, sz]), "aff_batch_last_launch_count": (i32, [vp]),
+        "aff_batch_results": (i32, [vp, vp, vp, sz]), "aff_batch_set_results_buffer": (i32, [vp, vp]), "aff_batch_last_launch_count": (i32, [vp]),
         "aff_batch_num_steps": (i32, [vp, sz]), "aff_batch_fetch_q": (i32, [vp, sz, vp, sz]),
         "aff_predict_batch": (i32, [vp, vp, sz, vp, sz, vp, sz, vp, vp]), "aff_rank_results": (None, [vp, sz, vp]),
         "aff_measure_fp64_peak": (dbl, [i32, dbl]), "aff_batch_h2d_bytes": (sz, [vp]),
@@ -305,6 +305,9 @@ class DeviceBatch:
         res = (Result * self.n)()
         _check(lib().aff_batch_results(self.h, stream, res, self.n), "aff_batch_results")
         return list(res)
+
+    def set_results_buffer(self, device_ptr):
+        _check(lib().aff_batch_set_results_buffer(self.h, device_ptr), "aff_batch_set_results_buffer")
 
     @property
     def results_device_ptr(self):

@@ -227,14 +227,21 @@ int aff_batch_launch(aff_batch* b, void* stream)
   return AFF_OK;
 }
 
-void* aff_batch_results_device(aff_batch* b) { return b ? (void*)b->results.p : nullptr; }
+void* aff_batch_results_device(aff_batch* b) { return b ? (void*)b->plan.results : nullptr; }
+
+int aff_batch_set_results_buffer(aff_batch* b, void* device_ptr)
+{
+  if (!b) return fail(AFF_ERR_INVALID, "aff_batch_set_results_buffer: null batch");
+  b->plan.results = device_ptr ? (aff_result*)device_ptr : b->results.p;
+  return AFF_OK;
+}
 
 int aff_batch_results(aff_batch* b, void* stream, aff_result* out, size_t n)
 {
   if (!b || !out) return fail(AFF_ERR_INVALID, "aff_batch_results: null argument");
   if (n > (size_t)b->plan.nCands) n = (size_t)b->plan.nCands;
   cudaStream_t st = (cudaStream_t)stream;
-  CUDA_TRY(cudaMemcpyAsync(out, b->results.p, n * sizeof(aff_result), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out, b->plan.results, n * sizeof(aff_result), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return AFF_OK;
 }

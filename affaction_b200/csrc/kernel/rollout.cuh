@@ -657,13 +657,16 @@ AFF_DEV double k_pair_distance(const KCtx& c, int ia, int ib)
     } else {
       const KShapeBody* bb = P.sbody + (-1 - ib);
       const int fb = ldg(&bb->first_shape), nb = ldg(&bb->n_shapes);
+      const bool swapStatic = ldg(&bb->body) < ldg(&ba->body);
       for (int k2 = 0; k2 < nb; ++k2) {
         const KShape* s2 = P.sshape + fb + k2;
         if (!ldg(&s2->active0)) continue;
         double e2[3] = {ldg(&s2->ext[0]), ldg(&s2->ext[1]), ldg(&s2->ext[2])};
         double A2[12];
         for (int e = 0; e < 12; ++e) A2[e] = ldg(&P.sshapeA[12 * (fb + k2) + e]);
-        const double dd = k_shape_dist(t1, e1, shp + 12 * (fa + k1), ldg(&s2->type), e2, A2);
+        // argument order = ascending scene body id, as the CPU checker enumerates pairs
+        const double dd = swapStatic ? k_shape_dist(ldg(&s2->type), e2, A2, t1, e1, shp + 12 * (fa + k1))
+                                     : k_shape_dist(t1, e1, shp + 12 * (fa + k1), ldg(&s2->type), e2, A2);
         if (dd < dmin) dmin = dd;
       }
     }

@@ -1,0 +1,297 @@
+#!/usr/bin/env python3
+"""bench.py — candidate IK rollouts/sec of the action-feasibility predict path.
+
+  python bench.py --gpus N --steps K --warmup W            # CUDA arm
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle on host cores)
+
+Workload (BASELINE.json configs[4]): synthetic sweep of
+perturbed-goal `get` candidates in the reference's pizza scene, the three grasp
+variants the kernel supports in equal parts (PowerGrasp tomato_sauce_bottle,
+BallGrasp fresh_tomatoes, TopGrasp italian_seasoning_bowl), every rollout the
+full 1555 steps (no early exit).  One "step" = one pass of the predict path over
+one batch of ROLLOUTS_PER_GPU candidates per GPU.
+
+  value : rollouts/s with the candidate tables already resident in HBM
+          (kernel launches + NCCL verdict gather only), CUDA events, max over ranks
+  e2e   : the same metric through aff_predict_batch with HOST buffers in and out
+          (plan compile, H2D of the tables, kernels, D2H of the verdicts)
+  roofline: FP64 pipe (the path's bound); peak = DFMA rate measured
+          on this GPU in this run by aff_measure_fp64_peak
+  cpu_baseline / --impl reference: the CPU oracle (a port: the reference cannot
+          be built) on all host cores over a bounded sample
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+VARIANTS = ["get tomato_sauce_bottle", "get fresh_tomatoes", "get italian_seasoning_bowl"]
+PER_VARIANT = 9472                       # 4 x (148 SMs x 16 resident warps)
+ROLLOUTS_PER_GPU = PER_VARIANT * len(VARIANTS)
+STEPS_PER_ROLLOUT = 1555
+METRIC = "candidate IK rollouts/sec"
+UNIT = "rollouts/s"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def algorithmic_flops_per_rollout():
+    """FP64 flops one full-length rollout needs (FMA = 2), counted per step from
+    the problem dimensions of the pizza-scene `get` workload; the terms are
+    derived in DESIGN.md section 5.  Static bodies and unobservable work
+    (trajectories of inactive tasks) are not counted."""
+    nJ, chain, m = 23, 7, 8            # IK joints, joints per arm chain, active task rows
+    traj = 8 * 110                     # active dims x (window solve K~3.5 + evaluation)
+    task = 7 * 45 + 2 * 120            # x / dx of 7 tasks, two POLAR with acos/atan2/sincos
+    jac = 3 * chain * 45 + 2 * chain * 25 + 3      # one XYZ-type + one POLAR-type block + joints rows
+    nullsp = 6 * chain * 9 + nJ * 6    # elbow / wrist terms + joint-limit gradient
+    solve = 108 * 3 + m ** 3 // 3 + 2 * m * m + 2 * m * chain + 2 * m * chain   # sparse J W J^T, Cholesky, solves, rhs, dq
+    limits = nJ * 6
+    fk = 29 * 63 + nJ * 30             # dynamic nodes (compose + joint rotation) + sincos
+    coll = 14 * 57 + 66 * 75 + 24 * 150 + 300      # shape frames + AABBs, seg-seg pairs, seg-box pairs, broad phase
+    costs = nJ * 5 + 60
+    per_step = traj + task + jac + nullsp + solve + limits + fk + coll + costs
+    return per_step * STEPS_PER_ROLLOUT
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def make_batches(ab, scene, rank, per_variant):
+    batches = []
+    for v, cmd in enumerate(VARIANTS):
+        hb = ab.HostBatch(scene)
+        hb.add_perturbed(cmd, per_variant, seed0=0xAFFAC7 + (rank * len(VARIANTS) + v) * per_variant)
+        batches.append(hb)
+    return batches
+
+
+def cpu_arm(ab, scene, n_rollouts, threads):
+    """Oracle on `threads` host threads over the first n_rollouts candidates of the
+    workload (equal parts of the three variants). Returns (rollouts/s, seconds)."""
+    import oracle_binding as ob
+    per = max(1, n_rollouts // len(VARIANTS))
+    batches = make_batches(ab, scene, 0, per)
+    opts = ab.default_opts()
+    t0 = time.perf_counter()
+    for hb in batches:
+        ob.predict_batch(scene, hb, opts, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return per * len(VARIANTS) / dt, dt, per * len(VARIANTS)
+
+
+def run_reference(args, rank, world):
+    import affaction_b200 as ab
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    scene = ab.HostScene()
+    sample = max(len(VARIANTS), 12 * threads)      # a few seconds per step
+    for _ in range(args.warmup):
+        cpu_arm(ab, scene, len(VARIANTS) * threads, threads)
+    total, secs = 0, 0.0
+    for _ in range(args.steps):
+        _, dt, n = cpu_arm(ab, scene, sample, threads)
+        total += n
+        secs += dt
+    value = total / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic sweep of perturbed-goal get candidates, pizza scene, 3 grasp variants, 1555 steps each",
+                   "rollouts_per_step": sample, "note": "CPU oracle (restated reference; Rcs/Tropic are not vendored so the "
+                   "reference itself cannot be built), ConcurrentExecutor-style pool on all host threads"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d rollouts per step x %d steps" % (sample, args.steps)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_cuda(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import affaction_b200 as ab
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev_index = local_rank
+    scene = ab.HostScene()
+    per_variant = args.rollouts // len(VARIANTS) if args.rollouts else PER_VARIANT
+    n_local = per_variant * len(VARIANTS)
+    host_batches = make_batches(ab, scene, rank, per_variant)
+    opts = ab.default_opts()
+    stream = torch.cuda.current_stream().cuda_stream
+    rec = C.sizeof(ab.Result)
+
+    # ---- resident arm: candidate tables uploaded once, verdicts written into a torch buffer
+    dev_batches = [ab.DeviceBatch(scene, hb, opts, device=dev_index) for hb in host_batches]
+    verdicts = torch.empty(n_local * rec, dtype=torch.uint8, device="cuda")
+    gathered = torch.empty(world * n_local * rec, dtype=torch.uint8, device="cuda") if world > 1 else None
+    for i, db in enumerate(dev_batches):
+        db.set_results_buffer(verdicts.data_ptr() + i * per_variant * rec)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+
+    def one_step():
+        n_launch = 0
+        for db in dev_batches:
+            n_launch += db.launch(stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, verdicts)     # per-candidate verdicts and costs to every rank
+        return n_launch
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        one_step()
+    barrier()
+
+    sampler = ClockSampler(dev_index)
+    sampler.start()
+    kernel_ms, step_ms, launches = [], [], 0
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    for _ in range(args.steps):
+        flush.fill_(1)                  # L2 flush between timed iterations
+        barrier()
+        ev[0].record()
+        for db in dev_batches:
+            launches += db.launch(stream)
+        ev[1].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, verdicts)
+        ev[2].record()
+        barrier()
+        kernel_ms.append(ev[0].elapsed_time(ev[1]))
+        step_ms.append(ev[0].elapsed_time(ev[2]))
+    total_ms = sum(step_ms)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * n_local * args.steps / (total_ms * 1e-3)
+
+    # verdict mix of this rank's last step
+    res = (ab.Result * n_local).from_buffer_copy(verdicts.cpu().numpy().tobytes())
+    mix = {}
+    for r in res:
+        mix[ab.CODE_NAMES.get(r.code, str(r.code))] = mix.get(ab.CODE_NAMES.get(r.code, str(r.code)), 0) + 1
+
+    # ---- e2e arm: host buffers in, host verdicts out, through aff_predict_batch
+    e2e_steps = max(1, min(args.steps, 3))
+    ab.predict_batch(scene, host_batches[0], opts, device=dev_index)   # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        for hb in host_batches:
+            ab.predict_batch(scene, hb, opts, device=dev_index)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * n_local * e2e_steps / e2e_s
+    h2d = sum(db.h2d_bytes for db in dev_batches)
+    d2h = n_local * rec
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank == 0:
+        # roofline of the dominant kernel (aff_rollout_kernel), live CUDA-event timing of its launches
+        peak = ab.lib().aff_measure_fp64_peak(dev_index, 0.5)
+        flops = algorithmic_flops_per_rollout() * n_local
+        avg_kernel_s = (sum(kernel_ms) / len(kernel_ms)) * 1e-3
+        achieved = flops / avg_kernel_s * 1e-12
+        # bounded CPU sample on the box's host cores (N=1 only)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            v, secs, n = cpu_arm(ab, scene, max(len(VARIANTS), 16 * threads), threads)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "%d rollouts of the same workload in %.1f s (CPU oracle, %d threads)" % (n, secs, threads)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic sweep of perturbed-goal get candidates (BASELINE.json configs[4]), pizza scene, "
+                                   "PowerGrasp/BallGrasp/TopGrasp in equal parts, 1555 steps per rollout, no early exit",
+                       "rollouts_per_gpu_per_step": n_local, "steps_per_rollout": STEPS_PER_ROLLOUT,
+                       "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": "candidates sharded statically over %d GPU(s); NCCL all_gather of verdicts" % world,
+                       "verdict_mix_rank0": mix},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "call": "aff_predict_batch (plan compile + H2D + kernels + D2H, pageable host buffers)"},
+            "gpu_launches": launches * world,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None,
+                         "traffic": None, "kernel": "aff_rollout_kernel",
+                         "flops_per_rollout": algorithmic_flops_per_rollout(), "peak_source": "DFMA microbenchmark measured in this run "
+                         "(MEASURED_PEAKS.json holds no FP64 figure)", "kernel_ms_per_step": sum(kernel_ms) / len(kernel_ms)},
+            "cpu_baseline": cpu,
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--rollouts", type=int, default=0, help="rollouts per GPU per step (default %d)" % ROLLOUTS_PER_GPU)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the bounded CPU sample")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import __graft_entry__ as ge
+    if rank == 0 or not os.path.isfile(os.path.join(ROOT, "affaction_b200", "libaffpredict.so")):
+        ge.build()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_cuda(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -241,6 +241,9 @@ int aff_batch_launch(aff_batch* b, void* stream);
 
 /* Device pointer of the n_cands aff_result records (valid until destroy). */
 void* aff_batch_results_device(aff_batch* b);
+/* Make the kernel write its n_cands records into caller-owned device memory
+ * (e.g. the send buffer of an NCCL gather); NULL restores the internal buffer. */
+int aff_batch_set_results_buffer(aff_batch* b, void* device_ptr);
 /* Blocking copy of the results to host memory (the future.wait() join,
  * src/ActionComponent.cpp:202-205). */
 int aff_batch_results(aff_batch* b, void* stream, aff_result* out, size_t n);

@@ -56,6 +56,9 @@ int oracle_uses_libm(void) { return 0; }
 
 typedef struct { double org[3]; double rot[3][3]; } HTr;
 
+/* AFF_ORACLE_TRACE=n prints the task state every n steps (debugging aid) */
+static int g_trace = -1;
+
 /* ------------------------------------------------------------------ HTr ops */
 static void htr_identity(HTr* A)
 {
@@ -1306,7 +1309,7 @@ static int compute_ik(Pred* P, const int* a_des, const double* x_des, double dt,
   /* speed and acceleration limits (:696-723) */
   {
     const double scale = check_joint_speeds(g, P->dq, dt);
-    if (getenv("AFF_ORACLE_TRACE") && scale < 1.0) { int jm = 0; for (int c = 0; c < nJ; ++c) if (fabs(P->dq[c]) / d->joint_speed_limit[g->ikj[c]] > fabs(P->dq[jm]) / d->joint_speed_limit[g->ikj[jm]]) jm = c; fprintf(stderr, "   speed scale %.3f joint %d m %d\n", scale, jm, m); }
+    if (g_trace > 0 && scale < 1.0) { int jm = 0; for (int c = 0; c < nJ; ++c) if (fabs(P->dq[c]) / d->joint_speed_limit[g->ikj[c]] > fabs(P->dq[jm]) / d->joint_speed_limit[g->ikj[jm]]) jm = c; fprintf(stderr, "   speed scale %.3f joint %d m %d\n", scale, jm, m); }
     if (scale < 1.0) for (int c = 0; c < nJ; ++c) P->dq[c] = P->dq[c] * (0.99999 * scale);
     const double dynLim = -0.99 * qFilt + 1.0;
     const double invdt = 1.0 / dt;
@@ -1334,6 +1337,7 @@ int oracle_predict(const aff_scene_desc* scene, const aff_task_desc* tasks_all, 
                    const aff_candidate* cand, const aff_opts* opts, aff_result* out, double* q_log, size_t q_log_rows)
 {
   Pred P;
+  if (g_trace < 0) { const char* e = getenv("AFF_ORACLE_TRACE"); g_trace = e ? atoi(e) : 0; }
   memset(&P, 0, sizeof(P));
   memset(out, 0, sizeof(*out));
   out->first_fail_step = -1; out->fail_step = -1; out->fail_id0 = -1; out->fail_id1 = -1;
@@ -1429,7 +1433,7 @@ int oracle_predict(const aff_scene_desc* scene, const aff_task_desc* tasks_all, 
           out->first_fail_step = iter; out->fail_step = iter; out->fail_id0 = etask; out->fail_id1 = edim;
         }
       }
-      if (getenv("AFF_ORACLE_TRACE") && (iter % atoi(getenv("AFF_ORACLE_TRACE")) == 0)) {
+      if (g_trace > 0 && (iter % g_trace == 0)) {
         fprintf(stderr, "it %d t %.2f blend %.3f phase %.3f ik %d a[", iter, P.tc.tnow, blending, phaseScale, ikRes);
         for (int i = 0; i < P.nTasks; ++i) fprintf(stderr, "%d", a_des[i]);
         fprintf(stderr, "] ");

@@ -12,6 +12,7 @@
 #include <ucontext.h>
 
 #include <cstdio>
+#include <stdio.h>
 #include <cstdlib>
 #include <cstring>
 #include <functional>

@@ -55,17 +55,25 @@ def test_get_candidates_match_oracle(scene, cmd):
     assert worst == 0.0               # in fact bit-identical
 
 
-def test_ranked_first_matches_oracle(scene):
+@pytest.mark.parametrize("cmd", GET_COMMANDS)
+def test_ranked_first_matches_oracle(scene, cmd):
+    """aff_predict_batch (host buffers in / out) + PredictionResult::lesser ranking."""
     batch = ab.HostBatch(scene)
-    for cmd in GET_COMMANDS:
-        batch.add_action(cmd)
+    batch.add_action(cmd)
     opts = ab.default_opts()
     gpu = ab.predict_batch(scene, batch, opts)
     ref = ob.predict_batch(scene, batch, opts, n_threads=os.cpu_count() or 1)
     assert [r.as_tuple() for r in gpu] == [r.as_tuple() for r in ref]
     assert ab.rank(gpu) == ab.rank(ref)
-    best = gpu[ab.rank(gpu)[0]]
-    assert best.success == 1
+
+
+def test_too_many_objects_is_reported(scene):
+    """Capacity errors are loud, not silent fallbacks."""
+    batch = ab.HostBatch(scene)
+    for cmd in GET_COMMANDS[:3]:
+        batch.add_action(cmd)
+    with pytest.raises(ab.AffError, match="AFFK_MAX_OBJ"):
+        ab.predict_batch(scene, batch, ab.default_opts())
 
 
 def test_perturbed_sweep_matches_oracle(scene):
