@@ -22,7 +22,8 @@
 #define AFFK_MAX_OBJ 2        // re-parentable objects per candidate
 #define AFFK_MAX_DSHAPE 20    // shapes on dynamic nodes
 #define AFFK_MAX_DBODY 16     // shape bodies on dynamic nodes
-#define AFFK_MAX_LIVE 192     // body pairs in the collision model of one step
+#define AFFK_MAX_NEAR 64      // body pairs found by the AABB test in one step
+#define AFFK_MAX_PAIRS 512    // precompiled shape pairs per type list
 #define AFFK_MAX_VIA_UNK 6    // unknown polynomial coefficients per 1-D window
 #define AFFK_MAX_ROUNDS 40    // FK schedule rounds
 #define AFFK_VIA_STRIDE 49    // doubles of solver scratch per trajectory lane (6*7 matrix + 6 solution, odd stride)
@@ -52,7 +53,7 @@ struct KShape
 {
   int32_t type;        // AFF_SHAPE_*
   int32_t active0;     // RCSSHAPE_COMPUTE_DISTANCE at start
-  int32_t node;        // node reference of the owning body
+  int32_t node;        // dynamic shapes: shared-memory slot of the owning body; static shapes: node reference
   int32_t pad;
   double ext[3];
   double A_CB[12];
@@ -72,10 +73,16 @@ struct KShapeBody
   int32_t pad;
 };
 
+// Precompiled shape pair of the collision model.  a/b: shape indices, >= 0 dynamic
+// shape table, < 0 static shape table (-1 - idx).  Segment-segment list: `a` is
+// dynamic; KP_SWAP says it is the SECOND argument in ascending-body-id order.
+// Segment-box/cylinder list: `a` is the segment, `b` the box or cylinder.
+struct __attribute__((aligned(16))) KPair { int32_t a, b, key, meta; };
+
 struct KTask
 {
   int32_t kind;
-  int32_t eff, ref, frame;   // node references (frame already resolved: AFFK_WORLD = world)
+  int32_t eff, ref, frame;   // shared-memory slots, -1 = none / world (frame already resolved)
   int32_t axis;
   int32_t n_joints;
   int32_t jidx[AFF_MAX_TASK_JOINTS];  // jacobi index, or -1 - (static value slot) for constrained joints
@@ -87,7 +94,8 @@ struct KTask
 
 struct KVia { double t, x, xd, xdd; int32_t flag; int32_t pad; };
 struct KAct { double t, horizon; int32_t on; int32_t pad; };
-struct KGraphCon { double t; int32_t kind; int32_t on; int32_t slot; int32_t parent; };  // parent: node reference
+// parent_tree: broad-phase tree of the new parent, or -2-s if the parent hangs below object s
+struct KGraphCon { double t; int32_t kind; int32_t on; int32_t slot; int32_t parent; int32_t parent_slot; int32_t parent_tree; };
 
 struct KCand
 {
@@ -108,8 +116,7 @@ struct KPlan
 {
   int32_t nJ, nDyn, nStatic, nRounds, nObj;
   int32_t nDynShapes, nDynBodies, nStatShapes, nStatBodies, nTrees;
-  int32_t nAlways;                 // always-live body pairs (tree x tree, tree x explicit)
-  int32_t ns_base, ns_upperarm[2], ns_forearm[2], ns_hand[2];   // node references, AFFK_WORLD = absent
+  int32_t ns_base, ns_upperarm[2], ns_forearm[2], ns_hand[2];   // shared-memory slots, -1 = absent
   uint32_t rbj_static_chain;       // IK joints moving some non-object rigid-body-joint body
   double bp_threshold;
 
@@ -124,13 +131,23 @@ struct KPlan
   double* statA;                   // [nStatic*12] world transforms   (written by the prologue)
   double* statSC;                  // [nStatic*2]  sin/cos of constant joints
   double* dynSC;                   // [nDyn*2]     sin/cos of constant joints on dynamic nodes
-  const int32_t* rounds;           // [nRounds*2] FK schedule: two dynamic nodes per round, -1 = none
+  const int32_t* fkprog;           // [nRounds*2] packed FK program words: two nodes per round (KFK_* in rollout.cuh)
+  const double* dynT;              // [nDyn*12] fixed transform of each dynamic node
+  const double* dynQ;              // [nDyn] value of constant joints
+  const int32_t* statpar_ref;      // [nStatPar] static nodes copied into shared memory as parents
+  const int32_t* obj_parent_slot;  // [nObj] initial parent slot of each object
+  const int32_t* obj_parent_tree;  // [nObj] broad-phase tree of that parent
+  const uint32_t* dyn_chain;       // [nDyn] IK joints moving each dynamic node by construction
+  const int32_t* dyn_under;        // [nDyn] slot+1 if the node is a re-parentable object or below one
+  int32_t nStatPar;
 
   const KShape* dshape; const KShapeBody* dbody;   // dynamic
   const KShape* sshape; const KShapeBody* sbody;   // static
   double* sshapeA;                 // [nStatShapes*12] world shape frames (prologue)
   double* sbodyAABB;               // [nStatBodies*6]                      (prologue)
-  const int32_t* always;           // [nAlways*2]: dynamic body index, other body (>=0 dynamic, <0: -1-static index)
+  const KPair* pairsSS; const KPair* pairsSB;      // precompiled shape pairs by type
+  int32_t nSS, nSB;
+  double* sseg;                    // [nStatShapes*8] p(3), d(3), r, pad of static SSL / SPHERE shapes (prologue)
   const int32_t* obj_node;         // [nObj] dynamic node of each object slot
   const int32_t* obj_body;         // [nObj] scene body id
   const double* obj_q6;            // [nObj*6] scene values of the six rigid-body dofs
@@ -140,7 +157,7 @@ struct KPlan
 
   // shared-memory layout of one warp, in doubles from the warp base
   int32_t o_node, o_q, o_qdot, o_dH, o_dq, o_sn, o_cs, o_J, o_L, o_rhs, o_dx, o_st, o_xdes, o_xcur, o_geo,
-          o_objrel, o_objq6, o_shp, o_baabb, o_taabb, o_scratch, o_live, warp_doubles;
+          o_objrel, o_objq6, o_shp, o_baabb, o_taabb, o_scratch, o_live, o_chain, o_tdesc, o_rmask, warp_doubles;
   int32_t JS, LS;                  // row strides of J and L (odd: conflict-free column access)
 
   aff_opts opts;

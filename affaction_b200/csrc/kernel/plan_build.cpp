@@ -233,6 +233,29 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     for (int n = 0; n < nD; ++n) { const int r = roundOf[n]; H.rounds[2 * r + used[r]++] = n; }
     P.nRounds = nR;
   }
+  // ---- static parents get a shared-memory slot behind the dynamic nodes; FK program words
+  std::vector<int> statParSlot;   // static node index -> slot, built lazily
+  auto slotOfRef = [&](int ref) -> int {
+    if (ref >= 0) return ref;
+    for (size_t k = 0; k < H.statpar_ref.size(); ++k) if (H.statpar_ref[k] == ref) return (int)H.dyn.size() + (int)k;
+    H.statpar_ref.push_back(ref);
+    return (int)H.dyn.size() + (int)H.statpar_ref.size() - 1;
+  };
+  {
+    const int nD = (int)H.dyn.size();
+    H.dynT.resize(12 * (size_t)std::max(nD, 1)); H.dynQ.resize((size_t)std::max(nD, 1));
+    for (int n = 0; n < nD; ++n) { std::memcpy(&H.dynT[12 * n], H.dyn[n].T, sizeof(double) * 12); H.dynQ[n] = H.dyn[n].qconst; }
+    H.fkprog.assign(H.rounds.size(), 255);
+    for (size_t i = 0; i < H.rounds.size(); ++i) {
+      const int n = H.rounds[i];
+      if (n < 0) continue;
+      const KNode& nd = H.dyn[n];
+      const int pslot = slotOfRef(nd.parent);
+      const int ident = (nd.kind == AFFK_NODE_OBJECT) ? 0 : nd.identityT;
+      H.fkprog[i] = (int32_t)((uint32_t)n | ((uint32_t)pslot << 8) | ((uint32_t)nd.kind << 16) | ((uint32_t)nd.jtype << 18) |
+                              ((uint32_t)ident << 21) | ((uint32_t)(nd.qidx & 63) << 22));
+    }
+  }
   // objects below objects (a connect parent under another object) would need a dynamic schedule
   for (int b : objBodies) if (S.parent[b] >= 0 && underObj[S.parent[b]]) { err = "objects nested in objects are not supported"; return AFF_ERR_UNSUPPORTED; }
 
@@ -259,17 +282,76 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   };
   for (int b = 0; b < nB; ++b) if (shapeBody[b]) addShapes(b, dynamicB[b] != 0);
   if ((int)H.dshape.size() > AFFK_MAX_DSHAPE || (int)H.dbody.size() > AFFK_MAX_DBODY) { err = "too many dynamic shapes"; return AFF_ERR_CAPACITY; }
-  for (size_t i = 0; i < H.dbody.size(); ++i) {
-    const KShapeBody& a = H.dbody[i];
-    const bool aTree = a.tree >= 0 || a.obj_slot;
-    for (size_t j = i + 1; j < H.dbody.size(); ++j) {
-      const KShapeBody& b = H.dbody[j];
-      const bool bTree = b.tree >= 0 || b.obj_slot;
-      if (!aTree && !bTree) continue;
-      if (a.tree >= 0 && b.tree >= 0 && a.tree == b.tree && !a.obj_slot && !b.obj_slot) continue;
-      H.always.push_back((int)i); H.always.push_back((int)j);
+  // ---- precompiled shape pairs of the collision model, by type.  A body pair is listed when it can
+  // ever be live without the AABB test: two dynamic bodies that are (or may come to be) in different
+  // trees or one of which is explicit / an object, and dynamic tree bodies against explicit static bodies.
+  {
+    auto isSeg = [](int t) { return t == AFF_SHAPE_SSL || t == AFF_SHAPE_SPHERE; };
+    auto metaOf = [&](const KShapeBody& A, int idxA, bool actA, const KShapeBody& B, int idxB, bool actB, bool swap) {
+      uint32_t m = 0;
+      m |= (uint32_t)(A.toggle_slot ? A.toggle_slot : A.obj_slot) & 3u;
+      m |= ((uint32_t)(B.toggle_slot ? B.toggle_slot : B.obj_slot) & 3u) << 2;
+      m |= (swap ? 1u : 0u) << 4;
+      m |= ((uint32_t)(A.tree + 1) & 15u) << 9;
+      m |= ((uint32_t)(B.tree + 1) & 15u) << 13;
+      m |= (A.explicit_bp ? 1u : 0u) << 17;
+      m |= (B.explicit_bp ? 1u : 0u) << 18;
+      m |= (actA ? 1u : 0u) << 19;
+      m |= (actB ? 1u : 0u) << 20;
+      m |= ((uint32_t)idxA & 31u) << 21;
+      m |= ((uint32_t)idxB & 31u) << 26;
+      // fixed membership and always paired: both in (different) trees, or one in a tree and the other explicit
+      const bool objInvolved = A.obj_slot || B.obj_slot;
+      const bool always = !objInvolved && ((A.tree >= 0 && B.tree >= 0) || (A.tree >= 0 && B.explicit_bp) || (B.tree >= 0 && A.explicit_bp));
+      if (!always) m |= 1u << 31;
+      return (int32_t)m;
+    };
+    // body-level candidates: (dynamic body index, other: >= 0 dynamic, < 0 static)
+    auto addBodyPair = [&](int ia, int ib) {
+      const KShapeBody& A = H.dbody[ia];
+      const KShapeBody& B = ib >= 0 ? H.dbody[ib] : H.sbody[-1 - ib];
+      const std::vector<KShape>& shA = H.dshape;
+      const std::vector<KShape>& shB = ib >= 0 ? H.dshape : H.sshape;
+      const bool aFirst = A.body < B.body;      // canonical argument order: ascending scene body id
+      const int key = aFirst ? ((A.body << 15) | B.body) : ((B.body << 15) | A.body);
+      for (int k1 = 0; k1 < A.n_shapes; ++k1)
+        for (int k2 = 0; k2 < B.n_shapes; ++k2) {
+          const KShape& s1 = shA[A.first_shape + k1];
+          const KShape& s2 = shB[B.first_shape + k2];
+          const int i1 = A.first_shape + k1;
+          const int i2 = ib >= 0 ? B.first_shape + k2 : -1 - (B.first_shape + k2);
+          KPair pr;
+          pr.key = key;
+          if (isSeg(s1.type) && isSeg(s2.type)) {
+            pr.a = i1; pr.b = i2;
+            pr.meta = metaOf(A, ia, s1.active0 != 0, B, ib >= 0 ? ib : 31, s2.active0 != 0, !aFirst);
+            H.pairsSS.push_back(pr);
+          } else if (isSeg(s1.type)) {
+            pr.a = i1; pr.b = i2;
+            pr.meta = metaOf(A, ia, s1.active0 != 0, B, ib >= 0 ? ib : 31, s2.active0 != 0, false);
+            H.pairsSB.push_back(pr);
+          } else if (isSeg(s2.type)) {
+            pr.a = i2; pr.b = i1;      // the segment goes first; meta keeps A/B = body roles of (a, b)
+            pr.meta = metaOf(B, ib >= 0 ? ib : 31, s2.active0 != 0, A, ia, s1.active0 != 0, false);
+            H.pairsSB.push_back(pr);
+          }
+          // box/cylinder against box/cylinder: no distance function, never part of any result
+        }
+    };
+    for (size_t i = 0; i < H.dbody.size(); ++i) {
+      const KShapeBody& a = H.dbody[i];
+      const bool aTree = a.tree >= 0 || a.obj_slot;
+      for (size_t j = i + 1; j < H.dbody.size(); ++j) {
+        const KShapeBody& b = H.dbody[j];
+        const bool bTree = b.tree >= 0 || b.obj_slot;
+        if (!aTree && !bTree) continue;
+        if (a.tree >= 0 && b.tree >= 0 && a.tree == b.tree && !a.obj_slot && !b.obj_slot) continue;
+        addBodyPair((int)i, (int)j);
+      }
+      if (aTree) for (size_t j = 0; j < H.sbody.size(); ++j) if (H.sbody[j].explicit_bp && H.sbody[j].any_active0) addBodyPair((int)i, -1 - (int)j);
     }
-    if (aTree) for (size_t j = 0; j < H.sbody.size(); ++j) if (H.sbody[j].explicit_bp) { H.always.push_back((int)i); H.always.push_back(-1 - (int)j); }
+    if (H.pairsSS.size() > AFFK_MAX_PAIRS || H.pairsSB.size() > AFFK_MAX_PAIRS) { err = "too many precompiled collision pairs"; return AFF_ERR_CAPACITY; }
+    if (H.dbody.size() > 31) { err = "too many dynamic shape bodies"; return AFF_ERR_CAPACITY; }
   }
 
   // ---- joints (jacobi order)
@@ -281,6 +363,8 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   for (int s = 0; s < nObj; ++s) {
     const int b = objBodies[s];
     H.obj_node.push_back(bodyRef[b]); H.obj_body.push_back(b);
+    H.obj_parent_slot.push_back(slotOfRef(H.dyn[bodyRef[b]].parent));
+    H.obj_parent_tree.push_back(S.parent[b] >= 0 ? treeB[S.parent[b]] : -1);
     for (int k = 0; k < 6; ++k) H.obj_q6.push_back(S.qInit[S.firstJoint[b] + k]);
   }
 
@@ -292,9 +376,9 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     std::memset(&k, 0, sizeof(k));
     if (t.kind < AFF_TASK_XYZ || t.kind > AFF_TASK_JOINTS) { err = "unsupported task kind"; return AFF_ERR_UNSUPPORTED; }
     k.kind = t.kind; k.axis = (t.axis >= 0 && t.axis < 3) ? t.axis : 2;
-    k.eff = t.effector >= 0 ? bodyRef[t.effector] : AFFK_WORLD;
-    k.ref = t.ref_body >= 0 ? bodyRef[t.ref_body] : AFFK_WORLD;
-    k.frame = (t.ref_frame == -2) ? AFFK_WORLD : (t.ref_frame >= 0 ? bodyRef[t.ref_frame] : k.ref);
+    k.eff = t.effector >= 0 ? slotOfRef(bodyRef[t.effector]) : -1;
+    k.ref = t.ref_body >= 0 ? slotOfRef(bodyRef[t.ref_body]) : -1;
+    k.frame = (t.ref_frame == -2) ? -1 : (t.ref_frame >= 0 ? slotOfRef(bodyRef[t.ref_frame]) : k.ref);
     if (t.kind != AFF_TASK_JOINTS && t.effector < 0) { err = "task without effector"; return AFF_ERR_INVALID; }
     // a reference to the world origin itself cannot be told apart from "no reference": forbid bodies aliased to world
     if (t.kind == AFF_TASK_JOINTS) {
@@ -398,6 +482,9 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
       if (cc[k].kind != AFF_CON_CONNECT && cc[k].kind != AFF_CON_COLLISION) continue;
       KGraphCon g; g.t = cc[k].t; g.kind = cc[k].kind; g.on = cc[k].flag ? 1 : 0; g.slot = objSlotOfBody[cc[k].body_a];
       g.parent = (cc[k].kind == AFF_CON_CONNECT) ? bodyRef[cc[k].body_b] : AFFK_WORLD;
+      g.parent_slot = (cc[k].kind == AFF_CON_CONNECT) ? slotOfRef(g.parent) : 0;
+      g.parent_tree = -1;
+      if (cc[k].kind == AFF_CON_CONNECT) g.parent_tree = underObj[cc[k].body_b] ? -2 - (underObj[cc[k].body_b] - 1) : treeB[cc[k].body_b];
       if (cc[k].kind == AFF_CON_CONNECT && cc[k].body_b >= 0 && underObj[cc[k].body_b] == g.slot + 1) { err = "connect onto the object's own subtree"; return AFF_ERR_INVALID; }
       H.gcons.push_back(g);
     }
@@ -411,8 +498,9 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   P.nJ = S.nJ; P.nDyn = (int)H.dyn.size(); P.nStatic = (int)H.stat.size(); P.nObj = nObj;
   P.nDynShapes = (int)H.dshape.size(); P.nDynBodies = (int)H.dbody.size();
   P.nStatShapes = (int)H.sshape.size(); P.nStatBodies = (int)H.sbody.size();
-  P.nTrees = (int)S.bpTree.size(); P.nAlways = (int)H.always.size() / 2;
-  auto refOf = [&](int b) { return b >= 0 ? bodyRef[b] : AFFK_WORLD; };
+  P.nTrees = (int)S.bpTree.size(); P.nSS = (int)H.pairsSS.size(); P.nSB = (int)H.pairsSB.size();
+  auto refOf = [&](int b) { return b >= 0 ? slotOfRef(bodyRef[b]) : -1; };
+  for (const KNode& nd : H.dyn) { H.dyn_chain.push_back(nd.chain); H.dyn_under.push_back(nd.under_obj); }
   P.ns_base = refOf(S.ns_base);
   for (int k = 0; k < 2; ++k) { P.ns_upperarm[k] = refOf(S.ns_upperarm[k]); P.ns_forearm[k] = refOf(S.ns_forearm[k]); P.ns_hand[k] = refOf(S.ns_hand[k]); }
   P.rbj_static_chain = rbjStatic;
@@ -423,20 +511,26 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   // ---- shared-memory layout (doubles)
   int o = 0;
   auto take = [&](int n) { const int at = o; o += n; return at; };
-  P.o_node = take(12 * std::max(P.nDyn, 1));
+  P.nStatPar = (int)H.statpar_ref.size();
+  if (P.nDyn + P.nStatPar > 250) { err = "too many FK node slots"; return AFF_ERR_CAPACITY; }
+  P.o_node = take(12 * std::max(P.nDyn + P.nStatPar, 1));
   P.o_q = take(32); P.o_qdot = take(32); P.o_dH = take(32); P.o_dq = take(32); P.o_sn = take(32); P.o_cs = take(32);
   P.o_dx = take(AFFK_MAX_XDIM);
   P.o_st = take(3 * std::max(H.maxXdim, 1));
   P.o_xdes = take(AFFK_MAX_XDIM); P.o_xcur = take(AFFK_MAX_XDIM);
   P.o_geo = take(12 * AFFK_MAX_TASKS);
   P.o_objrel = take(12 * AFFK_MAX_OBJ); P.o_objq6 = take(6 * AFFK_MAX_OBJ);
+  P.o_chain = take((P.nDyn + P.nStatPar + 1) / 2 + 1);      // uint32 per slot
+  P.o_tdesc = take(4 * AFFK_MAX_TASKS);                      // 8 ints per task
+  P.o_rmask = take(AFFK_MAX_XDIM / 2);                       // uint32 per J row
   // union region: trajectory solver scratch | J, L, rhs | collision scratch
   const int uBase = o;
   P.JS = (S.nJ | 1); P.LS = (H.maxXdim | 1);
   const int uTraj = AFFK_VIA_STRIDE * std::max(H.maxXdim, 1);
   const int mRows = std::max(H.maxXdim, 1);
   const int uIk = mRows * P.JS + mRows * P.LS + mRows;
-  const int uColl = 12 * std::max(P.nDynShapes, 1) + 6 * std::max(P.nDynBodies, 1) + 6 * std::max(P.nTrees, 1) + AFFK_MAX_LIVE;
+  // live list (2*MAX_NEAR ints) + body trees (MAX_DBODY ints) + costly-pair scratch (32 ints + 32 doubles)
+  const int uColl = 12 * std::max(P.nDynShapes, 1) + 6 * std::max(P.nDynBodies, 1) + 6 * std::max(P.nTrees, 1) + AFFK_MAX_NEAR + AFFK_MAX_DBODY / 2 + 16 + 32;
   P.o_scratch = uBase;
   P.o_J = uBase; P.o_L = uBase + mRows * P.JS; P.o_rhs = P.o_L + mRows * P.LS;
   P.o_shp = uBase; P.o_baabb = P.o_shp + 12 * std::max(P.nDynShapes, 1); P.o_taabb = P.o_baabb + 6 * std::max(P.nDynBodies, 1);

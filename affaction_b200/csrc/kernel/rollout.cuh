@@ -79,52 +79,38 @@ AFF_DEV void k_apply_joint(double* A, int type, double q)
 }
 
 // ------------------------------------------------------------------ context
+// Every body frame the step loop touches lives in shared memory as a "slot":
+// slots [0, nDyn) are the dynamic nodes, the following ones are copies of the
+// static frames the loop refers to (parents of dynamic nodes, task reference
+// bodies, base_footprint ...), made once per rollout.  -1 means "none / world".
 struct KCtx
 {
   const KPlan* P;
   const KCand* C;
   double* sm;        // warp base in shared memory
+  double* nodes;     // [nSlots][12]
+  unsigned* chain;   // [nSlots] IK joints (bit = jacobi index) that currently move the slot
+  int* tdesc;        // [nTasks][8] kind, eff, ref, frame, axis, xoff, dim, n_joints
   int lane;
   // re-parentable objects (warp-uniform)
-  int objParent[AFFK_MAX_OBJ];
+  int objParentSlot[AFFK_MAX_OBJ];
+  int objParentDynamic[AFFK_MAX_OBJ];
   unsigned objChain[AFFK_MAX_OBJ];
   int objTree[AFFK_MAX_OBJ];
   int objMode[AFFK_MAX_OBJ];    // 0 per-shape flags, 1 all on, 2 all off
   unsigned objHasRel;
 };
 
-AFF_DEV double* k_node(const KCtx& c, int n) { return c.sm + c.P->o_node + 12 * n; }
-AFF_DEV const double* k_ref(const KCtx& c, int ref)
-{
-  if (ref >= 0) return c.sm + c.P->o_node + 12 * ref;
-  if (ref == AFFK_WORLD) return c.P->statA + 12 * c.P->nStatic;   // identity slot
-  return c.P->statA + 12 * AFFK_STATIC_IDX(ref);
-}
-AFF_DEV unsigned k_chain(const KCtx& c, int ref)
-{
-  if (ref < 0) return 0u;
-  const KNode* n = c.P->dyn + ref;
-  unsigned m = ldg(&n->chain);
-  const int uo = ldg(&n->under_obj);
-  if (uo) m |= c.objChain[uo - 1];
-  return m;
-}
-AFF_DEV int k_tree_of_node(const KCtx& c, int ref)
-{
-  if (ref < 0) return -1;
-  const KNode* n = c.P->dyn + ref;
-  const int uo = ldg(&n->under_obj);
-  return uo ? c.objTree[uo - 1] : ldg(&n->tree);
-}
+AFF_DEV const double* k_slot(const KCtx& c, int slot) { return c.nodes + 12 * slot; }
 
-// Jacobian columns of this lane's IK joint for a point p fixed to node `ref`.
+// Jacobian columns of this lane's IK joint for a point p fixed to the body in `slot`.
 struct KJointFrame { double ax[3]; double org[3]; int type; int valid; };
 
-AFF_DEV void k_jac_cols(const KCtx& c, const KJointFrame& jf, int ref, const double* p, double* colT, double* colR)
+AFF_DEV void k_jac_cols(const KCtx& c, const KJointFrame& jf, int slot, const double* p, double* colT, double* colR)
 {
   colT[0] = colT[1] = colT[2] = 0.0;
   colR[0] = colR[1] = colR[2] = 0.0;
-  if (!jf.valid || !((k_chain(c, ref) >> c.lane) & 1u)) return;
+  if (slot < 0 || !jf.valid || !((c.chain[slot] >> c.lane) & 1u)) return;
   if (jf.type < AFF_JNT_ROT_X) { colT[0] = jf.ax[0]; colT[1] = jf.ax[1]; colT[2] = jf.ax[2]; }
   else {
     double r[3];
@@ -139,71 +125,116 @@ AFF_DEV void k_jac_cols(const KCtx& c, const KJointFrame& jf, int ref, const dou
 AFF_DEV void k_object_from_q6(const KCtx& c, int n, int slot)
 {
   double A[12];
-  const double* Pp = k_ref(c, c.objParent[slot]);
+  const double* Pp = k_slot(c, c.objParentSlot[slot]);
   for (int e = 0; e < 12; ++e) A[e] = Pp[e];
   const double* q6 = c.sm + c.P->o_objq6 + 6 * slot;
   for (int k = 0; k < 6; ++k) k_apply_joint(A, k, q6[k]);
-  double* out = k_node(c, n);
+  double* out = c.nodes + 12 * n;
   for (int e = 0; e < 12; ++e) out[e] = A[e];
 }
 
-// RcsGraph_setState for the dynamic nodes. `all` = also nodes that only change
-// at initialisation (objects resting on static parents).
-AFF_DEV void k_fk(const KCtx& c, bool init)
+// Per-lane constants of the element-parallel FK (lane -> HTr element e of group grp).
+struct KFkLane
+{
+  int tBase;       // first T element of the 3-term product
+  int pCol;        // column offset into the parent's rot rows (P[3+pCol], P[6+pCol], P[9+pCol])
+  int isOrg;       // e < 3: add P[e]
+  int e;           // element index, 12 = idle lane
+  unsigned rot;    // per rotation axis d: bits [7d..7d+4] partner lane, [7d+5] role A, [7d+6] role B
+  unsigned trans;  // per translation axis d: bits [5d..5d+4] partner lane (valid for e < 3)
+};
+
+AFF_DEV KFkLane k_fk_lane(int lane)
+{
+  KFkLane L;
+  const int grp = lane / 12, e = (grp < 2) ? lane % 12 : 12;
+  L.e = e; L.isOrg = e < 3; L.rot = 0u; L.trans = 0u;
+  if (e < 3) { L.tBase = 0; L.pCol = e; }
+  else if (e < 12) { L.tBase = 3 + 3 * ((e - 3) / 3); L.pCol = (e - 3) % 3; }
+  else { L.tBase = 0; L.pCol = 0; }
+  for (int d = 0; d < 3; ++d) {
+    unsigned partner = (unsigned)lane, ra = 0u, rb = 0u;
+    if (e >= 3 && e < 12) {
+      const int a = (d + 1) % 3, b = (d + 2) % 3, row = (e - 3) / 3, col = (e - 3) % 3;
+      if (row == a) { ra = 1u; partner = (unsigned)(grp * 12 + 3 + 3 * b + col); }
+      else if (row == b) { rb = 1u; partner = (unsigned)(grp * 12 + 3 + 3 * a + col); }
+    }
+    L.rot |= (partner | (ra << 5) | (rb << 6)) << (7 * d);
+    const unsigned tp = (e < 3) ? (unsigned)(grp * 12 + 3 + 3 * d + e) : (unsigned)lane;
+    L.trans |= tp << (5 * d);
+  }
+  return L;
+}
+
+// FK program word (plan_build.cpp): one per (round, group)
+#define KFK_NODE(w) ((w) & 255)               /* 255 = empty slot */
+#define KFK_PARENT(w) (((w) >> 8) & 255)      /* shared-memory slot of the parent */
+#define KFK_KIND(w) (((w) >> 16) & 3)
+#define KFK_JTYPE(w) (((w) >> 18) & 7)
+#define KFK_IDENT(w) (((w) >> 21) & 1)
+#define KFK_QIDX(w) (((w) >> 22) & 63)
+
+// RcsGraph_setState for the dynamic nodes: 12 lanes per node (one per HTr element), two nodes
+// per round on the host-built schedule; all parents are shared-memory slots.
+AFF_DEV void k_fk(const KCtx& c, const KFkLane& L, bool init)
 {
   const KPlan& P = *c.P;
   double* sn = c.sm + P.o_sn; double* cs = c.sm + P.o_cs;
   const double* q = c.sm + P.o_q;
+  double* nodes = c.nodes;
   if (c.lane < P.nJ) { double s, co; aff_sincos(q[c.lane], &s, &co); sn[c.lane] = s; cs[c.lane] = co; }
   w_sync();
-  const int grp = c.lane / 12, e = c.lane % 12;
+  const int grp = c.lane / 12;
   for (int r = 0; r < P.nRounds; ++r) {
-    const int n = (grp < 2) ? ldg(&P.rounds[2 * r + grp]) : -1;
+    const unsigned w = (grp < 2) ? (unsigned)ldg(&P.fkprog[2 * r + grp]) : 255u;
+    const int n = (int)KFK_NODE(w);
     double val = 0.0;
-    int kind = -1, jtype = 0, partner = c.lane, isA = 0, isB = 0;
+    const int kind = (int)KFK_KIND(w), jtype = (int)KFK_JTYPE(w);
+    bool store = false;
     double s = 0.0, co = 1.0, qv = 0.0;
-    bool skip = true;
-    if (n >= 0) {
-      const KNode* nd = P.dyn + n;
-      kind = ldg(&nd->kind);
+    if (n != 255 && L.e < 12) {
+      const double* Pp = nodes + 12 * (int)KFK_PARENT(w);
+      const double* T = P.dynT + 12 * n;
+      bool doCompose = true, tShared = false;
       if (kind == AFFK_NODE_OBJECT) {
-        const int slot = ldg(&nd->qidx);
-        if ((c.objHasRel >> slot) & 1u) {
-          val = k_compose_elem(c.sm + P.o_objrel + 12 * slot, k_ref(c, c.objParent[slot]), e);
-          skip = false;
-        } else if (init || c.objParent[slot] >= 0) {
-          if (e == 0) k_object_from_q6(c, n, slot);
-        }
-      } else {
-        const double* Pp = k_ref(c, ldg(&nd->parent));
-        val = ldg(&nd->identityT) ? Pp[e] : k_compose_elem(nd->T, Pp, e);
-        skip = false;
-        if (kind == AFFK_NODE_JOINT_IK || kind == AFFK_NODE_JOINT_CONST) {
-          jtype = ldg(&nd->jtype);
-          if (kind == AFFK_NODE_JOINT_IK) { const int qi = ldg(&nd->qidx); s = sn[qi]; co = cs[qi]; qv = q[qi]; }
-          else { s = ldg(&P.dynSC[2 * n]); co = ldg(&P.dynSC[2 * n + 1]); qv = ldg(&nd->qconst); }
-          if (jtype >= AFF_JNT_ROT_X && e >= 3) {
-            const int d = jtype - AFF_JNT_ROT_X, a = (d + 1) % 3, b = (d + 2) % 3;
-            const int row = (e - 3) / 3, col = (e - 3) % 3;
-            if (row == a) { isA = 1; partner = grp * 12 + 3 + 3 * b + col; }
-            else if (row == b) { isB = 1; partner = grp * 12 + 3 + 3 * a + col; }
-          } else if (jtype < AFF_JNT_ROT_X && e < 3) {
-            partner = grp * 12 + 3 + 3 * jtype + e;   // axis component for the translation
-          }
+        const int slot = (int)KFK_QIDX(w);
+        Pp = nodes + 12 * c.objParentSlot[slot];
+        if ((c.objHasRel >> slot) & 1u) tShared = true;
+        else {
+          doCompose = false;
+          if ((init || c.objParentDynamic[slot]) && L.e == 0) k_object_from_q6(c, n, slot);
         }
       }
+      if (doCompose) {
+        store = true;
+        if (KFK_IDENT(w)) val = Pp[L.e];
+        else {
+          const double acc0 = L.isOrg ? Pp[L.e] : 0.0;
+          double t0, t1, t2;
+          if (tShared) { const double* R = c.sm + P.o_objrel + 12 * (int)KFK_QIDX(w); t0 = R[L.tBase]; t1 = R[L.tBase + 1]; t2 = R[L.tBase + 2]; }
+          else { t0 = ldg(&T[L.tBase]); t1 = ldg(&T[L.tBase + 1]); t2 = ldg(&T[L.tBase + 2]); }
+          val = fma(t2, Pp[9 + L.pCol], fma(t1, Pp[6 + L.pCol], fma(t0, Pp[3 + L.pCol], acc0)));
+        }
+        if (kind == AFFK_NODE_JOINT_IK) { const int qi = (int)KFK_QIDX(w); s = sn[qi]; co = cs[qi]; qv = q[qi]; }
+        else if (kind == AFFK_NODE_JOINT_CONST) { s = ldg(&P.dynSC[2 * n]); co = ldg(&P.dynSC[2 * n + 1]); qv = ldg(&P.dynQ[n]); }
+      }
     }
+    const bool isJoint = store && (kind == AFFK_NODE_JOINT_IK || kind == AFFK_NODE_JOINT_CONST);
+    const bool isRot = jtype >= AFF_JNT_ROT_X;
+    const int d = isRot ? jtype - AFF_JNT_ROT_X : jtype;
+    const unsigned ri = (L.rot >> (7 * d)) & 127u;
+    const int partner = isJoint ? (isRot ? (int)(ri & 31u) : (int)((L.trans >> (5 * d)) & 31u)) : c.lane;
     const double other = w_shfl(val, partner);
-    if (!skip) {
-      if (kind == AFFK_NODE_JOINT_IK || kind == AFFK_NODE_JOINT_CONST) {
-        if (jtype >= AFF_JNT_ROT_X) {
-          if (isA) val = fma(s, other, co * val);            // ra' = c ra + s rb
-          else if (isB) val = fma(co, val, -(s * other));    // rb' = c rb - s ra
-        } else if (e < 3) {
+    if (store) {
+      if (isJoint) {
+        if (isRot) {
+          if (ri & 32u) val = fma(s, other, co * val);             // ra' = c ra + s rb
+          else if (ri & 64u) val = fma(co, val, -(s * other));     // rb' = c rb - s ra
+        } else if (L.isOrg) {
           val = fma(qv, other, val);
         }
       }
-      k_node(c, n)[e] = val;
+      nodes[12 * n + L.e] = val;
     }
     w_sync();
   }
@@ -296,6 +327,15 @@ AFF_DEV void k_via_step(double* st, const KVia* vias, int n, double tnow, double
 // POLAR     : 0-2 a (axis in ref frame), 3-5 e1, 6-8 e2, 9-11 pe
 // INCLINATION: 0-2 u, 3-5 v, 6-8 n (unit, or zero), 9-11 pe
 #define AFFK_GEO 12
+// task descriptor words in shared memory
+#define TD_KIND 0
+#define TD_EFF 1
+#define TD_REF 2
+#define TD_FRAME 3
+#define TD_AXIS 4
+#define TD_XOFF 5
+#define TD_DIM 6
+#define TD_NJ 7
 
 AFF_DEV void k_tangent_basis(const double* a, double* e1, double* e2)
 {
@@ -311,40 +351,40 @@ AFF_DEV void k_tangent_basis(const double* a, double* e1, double* e2)
   k_cross(e2, a, e1);
 }
 
-AFF_DEV void k_task_geo(const KCtx& c, const KTask* tk, double* geo, double* xcur)
+AFF_DEV void k_task_geo(const KCtx& c, const int* td, const KTask* tk, double* geo, double* xcur)
 {
-  const int kind = ldg(&tk->kind), eff = ldg(&tk->eff), ref = ldg(&tk->ref), frame = ldg(&tk->frame), axis = ldg(&tk->axis);
-  const int xoff = ldg(&tk->xoff);
+  const int kind = td[TD_KIND], eff = td[TD_EFF], ref = td[TD_REF], frame = td[TD_FRAME], axis = td[TD_AXIS];
+  const int xoff = td[TD_XOFF];
   if (kind <= AFF_TASK_Z) {
-    const double* Ae = k_ref(c, eff);
+    const double* Ae = k_slot(c, eff);
     double r[3], xr[3];
     for (int k = 0; k < 3; ++k) {
       geo[k] = Ae[k];
-      const double prk = (ref != AFFK_WORLD) ? k_ref(c, ref)[k] : 0.0;
+      const double prk = (ref >= 0) ? k_slot(c, ref)[k] : 0.0;
       geo[3 + k] = prk;
-      r[k] = (ref != AFFK_WORLD) ? Ae[k] - prk : Ae[k];
+      r[k] = (ref >= 0) ? Ae[k] - prk : Ae[k];
       geo[6 + k] = r[k];
     }
-    if (frame != AFFK_WORLD) k_mulv(xr, k_ref(c, frame) + 3, r);
+    if (frame >= 0) k_mulv(xr, k_slot(c, frame) + 3, r);
     else { xr[0] = r[0]; xr[1] = r[1]; xr[2] = r[2]; }
     if (kind == AFF_TASK_XYZ) { xcur[xoff] = xr[0]; xcur[xoff + 1] = xr[1]; xcur[xoff + 2] = xr[2]; }
     else xcur[xoff] = xr[kind - AFF_TASK_X];
   } else if (kind == AFF_TASK_POLAR) {
-    const double* Ae = k_ref(c, eff);
+    const double* Ae = k_slot(c, eff);
     const double* aI = Ae + 3 + 3 * axis;
     double a[3], e1[3], e2[3];
-    if (ref != AFFK_WORLD) k_mulv(a, k_ref(c, ref) + 3, aI);
+    if (ref >= 0) k_mulv(a, k_slot(c, ref) + 3, aI);
     else { a[0] = aI[0]; a[1] = aI[1]; a[2] = aI[2]; }
     k_tangent_basis(a, e1, e2);
     for (int k = 0; k < 3; ++k) { geo[k] = a[k]; geo[3 + k] = e1[k]; geo[6 + k] = e2[k]; geo[9 + k] = Ae[k]; }
     xcur[xoff] = aff_acos(a[2]);
     xcur[xoff + 1] = aff_atan2(a[1], a[0]);
   } else if (kind == AFF_TASK_INCLINATION) {
-    const double* Ae = k_ref(c, eff);
+    const double* Ae = k_slot(c, eff);
     const double* aI = Ae + 3 + 3 * axis;
     double u[3], v[3], n[3];
     for (int k = 0; k < 3; ++k) u[k] = aI[k];
-    if (ref != AFFK_WORLD) { const double* z = k_ref(c, ref) + 3 + 6; v[0] = z[0]; v[1] = z[1]; v[2] = z[2]; }
+    if (ref >= 0) { const double* z = k_slot(c, ref) + 3 + 6; v[0] = z[0]; v[1] = z[1]; v[2] = z[2]; }
     else { v[0] = 0.0; v[1] = 0.0; v[2] = 1.0; }
     k_cross(n, v, u);
     const double sn = sqrt(k_dot(n, n));
@@ -353,7 +393,7 @@ AFF_DEV void k_task_geo(const KCtx& c, const KTask* tk, double* geo, double* xcu
     for (int k = 0; k < 3; ++k) { geo[k] = u[k]; geo[3 + k] = v[k]; geo[6 + k] = n[k]; geo[9 + k] = Ae[k]; }
     xcur[xoff] = aff_acos(k_dot(u, v));
   } else {   // JOINTS
-    const int nj = ldg(&tk->n_joints);
+    const int nj = td[TD_NJ];
     const double* q = c.sm + c.P->o_q;
     for (int i = 0; i < nj; ++i) {
       const int ji = ldg(&tk->jidx[i]);
@@ -373,9 +413,9 @@ AFF_DEV double k_region_dx(const KTask* tk, double e)
 }
 
 // Task::computeDX towards xdes, from geo / xcur of the current state.
-AFF_DEV void k_task_dx(const KTask* tk, const double* geo, const double* xcur, const double* xdes, double* dx)
+AFF_DEV void k_task_dx(const int* td, const KTask* tk, const double* geo, const double* xcur, const double* xdes, double* dx)
 {
-  const int kind = ldg(&tk->kind), xoff = ldg(&tk->xoff);
+  const int kind = td[TD_KIND], xoff = td[TD_XOFF];
   if (kind == AFF_TASK_POLAR) {
     const double* a = geo; const double* e1 = geo + 3; const double* e2 = geo + 6;
     double ad[3], n[3], w[3], sp, cp, st, ct;
@@ -392,45 +432,41 @@ AFF_DEV void k_task_dx(const KTask* tk, const double* geo, const double* xcur, c
     dx[1] = k_dot(e2, w);
     return;
   }
-  const int dim = (kind == AFF_TASK_XYZ) ? 3 : ((kind == AFF_TASK_JOINTS) ? ldg(&tk->n_joints) : 1);
+  const int dim = td[TD_DIM];
   for (int i = 0; i < dim; ++i) dx[i] = k_region_dx(tk, xdes[xoff + i] - xcur[xoff + i]);
 }
 
-AFF_DEV int k_task_dim(const KTask* tk)
+// Rows of one task in column `lane` of J (Task::computeJ).  Returns a bit per
+// row that is non-zero in this column.
+AFF_DEV unsigned k_task_J(const KCtx& c, const KJointFrame& jf, const int* td, const KTask* tk, const double* geo, double* Jrow0, int Jstride)
 {
-  const int kind = ldg(&tk->kind);
-  if (kind == AFF_TASK_XYZ) return 3;
-  if (kind == AFF_TASK_POLAR) return 2;
-  if (kind == AFF_TASK_JOINTS) return ldg(&tk->n_joints);
-  return 1;
-}
-
-// Rows of task tk in column `lane` of J (Task::computeJ).
-AFF_DEV void k_task_J(const KCtx& c, const KJointFrame& jf, const KTask* tk, const double* geo, double* Jrow0, int Jstride)
-{
-  const int kind = ldg(&tk->kind), eff = ldg(&tk->eff), ref = ldg(&tk->ref), frame = ldg(&tk->frame);
+  const int kind = td[TD_KIND], eff = td[TD_EFF], ref = td[TD_REF], frame = td[TD_FRAME];
   const int col = c.lane;
+  unsigned nz = 0u;
   if (kind <= AFF_TASK_Z) {
     double te[3], re[3], tr[3], rr[3], tf[3], rf[3], cr[3], cl[3], out[3];
     const double zero[3] = {0.0, 0.0, 0.0};
     k_jac_cols(c, jf, eff, geo, te, re);
     k_jac_cols(c, jf, ref, geo + 3, tr, rr);
-    k_jac_cols(c, jf, frame, (frame != AFFK_WORLD) ? k_ref(c, frame) : zero, tf, rf);
+    k_jac_cols(c, jf, frame, (frame >= 0) ? k_slot(c, frame) : zero, tf, rf);
     k_cross(cr, geo + 6, rf);
     for (int k = 0; k < 3; ++k) cl[k] = (te[k] - tr[k]) + cr[k];
-    if (frame != AFFK_WORLD) k_mulv(out, k_ref(c, frame) + 3, cl);
+    if (frame >= 0) k_mulv(out, k_slot(c, frame) + 3, cl);
     else { out[0] = cl[0]; out[1] = cl[1]; out[2] = cl[2]; }
-    if (kind == AFF_TASK_XYZ) { Jrow0[col] = out[0]; Jrow0[Jstride + col] = out[1]; Jrow0[2 * Jstride + col] = out[2]; }
-    else Jrow0[col] = out[kind - AFF_TASK_X];
+    if (kind == AFF_TASK_XYZ) {
+      Jrow0[col] = out[0]; Jrow0[Jstride + col] = out[1]; Jrow0[2 * Jstride + col] = out[2];
+      nz = (out[0] != 0.0 ? 1u : 0u) | (out[1] != 0.0 ? 2u : 0u) | (out[2] != 0.0 ? 4u : 0u);
+    } else { const double v = out[kind - AFF_TASK_X]; Jrow0[col] = v; nz = v != 0.0 ? 1u : 0u; }
   } else if (kind == AFF_TASK_POLAR) {
     double te[3], re[3], tr[3], rr[3], wI[3], w[3];
     k_jac_cols(c, jf, eff, geo + 9, te, re);
     k_jac_cols(c, jf, ref, geo + 9, tr, rr);
     for (int k = 0; k < 3; ++k) wI[k] = re[k] - rr[k];
-    if (ref != AFFK_WORLD) k_mulv(w, k_ref(c, ref) + 3, wI);
+    if (ref >= 0) k_mulv(w, k_slot(c, ref) + 3, wI);
     else { w[0] = wI[0]; w[1] = wI[1]; w[2] = wI[2]; }
-    Jrow0[col] = k_dot(geo + 3, w);
-    Jrow0[Jstride + col] = k_dot(geo + 6, w);
+    const double j0 = k_dot(geo + 3, w), j1 = k_dot(geo + 6, w);
+    Jrow0[col] = j0; Jrow0[Jstride + col] = j1;
+    nz = (j0 != 0.0 ? 1u : 0u) | (j1 != 0.0 ? 2u : 0u);
   } else if (kind == AFF_TASK_INCLINATION) {
     double te[3], re[3], tr[3], rr[3], wI[3];
     const double* n = geo + 6;
@@ -442,10 +478,12 @@ AFF_DEV void k_task_J(const KCtx& c, const KJointFrame& jf, const KTask* tk, con
       v = k_dot(n, wI);
     }
     Jrow0[col] = v;
+    nz = v != 0.0 ? 1u : 0u;
   } else {
-    const int nj = ldg(&tk->n_joints);
-    for (int i = 0; i < nj; ++i) Jrow0[i * Jstride + col] = (ldg(&tk->jidx[i]) == col) ? 1.0 : 0.0;
+    const int nj = td[TD_NJ];
+    for (int i = 0; i < nj; ++i) { const bool on = ldg(&tk->jidx[i]) == col; Jrow0[i * Jstride + col] = on ? 1.0 : 0.0; if (on) nz |= 1u << i; }
   }
+  return nz;
 }
 
 // -------------------------------------------------------- shape distances
@@ -630,8 +668,9 @@ AFF_DEV bool k_dshape_active(const KCtx& c, const KShape* sh, int toggleSlotPlus
   return ldg(&sh->active0) != 0;
 }
 
-// Distance of a live body pair = min over active shape pairs.
+// Distance of a body pair found by the AABB test = min over active shape pairs.
 // ia: dynamic body index; ib >= 0 dynamic body index, ib < 0 static body (-1-ib).
+// (Rare path: only bodies whose boxes come within DistanceThreshold.)
 AFF_DEV double k_pair_distance(const KCtx& c, int ia, int ib)
 {
   const KPlan& P = *c.P;
@@ -674,9 +713,68 @@ AFF_DEV double k_pair_distance(const KCtx& c, int ia, int ib)
   return dmin;
 }
 
+// meta word of a precompiled shape pair (plan_build.cpp: packPairMeta)
+#define KP_SLOT_A(m) ((m) & 3)
+#define KP_SLOT_B(m) (((m) >> 2) & 3)
+#define KP_SWAP(m) (((m) >> 4) & 1)
+#define KP_GROUP(m) (((m) >> 5) & 7)       /* followers that belong to this leader */
+#define KP_FOLLOWER(m) (((m) >> 8) & 1)
+#define KP_TREE_A(m) ((int)(((m) >> 9) & 15) - 1)
+#define KP_TREE_B(m) ((int)(((m) >> 13) & 15) - 1)
+#define KP_EXPL_A(m) (((m) >> 17) & 1)
+#define KP_EXPL_B(m) (((m) >> 18) & 1)
+#define KP_ACT_A(m) (((m) >> 19) & 1)
+#define KP_ACT_B(m) (((m) >> 20) & 1)
+#define KP_BODY_A(m) (((m) >> 21) & 31)
+#define KP_BODY_B(m) (((m) >> 26) & 31)    /* 31 = static body */
+#define KP_RULE(m) (((unsigned)(m)) >> 31)  /* liveness must be decided per step */
+
+// Is a precompiled pair part of this step's collision model?  Tree x tree and
+// tree x explicit pairs of fixed membership always are (no RULE bit).  Pairs
+// involving a re-parentable object depend on its shape flags and current tree,
+// and a tree body pairs with a non-explicit body outside all trees only while
+// their AABBs (inflated by the threshold) overlap.
+AFF_DEV bool k_pair_live(const KCtx& c, int meta, const double* baabb, double thr)
+{
+  if (!KP_RULE(meta)) return true;
+  const int sa = KP_SLOT_A(meta), sb = KP_SLOT_B(meta);
+  bool actA = KP_ACT_A(meta), actB = KP_ACT_B(meta);
+  int ta = KP_TREE_A(meta), tb = KP_TREE_B(meta);
+  if (sa) { const int mode = c.objMode[sa - 1]; if (mode == 1) actA = true; else if (mode == 2) actA = false; ta = c.objTree[sa - 1]; }
+  if (sb) { const int mode = c.objMode[sb - 1]; if (mode == 1) actB = true; else if (mode == 2) actB = false; tb = c.objTree[sb - 1]; }
+  if (!actA || !actB) return false;
+  if (ta < 0 && tb < 0) return false;
+  if (ta >= 0 && tb >= 0) return ta != tb;
+  const bool otherExplicit = (ta >= 0) ? KP_EXPL_B(meta) : KP_EXPL_A(meta);
+  if (otherExplicit) return true;
+  const int ba = KP_BODY_A(meta), bb = KP_BODY_B(meta);
+  if (bb == 31) return false;   // static, not explicit: handled by the AABB path
+  return k_aabb_overlap(baabb + 6 * ba, baabb + 6 * bb, thr);
+}
+
+// Fold one shape-pair distance into the lane's running minimum; pairs closer than the
+// threshold (rare) are appended to a scratch list for the ordered cost sum.
+struct KPairAcc { double best; int bestKey; int nCostly; };
+
+AFF_DEV void k_pair_account(KPairAcc& acc, bool on, double d, int key, double thr, int* ckey, double* cdist)
+{
+  if (on && (d < acc.best || (d == acc.best && key < acc.bestKey))) { acc.best = d; acc.bestKey = key; }
+  const int costly = on && thr > 0.0 && d < thr;
+  const unsigned m = w_ballot(costly);
+  if (m) {
+    if (costly) {
+      const int pos = acc.nCostly + w_popc(m & ((1u << w_lane()) - 1u));
+      if (pos < 32) { ckey[pos] = key; cdist[pos] = d; }
+    }
+    acc.nCostly += w_popc(m);
+  }
+}
+
 // ControllerBase::computeCollisionModel: broad phase + narrow phase
 // (see the rule list above collmdl_compute() in oracle/oracle.c).
-AFF_DEV KCollResult k_collision(const KCtx& c)
+// `need`: the caller only looks at the minimum if it is below this value (the running minimum of
+// the rollout or the 1 mm collision limit), so the warp-wide arg-min is skipped otherwise.
+AFF_DEV KCollResult k_collision(const KCtx& c, double need)
 {
   const KPlan& P = *c.P;
   const int lane = c.lane;
@@ -684,48 +782,64 @@ AFF_DEV KCollResult k_collision(const KCtx& c)
   double* shp = c.sm + P.o_shp;
   double* baabb = c.sm + P.o_baabb;
   double* taabb = c.sm + P.o_taabb;
-  int* live = (int*)(c.sm + P.o_live);             // pairs: [2*i] = dyn body a, [2*i+1] = other
-  // 1. world frames of the dynamic shapes
+  int* live = (int*)(c.sm + P.o_live);             // AABB-found pairs: [2*i] = dyn body a, [2*i+1] = other
+  int* btree = live + 2 * AFFK_MAX_NEAR;           // tree of each dynamic body, -1 none, -2 inactive
+  int* ckey = btree + AFFK_MAX_DBODY;              // scratch: pairs closer than the threshold
+  double* cdist = (double*)(ckey + 32);
+  // 1. world records of the dynamic shapes: org (0-2), SSL direction d = length * z-axis (3-5),
+  //    z-axis (9-11); boxes and cylinders get the full frame.
   for (int s = lane; s < P.nDynShapes; s += 32) {
     const KShape* sh = P.dshape + s;
-    const double* An = k_ref(c, ldg(&sh->node));
-    double W[12];
-    k_compose(W, sh->A_CB, An);
-    for (int e = 0; e < 12; ++e) shp[12 * s + e] = W[e];
+    const double* An = k_slot(c, ldg(&sh->node));
+    const int type = ldg(&sh->type);
+    double* W = shp + 12 * s;
+    if (type == AFF_SHAPE_SSL || type == AFF_SHAPE_SPHERE) {
+      for (int e = 0; e < 3; ++e) W[e] = k_compose_elem(sh->A_CB, An, e);
+      if (type == AFF_SHAPE_SSL) {
+        const double len = ldg(&sh->ext[2]);
+        for (int e = 0; e < 3; ++e) { const double ax = k_compose_elem(sh->A_CB, An, 9 + e); W[9 + e] = ax; W[3 + e] = len * ax; }
+      } else { W[3] = 0.0; W[4] = 0.0; W[5] = 0.0; }
+    } else {
+      for (int e = 0; e < 12; ++e) W[e] = k_compose_elem(sh->A_CB, An, e);
+    }
   }
   w_sync();
   // 2. per dynamic body: active flag, tree, AABB
-  int myActive = 0, myTree = -1;
   if (lane < P.nDynBodies) {
     const KShapeBody* b = P.dbody + lane;
     const int f = ldg(&b->first_shape), n = ldg(&b->n_shapes), os = ldg(&b->obj_slot), ts = ldg(&b->toggle_slot);
     double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    int act = 0;
     for (int k = 0; k < n; ++k) {
       const KShape* sh = P.dshape + f + k;
       if (!k_dshape_active(c, sh, ts)) continue;
-      myActive = 1;
-      double ext[3] = {ldg(&sh->ext[0]), ldg(&sh->ext[1]), ldg(&sh->ext[2])};
-      double smn[3], smx[3];
-      k_shape_aabb(ldg(&sh->type), ext, shp + 12 * (f + k), smn, smx);
-      for (int q = 0; q < 3; ++q) { if (smn[q] < mn[q]) mn[q] = smn[q]; if (smx[q] > mx[q]) mx[q] = smx[q]; }
+      act = 1;
+      const int type = ldg(&sh->type);
+      const double* W = shp + 12 * (f + k);
+      if (type == AFF_SHAPE_SSL || type == AFF_SHAPE_SPHERE) {
+        const double r = ldg(&sh->ext[0]);
+        for (int q = 0; q < 3; ++q) {
+          const double p0 = W[q], p1 = p0 + W[3 + q];
+          const double lo = ((p0 < p1) ? p0 : p1) - r, hi = ((p0 > p1) ? p0 : p1) + r;
+          if (lo < mn[q]) mn[q] = lo;
+          if (hi > mx[q]) mx[q] = hi;
+        }
+      } else {
+        double ext[3] = {ldg(&sh->ext[0]), ldg(&sh->ext[1]), ldg(&sh->ext[2])};
+        double smn[3], smx[3];
+        k_shape_aabb(type, ext, W, smn, smx);
+        for (int q = 0; q < 3; ++q) { if (smn[q] < mn[q]) mn[q] = smn[q]; if (smx[q] > mx[q]) mx[q] = smx[q]; }
+      }
     }
     for (int q = 0; q < 3; ++q) { baabb[6 * lane + q] = mn[q]; baabb[6 * lane + 3 + q] = mx[q]; }
-    myTree = os ? c.objTree[os - 1] : ldg(&b->tree);
-  }
-  const unsigned activeMask = w_ballot(myActive);
-  // tree id of every dynamic body, packed 4 bits each (tree+1), 16 bodies -> 64 bits in two words
-  unsigned treeLo = 0u, treeHi = 0u;
-  for (int b = 0; b < P.nDynBodies; ++b) {
-    const int t = w_shfl(myTree, b) + 1;
-    if (b < 8) treeLo |= (unsigned)(t & 15) << (4 * b); else treeHi |= (unsigned)(t & 15) << (4 * (b - 8));
+    btree[lane] = act ? (os ? c.objTree[os - 1] : ldg(&b->tree)) : -2;
   }
   w_sync();
   // 3. tree AABBs
   if (lane < P.nTrees) {
     double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
     for (int b = 0; b < P.nDynBodies; ++b) {
-      const int t = (int)(((b < 8 ? treeLo >> (4 * b) : treeHi >> (4 * (b - 8))) & 15u)) - 1;
-      if (t != lane || !((activeMask >> b) & 1u)) continue;
+      if (btree[b] != lane) continue;
       for (int q = 0; q < 3; ++q) {
         const double lo = baabb[6 * b + q], hi = baabb[6 * b + 3 + q];
         if (lo < mn[q]) mn[q] = lo;
@@ -735,50 +849,15 @@ AFF_DEV KCollResult k_collision(const KCtx& c)
     for (int q = 0; q < 3; ++q) { taabb[6 * lane + q] = mn[q]; taabb[6 * lane + 3 + q] = mx[q]; }
   }
   w_sync();
+  // 4. static bodies that are not explicit: two-level AABB test (tree box, then tree bodies)
   int nLive = 0;
-  // 4a. candidate pairs among dynamic bodies and against explicit static bodies
-  for (int base = 0; base < P.nAlways; base += 32) {
-    const int i = base + lane;
-    int isLive = 0, ia = 0, ib = 0;
-    if (i < P.nAlways) {
-      ia = ldg(&P.always[2 * i]); ib = ldg(&P.always[2 * i + 1]);
-      const int ta = (int)(((ia < 8 ? treeLo >> (4 * ia) : treeHi >> (4 * (ia - 8))) & 15u)) - 1;
-      const bool actA = (activeMask >> ia) & 1u;
-      if (ib >= 0) {
-        const int tb = (int)(((ib < 8 ? treeLo >> (4 * ib) : treeHi >> (4 * (ib - 8))) & 15u)) - 1;
-        const bool actB = (activeMask >> ib) & 1u;
-        if (actA && actB && !(ta < 0 && tb < 0)) {
-          if (ta >= 0 && tb >= 0) isLive = (ta != tb);
-          else {
-            const int other = (ta >= 0) ? ib : ia;
-            if (ldg(&P.dbody[other].explicit_bp)) isLive = 1;
-            else isLive = k_aabb_overlap(baabb + 6 * ia, baabb + 6 * ib, thr);
-          }
-        }
-      } else {
-        // static explicit body: live iff a is in a tree
-        const KShapeBody* sb = P.sbody + (-1 - ib);
-        isLive = actA && ta >= 0 && ldg(&sb->any_active0);
-      }
-    }
-    const unsigned m = w_ballot(isLive);
-    if (isLive) {
-      const int pos = nLive + w_popc(m & ((1u << lane) - 1u));
-      if (pos < AFFK_MAX_LIVE) { live[2 * pos] = ia; live[2 * pos + 1] = ib; }
-    }
-    nLive += w_popc(m);
-  }
-  // 4b. static bodies that are not explicit: two-level AABB test
   for (int base = 0; base < P.nStatBodies; base += 32) {
     const int i = base + lane;
     int near = 0;
-    if (i < P.nStatBodies) {
-      const KShapeBody* sb = P.sbody + i;
-      if (!ldg(&sb->explicit_bp) && ldg(&sb->any_active0)) {
-        double bb[6];
-        for (int q = 0; q < 6; ++q) bb[q] = ldg(&P.sbodyAABB[6 * i + q]);
-        for (int t = 0; t < P.nTrees; ++t) if (k_aabb_overlap(taabb + 6 * t, bb, thr)) near = 1;
-      }
+    if (i < P.nStatBodies && ldg(&P.sbody[i].explicit_bp) == 0 && ldg(&P.sbody[i].any_active0)) {
+      double bb[6];
+      for (int q = 0; q < 6; ++q) bb[q] = ldg(&P.sbodyAABB[6 * i + q]);
+      for (int t = 0; t < P.nTrees; ++t) if (k_aabb_overlap(taabb + 6 * t, bb, thr)) near = 1;
     }
     unsigned nm = w_ballot(near);
     while (nm) {   // rare: a static body is close to a tree; test it against each tree body
@@ -786,70 +865,105 @@ AFF_DEV KCollResult k_collision(const KCtx& c)
       nm &= nm - 1u;
       const int sidx = base + src;
       int isLive = 0;
-      if (lane < P.nDynBodies && ((activeMask >> lane) & 1u)) {
-        const int ta = (int)(((lane < 8 ? treeLo >> (4 * lane) : treeHi >> (4 * (lane - 8))) & 15u)) - 1;
-        if (ta >= 0) {
-          double bb[6];
-          for (int q = 0; q < 6; ++q) bb[q] = ldg(&P.sbodyAABB[6 * sidx + q]);
-          isLive = k_aabb_overlap(baabb + 6 * lane, bb, thr);
-        }
+      if (lane < P.nDynBodies && btree[lane] >= 0) {
+        double bb[6];
+        for (int q = 0; q < 6; ++q) bb[q] = ldg(&P.sbodyAABB[6 * sidx + q]);
+        isLive = k_aabb_overlap(baabb + 6 * lane, bb, thr);
       }
       const unsigned m = w_ballot(isLive);
       if (isLive) {
         const int pos = nLive + w_popc(m & ((1u << lane) - 1u));
-        if (pos < AFFK_MAX_LIVE) { live[2 * pos] = lane; live[2 * pos + 1] = -1 - sidx; }
+        if (pos < AFFK_MAX_NEAR) { live[2 * pos] = lane; live[2 * pos + 1] = -1 - sidx; }
       }
       nLive += w_popc(m);
     }
   }
-  w_sync();
-  if (nLive > AFFK_MAX_LIVE) nLive = AFFK_MAX_LIVE;
-  // 5. narrow phase
-  double best = DBL_MAX; int bestKey = 0x7fffffff;
-  double myCost[AFFK_MAX_LIVE / 32]; int myKey[AFFK_MAX_LIVE / 32];
-  int nCostly = 0;
-  for (int r = 0; r < AFFK_MAX_LIVE / 32; ++r) { myCost[r] = 0.0; myKey[r] = 0x7fffffff; }
-#pragma unroll
-  for (int r = 0; r < AFFK_MAX_LIVE / 32; ++r) {
-    const int i = 32 * r + lane;
+  if (nLive > AFFK_MAX_NEAR) nLive = AFFK_MAX_NEAR;
+  // 5. narrow phase over the precompiled, type-sorted shape-pair lists
+  KPairAcc acc;
+  acc.best = DBL_MAX; acc.bestKey = 0x7fffffff; acc.nCostly = 0;
+  // 5a. segment - segment (capsules, spheres)
+  for (int base = 0; base < P.nSS; base += 32) {
+    const int i = base + lane;
+    double d = DBL_MAX; int key = 0x7fffffff, meta = 0; bool on = false;
+    if (i < P.nSS) {
+      const KPair pr = ldg_pair(&P.pairsSS[i]);
+      meta = pr.meta; key = pr.key;
+      on = k_pair_live(c, meta, baabb, thr);
+      if (on) {
+        const double* A = shp + 12 * pr.a;
+        const double rA = ldg(&P.dshape[pr.a].ext[0]);
+        double pB[3], dB[3], rB;
+        if (pr.b >= 0) { const double* B = shp + 12 * pr.b; for (int k = 0; k < 3; ++k) { pB[k] = B[k]; dB[k] = B[3 + k]; } rB = ldg(&P.dshape[pr.b].ext[0]); }
+        else { const double* B = P.sseg + 8 * (-1 - pr.b); for (int k = 0; k < 3; ++k) { pB[k] = ldg(&B[k]); dB[k] = ldg(&B[3 + k]); } rB = ldg(&B[6]); }
+        d = KP_SWAP(meta) ? (k_seg_seg(pB, dB, A, A + 3) - rB) - rA : (k_seg_seg(A, A + 3, pB, dB) - rA) - rB;
+      }
+    }
+    k_pair_account(acc, on, d, key, thr, ckey, cdist);
+  }
+  // 5b. segment - box and segment - cylinder (the segment is always the first argument)
+  for (int base = 0; base < P.nSB; base += 32) {
+    const int i = base + lane;
+    double d = DBL_MAX; int key = 0x7fffffff, meta = 0; bool on = false;
+    if (i < P.nSB) {
+      const KPair pr = ldg_pair(&P.pairsSB[i]);
+      meta = pr.meta; key = pr.key;
+      on = k_pair_live(c, meta, baabb, thr);
+      if (on) {
+        // a = segment shape (dynamic >= 0 / static < 0), b = box or cylinder shape
+        double pS[3], dS[3], rS, F[12], ext[3]; int typeB;
+        if (pr.a >= 0) { const double* A = shp + 12 * pr.a; for (int k = 0; k < 3; ++k) { pS[k] = A[k]; dS[k] = A[3 + k]; } rS = ldg(&P.dshape[pr.a].ext[0]); }
+        else { const double* A = P.sseg + 8 * (-1 - pr.a); for (int k = 0; k < 3; ++k) { pS[k] = ldg(&A[k]); dS[k] = ldg(&A[3 + k]); } rS = ldg(&A[6]); }
+        if (pr.b >= 0) { const double* B = shp + 12 * pr.b; for (int e = 0; e < 12; ++e) F[e] = B[e]; const KShape* sb = P.dshape + pr.b; typeB = ldg(&sb->type); for (int k = 0; k < 3; ++k) ext[k] = ldg(&sb->ext[k]); }
+        else { const int si = -1 - pr.b; for (int e = 0; e < 12; ++e) F[e] = ldg(&P.sshapeA[12 * si + e]); const KShape* sb = P.sshape + si; typeB = ldg(&sb->type); for (int k = 0; k < 3; ++k) ext[k] = ldg(&sb->ext[k]); }
+        double rel[3], pl[3], dl[3];
+        for (int k = 0; k < 3; ++k) rel[k] = pS[k] - F[k];
+        k_mulv(pl, F + 3, rel);
+        k_mulv(dl, F + 3, dS);
+        if (typeB == AFF_SHAPE_BOX) { const double h[3] = {0.5 * ext[0], 0.5 * ext[1], 0.5 * ext[2]}; d = k_seg_box(pl, dl, h) - rS; }
+        else d = k_seg_cyl(pl, dl, 0.5 * ext[2], ext[0]) - rS;
+      }
+    }
+    k_pair_account(acc, on, d, key, thr, ckey, cdist);
+  }
+  // 5c. pairs found by the AABB test (rare)
+  for (int base = 0; base < nLive; base += 32) {
+    const int i = base + lane;
+    double d = DBL_MAX; int key = 0x7fffffff;
     if (i < nLive) {
       const int ia = live[2 * i], ib = live[2 * i + 1];
-      const double d = k_pair_distance(c, ia, ib);
+      d = k_pair_distance(c, ia, ib);
       const int bodyA = ldg(&P.dbody[ia].body);
       const int bodyB = (ib >= 0) ? ldg(&P.dbody[ib].body) : ldg(&P.sbody[-1 - ib].body);
       const int b1 = bodyA < bodyB ? bodyA : bodyB, b2 = bodyA < bodyB ? bodyB : bodyA;
-      const int key = (b1 << 15) | b2;
-      if (d < best || (d == best && key < bestKey)) { best = d; bestKey = key; }
-      if (thr > 0.0) {
-        if (d < 0.0) { myCost[r] = 1.0 - (2.0 * d) / thr; myKey[r] = key; nCostly++; }
-        else if (d < thr) { const double u = (d - thr) / thr; myCost[r] = u * u; myKey[r] = key; nCostly++; }
-      }
+      key = (b1 << 15) | b2;
     }
+    k_pair_account(acc, i < nLive, d, key, thr, ckey, cdist);
   }
   KCollResult res;
-  w_min_keyed(best, bestKey);
-  res.minDist = best;
-  if (nLive == 0 || !(best < DBL_MAX)) { res.minB1 = -1; res.minB2 = -1; }
-  else { res.minB1 = bestKey >> 15; res.minB2 = bestKey & 0x7fff; }
-  // cost: sum of the non-zero pair terms in ascending (b1, b2) order
+  double best = acc.best; int bestKey = acc.bestKey;
+  if (w_ballot(best < need)) {
+    w_min_keyed(best, bestKey);
+    res.minDist = best;
+    if (!(best < DBL_MAX)) { res.minB1 = -1; res.minB2 = -1; }
+    else { res.minB1 = bestKey >> 15; res.minB2 = bestKey & 0x7fff; }
+  } else { res.minDist = DBL_MAX; res.minB1 = -1; res.minB2 = -1; }
+  // cost: one term per BODY pair (its closest shape pair), added in ascending (b1, b2) order.
+  // Only pairs closer than the threshold contribute, so this loop almost never runs.
   res.cost = 0.0;
-  unsigned anyCost = w_ballot(nCostly > 0);
-  while (anyCost) {
-    double dummy = 0.0; int k = 0x7fffffff; double kc = 0.0;
-#pragma unroll
-    for (int r = 0; r < AFFK_MAX_LIVE / 32; ++r) if (myKey[r] < k) { k = myKey[r]; kc = myCost[r]; }
-    int kmin = k;
-    w_min_keyed(dummy, kmin);
-    const int owner = w_ffs(w_ballot(k == kmin && k != 0x7fffffff)) - 1;
-    double term = 0.0;
-    if (lane == owner) {
-      term = kc; nCostly--;
-#pragma unroll
-      for (int r = 0; r < AFFK_MAX_LIVE / 32; ++r) if (myKey[r] == k) myKey[r] = 0x7fffffff;
+  if (acc.nCostly > 0) {
+    w_sync();
+    const int n = acc.nCostly < 32 ? acc.nCostly : 32;
+    int myKey = (lane < n) ? ckey[lane] : 0x7fffffff;
+    const double myD = (lane < n) ? cdist[lane] : DBL_MAX;
+    for (;;) {
+      int kmin = myKey;
+      for (int off = 16; off >= 1; off >>= 1) { const int o = w_shfl_xor(kmin, off); kmin = o < kmin ? o : kmin; }
+      if (kmin == 0x7fffffff) break;
+      const double d = w_min(myKey == kmin ? myD : DBL_MAX);
+      res.cost = res.cost + ((d < 0.0) ? 1.0 - (2.0 * d) / thr : ((d - thr) / thr) * ((d - thr) / thr));
+      if (myKey == kmin) myKey = 0x7fffffff;
     }
-    term = w_shfl(term, owner);
-    res.cost = res.cost + term;
-    anyCost = w_ballot(nCostly > 0);
   }
   return res;
 }
@@ -859,24 +973,38 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
 {
   KCtx c;
   c.P = &P; c.C = P.cands + cand; c.sm = sm; c.lane = w_lane();
+  c.nodes = sm + P.o_node;
+  c.chain = (unsigned*)(sm + P.o_chain);
+  c.tdesc = (int*)(sm + P.o_tdesc);
   const KCand& C = *c.C;
   const int lane = c.lane, nJ = P.nJ;
   const double dt = P.opts.dt;
   const int nTasks = ldg(&C.n_tasks), xdim = ldg(&C.xdim);
   const KTask* tasks = P.tasks + ldg(&C.first_task);
-  double* q = sm + P.o_q; double* qdot = sm + P.o_qdot; double* dH = sm + P.o_dH; double* dq = sm + P.o_dq;
+  double* q = sm + P.o_q; double* qdot = sm + P.o_qdot; double* vbuf = sm + P.o_dH; double* wbuf = sm + P.o_dq;
   double* J = sm + P.o_J; double* L = sm + P.o_L; double* rhs = sm + P.o_rhs; double* dxv = sm + P.o_dx;
   double* st = sm + P.o_st; double* xdes = sm + P.o_xdes; double* xcur = sm + P.o_xcur; double* geo = sm + P.o_geo;
+  unsigned* rmask = (unsigned*)(sm + P.o_rmask);
   const int JS = P.JS, LS = P.LS;
+  const int nSlots = P.nDyn + P.nStatPar;
 
   // ---- per-lane constants
   double jq0 = 0, jqmin = 0, jqmax = 0, jspeed = AFFK_NO_LIMIT, jacc = AFFK_NO_LIMIT, jwjl = 0, jw = 0;
-  int jnode = -1, jtype = 0;
+  int jnode = 0, jtype = 0;
   if (lane < nJ) {
     jq0 = ldg(&P.jq0[lane]); jqmin = ldg(&P.jq_min[lane]); jqmax = ldg(&P.jq_max[lane]);
     jspeed = ldg(&P.jspeed[lane]); jacc = ldg(&P.jacc[lane]); jwjl = ldg(&P.jwjl[lane]); jw = ldg(&P.jwmetric[lane]);
     jnode = ldg(&P.j_node[lane]); jtype = ldg(&P.j_type[lane]);
-    q[lane] = ldg(&P.jq_init[lane]); qdot[lane] = 0.0;
+    q[lane] = ldg(&P.jq_init[lane]); qdot[lane] = 0.0; wbuf[lane] = jw;
+  }
+  // task descriptors -> shared memory
+  if (lane < nTasks) {
+    const KTask* tk = tasks + lane;
+    int* td = c.tdesc + 8 * lane;
+    const int kind = ldg(&tk->kind);
+    td[TD_KIND] = kind; td[TD_EFF] = ldg(&tk->eff); td[TD_REF] = ldg(&tk->ref); td[TD_FRAME] = ldg(&tk->frame);
+    td[TD_AXIS] = ldg(&tk->axis); td[TD_XOFF] = ldg(&tk->xoff); td[TD_NJ] = ldg(&tk->n_joints);
+    td[TD_DIM] = (kind == AFF_TASK_XYZ) ? 3 : ((kind == AFF_TASK_POLAR) ? 2 : ((kind == AFF_TASK_JOINTS) ? ldg(&tk->n_joints) : 1));
   }
   // task of this lane's dimension
   int myTask = -1;
@@ -892,37 +1020,48 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
   const int nGcon = ldg(&C.n_gcon);
   unsigned gfired = 0u;
 
+  // ---- slots: static frames the loop refers to, chains
+  for (int i = lane; i < 12 * P.nStatPar; i += 32) {
+    const int k = i / 12, e = i % 12;
+    const int ref = ldg(&P.statpar_ref[k]);
+    const double* src = (ref == AFFK_WORLD) ? P.statA + 12 * P.nStatic : P.statA + 12 * AFFK_STATIC_IDX(ref);
+    c.nodes[12 * (P.nDyn + k) + e] = ldg(&src[e]);
+  }
+  for (int i = lane; i < nSlots; i += 32) c.chain[i] = (i < P.nDyn) ? ldg(&P.dyn_chain[i]) : 0u;
+  w_sync();
   // ---- objects
   c.objHasRel = 0u;
-  for (int s = 0; s < AFFK_MAX_OBJ; ++s) { c.objParent[s] = AFFK_WORLD; c.objChain[s] = 0u; c.objTree[s] = -1; c.objMode[s] = 0; }
+  for (int s = 0; s < AFFK_MAX_OBJ; ++s) { c.objParentSlot[s] = 0; c.objParentDynamic[s] = 0; c.objChain[s] = 0u; c.objTree[s] = -1; c.objMode[s] = 0; }
   for (int s = 0; s < P.nObj; ++s) {
-    const int n = ldg(&P.obj_node[s]);
-    const int par = ldg(&P.dyn[n].parent);
-    c.objParent[s] = par;
+    const int ps = ldg(&P.obj_parent_slot[s]);
+    c.objParentSlot[s] = ps;
+    c.objParentDynamic[s] = ps < P.nDyn;
+    c.objChain[s] = c.chain[ps];                      // held in a hand at start: the hand's chain
+    c.objTree[s] = ldg(&P.obj_parent_tree[s]);
   }
-  // chains / trees of objects hanging on dynamic parents (e.g. held in a hand at start)
-  for (int s = 0; s < P.nObj; ++s) { c.objChain[s] = k_chain(c, c.objParent[s]); c.objTree[s] = k_tree_of_node(c, c.objParent[s]); }
+  w_sync();
+  for (int i = lane; i < P.nDyn; i += 32) { const int uo = ldg(&P.dyn_under[i]); if (uo) c.chain[i] = ldg(&P.dyn_chain[i]) | c.objChain[uo - 1]; }
   if (lane < 6) {
     for (int s = 0; s < P.nObj; ++s)
       sm[P.o_objq6 + 6 * s + lane] = (ldg(&C.pose_slot) == s) ? ldg(&C.pose_q6[lane]) : ldg(&P.obj_q6[6 * s + lane]);
   }
   if (lane < xdim) { st[3 * lane] = 0.0; st[3 * lane + 1] = 0.0; st[3 * lane + 2] = 0.0; xdes[lane] = 0.0; }
+  const KFkLane fkLane = k_fk_lane(lane);
   w_sync();
 
   // ---- initial state
-  k_fk(c, true);
+  k_fk(c, fkLane, true);
   const int nSteps = ldg(&C.n_steps);
   const int qrows = P.qlog_rows;
   double* qlog = P.qlog ? P.qlog + (size_t)cand * qrows * nJ : nullptr;
   if (qlog && lane < nJ && qrows > 0) qlog[lane] = q[lane];
 
-  aff_result res;
-  res.idx = cand; res.success = 0; res.code = 0; res.first_code = 0; res.first_fail_step = -1; res.fail_step = -1;
-  res.fail_id0 = -1; res.fail_id1 = -1; res.min_dist_b1 = -1; res.min_dist_b2 = -1; res.n_steps = 0; res.reserved = 0;
-  res.jmask_bits = 0ull; res.min_dist = DBL_MAX; res.jl_cost = 0.0; res.coll_cost = 0.0; res.track_err = 0.0;
+  // result fields (warp-uniform scalars; written once at the end)
+  int r_code = 0, r_first_code = 0, r_first_fail = -1, r_fail_step = -1, r_id0 = -1, r_id1 = -1, r_b1 = -1, r_b2 = -1;
+  double r_minDist = DBL_MAX;
 
-  KCollResult cm = k_collision(c);
-  res.min_dist = cm.minDist; res.min_dist_b1 = cm.minB1; res.min_dist_b2 = cm.minB2;
+  KCollResult cm = k_collision(c, DBL_MAX);
+  r_minDist = cm.minDist; r_b1 = cm.minB1; r_b2 = cm.minB2;
 
   // check(): checkLimits(jl, coll, speed, 0, 0, 0.01)  (src/TrajectoryPredictor.cpp:426-441)
   {
@@ -930,21 +1069,28 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
     bool ok0 = w_ballot(viol) == 0u;
     if (cm.minB1 >= 0 && cm.minDist < 0.01) ok0 = false;
     if (!ok0) {
-      res.code = AFF_CODE_INITIAL_STATE; res.first_code = AFF_CODE_INITIAL_STATE; res.first_fail_step = 0; res.fail_step = 0;
-      if (lane == 0) P.results[cand] = res;
+      if (lane == 0) {
+        aff_result res;
+        res.idx = cand; res.success = 0; res.code = AFF_CODE_INITIAL_STATE; res.first_code = AFF_CODE_INITIAL_STATE;
+        res.first_fail_step = 0; res.fail_step = 0; res.fail_id0 = -1; res.fail_id1 = -1;
+        res.min_dist_b1 = r_b1; res.min_dist_b2 = r_b2; res.n_steps = 0; res.reserved = 0; res.jmask_bits = 0ull;
+        res.min_dist = r_minDist; res.jl_cost = 0.0; res.coll_cost = 0.0; res.track_err = 0.0;
+        P.results[cand] = res;
+      }
       return;
     }
   }
 
   // geometry of the initial state (for the first re-initialisation of the trajectories)
-  if (lane < nTasks) k_task_geo(c, tasks + lane, geo + AFFK_GEO * lane, xcur);
+  if (lane < nTasks) k_task_geo(c, c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur);
   w_sync();
 
   unsigned activeMask = 0u, prevMask = 0u, jmaskBits = 0u;
   unsigned emask = ~(P.rbj_static_chain);
   for (int s = 0; s < P.nObj; ++s) emask &= ~c.objChain[s];
   double tnow = 0.0, qFilt = 0.0, err = 0.0, jlSum = 0.0, collSum = 0.0, endTime = ldg(&C.end_abs);
-  const double motionDuration = ldg(&C.end_abs) - ldg(&C.start_abs);
+  const double endAbs = ldg(&C.end_abs);
+  const double motionDuration = endAbs - ldg(&C.start_abs);
   const double alpha = P.opts.alpha, lambda = P.opts.lambda, qFiltDecay = P.opts.q_filt_decay;
   int success = 1, rows = 1;
 
@@ -954,16 +1100,25 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
     if (qFiltDecay <= 0.0) qFilt = 0.0;
     else qFilt = k_clip(qFilt - (1.0 / qFiltDecay) * dt, 0.0, 1.0);
 
-    // ---- tc->step(dt): trajectories
+    // ---- tc->step(dt): trajectories.  The state of an inactive task's trajectory is overwritten at
+    // the start of the next step unless the task switches on in this one, so only then is it computed.
+    const double tnext = tnow + dt;
+    const int ah = w_shfl(actHead, myTask < 0 ? 0 : myTask), ae = w_shfl(actEnd, myTask < 0 ? 0 : myTask);
     if (lane < xdim) {
-      double s3[3];
-      if (!((activeMask >> myTask) & 1u)) { s3[0] = xcur[lane]; s3[1] = 0.0; s3[2] = 0.0; }
-      else { s3[0] = st[3 * lane]; s3[1] = st[3 * lane + 1]; s3[2] = st[3 * lane + 2]; }
-      k_via_step(s3, vias + viaHead, viaEnd - viaHead, tnow, dt, sm + P.o_scratch + AFFK_VIA_STRIDE * lane);
-      st[3 * lane] = s3[0]; st[3 * lane + 1] = s3[1]; st[3 * lane + 2] = s3[2];
-      xdes[lane] = s3[0];
+      const bool active = (activeMask >> myTask) & 1u;
+      // does an activation point of my task fire in this step and switch it on?
+      bool switchesOn = false;
+      for (int k = ah; k < ae; ++k) { if (!(ldg(&acts[k].t) - tnext < AFFK_TRAJ_EPS)) break; switchesOn = ldg(&acts[k].on) != 0; }
+      if (active || switchesOn) {
+        double s3[3];
+        if (!active) { s3[0] = xcur[lane]; s3[1] = 0.0; s3[2] = 0.0; }
+        else { s3[0] = st[3 * lane]; s3[1] = st[3 * lane + 1]; s3[2] = st[3 * lane + 2]; }
+        k_via_step(s3, vias + viaHead, viaEnd - viaHead, tnow, dt, sm + P.o_scratch + AFFK_VIA_STRIDE * lane);
+        st[3 * lane] = s3[0]; st[3 * lane + 1] = s3[1]; st[3 * lane + 2] = s3[2];
+        xdes[lane] = s3[0];
+      }
     }
-    tnow = tnow + dt;
+    tnow = tnext;
     // graph constraints
     for (int k = 0; k < nGcon; ++k) {
       if ((gfired >> k) & 1u) continue;
@@ -971,12 +1126,12 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
       const int kind = ldg(&gcons[k].kind), slot = ldg(&gcons[k].slot);
       if (kind == AFF_CON_CONNECT) {
         if (tc - tnow < AFFK_TRAJ_EPS) {
-          const int par = ldg(&gcons[k].parent);
+          const int ps = ldg(&gcons[k].parent_slot);
           const int on = ldg(&P.obj_node[slot]);
           w_sync();
           if (lane < 12) {
             // HTr_invTransform: child relative to the new parent
-            const double* Cc = k_node(c, on); const double* Pp = k_ref(c, par);
+            const double* Cc = k_slot(c, on); const double* Pp = k_slot(c, ps);
             double v;
             if (lane < 3) {
               const double d0 = Cc[0] - Pp[0], d1 = Cc[1] - Pp[1], d2 = Cc[2] - Pp[2];
@@ -987,11 +1142,14 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
             }
             sm[P.o_objrel + 12 * slot + lane] = v;
           }
-          w_sync();
           c.objHasRel |= 1u << slot;
-          c.objParent[slot] = par;
-          c.objChain[slot] = k_chain(c, par);
-          c.objTree[slot] = k_tree_of_node(c, par);
+          c.objParentSlot[slot] = ps;
+          c.objParentDynamic[slot] = ps < P.nDyn;
+          c.objChain[slot] = c.chain[ps];
+          const int pt = ldg(&gcons[k].parent_tree);
+          c.objTree[slot] = (pt <= -2) ? c.objTree[-2 - pt] : pt;
+          w_sync();
+          for (int i = lane; i < P.nDyn; i += 32) if (ldg(&P.dyn_under[i]) == slot + 1) c.chain[i] = ldg(&P.dyn_chain[i]) | c.objChain[slot];
           emask = ~(P.rbj_static_chain);
           for (int s = 0; s < P.nObj; ++s) emask &= ~c.objChain[s];
           gfired |= 1u << k;
@@ -1011,7 +1169,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
     prevMask = activeMask;
     activeMask = w_ballot(lane < nTasks && myActive);
     {
-      const double rem = ldg(&C.end_abs) - tnow;
+      const double rem = endAbs - tnow;
       endTime = rem > 0.0 ? rem : 0.0;
     }
     // blending
@@ -1020,7 +1178,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
       if (actHead < actEnd) { const double h = ldg(&acts[actHead].horizon); if (h > 0.0) bl = k_clip((ldg(&acts[actHead].t) - tnow) / h, 0.0, 1.0); }
       if (lastSwitchH > 0.0) { const double up = k_clip((tnow - lastSwitchT) / lastSwitchH, 0.0, 1.0); if (up < bl) bl = up; }
     }
-    double blending = w_min(bl);
+    double blending = w_ballot(bl < 1.0) ? w_min(bl) : 1.0;
     if (activeMask == 0u) blending = 0.0;
     const double phase = (motionDuration > 0.0) ? 1.0 - (endTime / motionDuration) : 0.0;
     const double phaseScale = aff_sin(AFF_PI * phase);
@@ -1032,24 +1190,25 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
     int m = 0, myRow = 0;
     for (int t = 0; t < nTasks; ++t) {
       if (t == lane) myRow = m;
-      if ((activeMask >> t) & 1u) m += k_task_dim(tasks + t);
+      if ((activeMask >> t) & 1u) m += c.tdesc[8 * t + TD_DIM];
     }
-    if (lane < nTasks && ((activeMask >> lane) & 1u)) k_task_dx(tasks + lane, geo + AFFK_GEO * lane, xcur, xdes, dxv + myRow);
+    if (lane < nTasks && ((activeMask >> lane) & 1u)) k_task_dx(c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur, xdes, dxv + myRow);
     // joint frame of this lane's IK joint
     KJointFrame jf;
     jf.valid = (lane < nJ); jf.type = jtype;
-    if (jf.valid) {
-      const double* A = k_node(c, jnode);
+    {
+      const double* A = k_slot(c, jnode);
       const int ar = (jtype < AFF_JNT_ROT_X) ? jtype : jtype - AFF_JNT_ROT_X;
       for (int k = 0; k < 3; ++k) { jf.ax[k] = A[3 + 3 * ar + k]; jf.org[k] = A[k]; }
-    } else { for (int k = 0; k < 3; ++k) { jf.ax[k] = 0.0; jf.org[k] = 0.0; } }
-    // J columns
+    }
+    // J columns; nz = rows of this column that are non-zero
+    unsigned nz = 0u;
     {
       int row = 0;
       for (int t = 0; t < nTasks; ++t) {
         if (!((activeMask >> t) & 1u)) continue;
-        if (lane < nJ) k_task_J(c, jf, tasks + t, geo + AFFK_GEO * t, J + row * JS, JS);
-        row += k_task_dim(tasks + t);
+        if (lane < nJ) nz |= k_task_J(c, jf, c.tdesc + 8 * t, tasks + t, geo + AFFK_GEO * t, J + row * JS, JS) << row;
+        row += c.tdesc[8 * t + TD_DIM];
       }
     }
     // dH: joint limit gradient + elbow / wrist terms (:589-625)
@@ -1061,18 +1220,17 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
     }
     {
       double ex = 0.0, tmp = 0.0;
-      if (P.ns_base != AFFK_WORLD) {   // AFFK_WORLD = base_footprint absent: no extra null space
+      if (P.ns_base >= 0) {   // -1: base_footprint absent, no extra null space
         const int base = P.ns_base;
-        const bool haveBase = true;
-        const double* Ab = k_ref(c, base);
+        const double* Ab = k_slot(c, base);
         // elbows, then hands (boundary 0.15 / 0.0)
-        for (int pass = 0; pass < 2 && haveBase; ++pass) {
+        for (int pass = 0; pass < 2; ++pass) {
           const double boundary = pass ? 0.0 : 0.15;
           for (int side = 0; side < 2; ++side) {
             const int el = pass ? P.ns_hand[side] : P.ns_forearm[side];
             const int sh = P.ns_upperarm[side];
-            if (el == AFFK_WORLD || sh == AFFK_WORLD) continue;
-            const double* Ae = k_ref(c, el); const double* As = k_ref(c, sh);
+            if (el < 0 || sh < 0) continue;
+            const double* Ae = k_slot(c, el); const double* As = k_slot(c, sh);
             double dS[3], dE[3];
             for (int k = 0; k < 3; ++k) { dS[k] = As[k] - Ab[k]; dE[k] = Ae[k] - Ab[k]; }
             const double yS = fma(Ab[3 + 3 + 2], dS[2], fma(Ab[3 + 3 + 1], dS[1], Ab[3 + 3] * dS[0]));
@@ -1088,10 +1246,10 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
         }
         ex = ex + tmp;
         tmp = 0.0;
-        for (int side = 0; side < 2 && haveBase; ++side) {
+        for (int side = 0; side < 2; ++side) {
           const int wr = P.ns_hand[side];
-          if (wr == AFFK_WORLD) continue;
-          const double* Aw = k_ref(c, wr);
+          if (wr < 0) continue;
+          const double* Aw = k_slot(c, wr);
           double dW[3];
           for (int k = 0; k < 3; ++k) dW[k] = Aw[k] - Ab[k];
           const double x = fma(Ab[3 + 2], dW[2], fma(Ab[3 + 1], dW[1], Ab[3] * dW[0]));
@@ -1108,27 +1266,24 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
       // RcsGraph_checkJointSpeeds(dH_extra, dt, IK)
       double sc = 1.0;
       if (lane < nJ && jspeed < AFFK_NO_LIMIT) { const double a = fabs(ex), mx = jspeed * dt; if (a > mx) sc = mx / a; }
-      const double scale = w_min(sc);
-      if (scale < 1.0) ex = ex * (0.99999 * scale);
+      if (w_ballot(sc < 1.0)) { const double scale = w_min(sc); ex = ex * (0.99999 * scale); }
       dHv = dHv + ex * phaseScale;
     }
-    w_sync();   // J complete
-    // joint masks (:636-675)
+    // joint masks (:636-675); row masks of J for the sparse products below
     {
-      int on = 0;
-      if (lane < nJ) for (int r = 0; r < m; ++r) if (J[r * JS + lane] != 0.0) on = 1;
-      const unsigned aMask = w_ballot(on);
+      const unsigned aMask = w_ballot(nz != 0u);
       jmaskBits |= aMask;
       if (lane < nJ && !(((aMask | emask) >> lane) & 1u)) dHv = dHv * 0.0;
+      for (int r = 0; r < m; ++r) { const unsigned rm = w_ballot((nz >> r) & 1u); if (lane == r) rmask[r] = rm; }
     }
     // ---- solveRightInverse
     const double vv = (lane < nJ) ? jw * dHv : 0.0;
-    if (lane < nJ) dH[lane] = vv;          // v = W^-1 dH
-    if (lane < nJ) dq[lane] = jw;          // w, read by the entry lanes below
+    if (lane < nJ) vbuf[lane] = vv;          // v = W^-1 dH
     w_sync();
     if (lane < m) {
       double acc = dxv[lane];
-      for (int j = 0; j < nJ; ++j) acc = fma(J[lane * JS + j], dH[j], acc);
+      unsigned mk = rmask[lane];
+      while (mk) { const int j = w_ffs(mk) - 1; mk &= mk - 1u; acc = fma(J[lane * JS + j], vbuf[j], acc); }
       rhs[lane] = acc;
     }
     {
@@ -1137,33 +1292,34 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
         const int e = ebase + lane;
         if (e < nEnt) {
           // e -> (i, k), k <= i
-          int i = 0;
+          int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
           while ((i + 1) * (i + 2) / 2 <= e) ++i;
+          while (i * (i + 1) / 2 > e) --i;
           const int k = e - i * (i + 1) / 2;
           double acc = 0.0;
-          for (int j = 0; j < nJ; ++j) acc = fma(J[i * JS + j] * dq[j], J[k * JS + j], acc);
+          unsigned mk = rmask[i] & rmask[k];
+          while (mk) { const int j = w_ffs(mk) - 1; mk &= mk - 1u; acc = fma(J[i * JS + j] * wbuf[j], J[k * JS + j], acc); }
           if (i == k) acc = acc + lambda;
           L[i * LS + k] = acc;
         }
       }
     }
     w_sync();
+    // Cholesky, one lane per row, reciprocal pivots
     int singular = 0;
+    double myInv = 1.0;     // lane i keeps 1 / L[i][i]
     for (int j = 0; j < m; ++j) {
-      // column j: lane i >= j computes L[i][j]
-      double sdiag = L[j * LS + j];
-      for (int k = 0; k < j; ++k) sdiag = fma(-L[j * LS + k], L[j * LS + k], sdiag);
-      if (!(sdiag > 0.0)) { singular = 1; break; }
-      const double ljj = sqrt(sdiag);
       double t = 0.0;
-      if (lane > j && lane < m) {
+      if (lane >= j && lane < m) {
         t = L[lane * LS + j];
         for (int k = 0; k < j; ++k) t = fma(-L[lane * LS + k], L[j * LS + k], t);
-        t = t / ljj;
       }
-      w_sync();
-      if (lane == j) L[j * LS + j] = ljj;
-      if (lane > j && lane < m) L[lane * LS + j] = t;
+      const double sdiag = w_shfl(t, j);
+      if (!(sdiag > 0.0)) { singular = 1; break; }
+      const double ljj = sqrt(sdiag);
+      const double inv = 1.0 / ljj;
+      if (lane == j) { L[j * LS + j] = ljj; myInv = inv; }
+      else if (lane > j && lane < m) L[lane * LS + j] = t * inv;
       w_sync();
     }
     int ikRes = 0, id0 = -1, id1 = -1;
@@ -1173,16 +1329,14 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
       // forward substitution L y = rhs (lane i owns y[i]); column oriented
       double yi = (lane < m) ? rhs[lane] : 0.0;
       for (int i = 0; i < m; ++i) {
-        double yfin = 0.0;
-        if (lane == i) { yi = yi / L[i * LS + i]; yfin = yi; }
-        yfin = w_shfl(yfin, i);
+        if (lane == i) yi = yi * myInv;
+        const double yfin = w_shfl(yi, i);
         if (lane > i && lane < m) yi = fma(-L[lane * LS + i], yfin, yi);
       }
       // backward substitution L^T z = y
       for (int i = m - 1; i >= 0; --i) {
-        double zfin = 0.0;
-        if (lane == i) { yi = yi / L[i * LS + i]; zfin = yi; }
-        zfin = w_shfl(zfin, i);
+        if (lane == i) yi = yi * myInv;
+        const double zfin = w_shfl(yi, i);
         if (lane < i) yi = fma(-L[i * LS + lane], zfin, yi);
       }
       if (lane < m) rhs[lane] = yi;
@@ -1190,34 +1344,34 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
       double dqv = 0.0;
       if (lane < nJ) {
         double acc = 0.0;
-        for (int i = 0; i < m; ++i) acc = fma(J[i * JS + lane], rhs[i], acc);
+        unsigned mk = nz;
+        while (mk) { const int i = w_ffs(mk) - 1; mk &= mk - 1u; acc = fma(J[i * JS + lane], rhs[i], acc); }
         dqv = fma(jw, acc, -vv);
       }
       // speed and acceleration limits (:696-723)
       {
         double sc = 1.0;
         if (lane < nJ && jspeed < AFFK_NO_LIMIT) { const double a = fabs(dqv), mx = jspeed * dt; if (a > mx) sc = mx / a; }
-        const double scale = w_min(sc);
-        if (scale < 1.0) dqv = dqv * (0.99999 * scale);
+        if (w_ballot(sc < 1.0)) { const double scale = w_min(sc); dqv = dqv * (0.99999 * scale); }
       }
       const double dynLim = -0.99 * qFilt + 1.0;
       const double invdt = 1.0 / dt;
       double qd = 0.0;
       if (lane < nJ) {
         qd = dqv * invdt;
+        const double qdPrev = qdot[lane];
         if (jacc < AFFK_NO_LIMIT) {
           const double lim = (dynLim * jacc) * dt;
-          const double dv = qd - qdot[lane];
-          if (dv > lim) qd = qdot[lane] + lim;
-          else if (dv < -lim) qd = qdot[lane] - lim;
+          const double dv = qd - qdPrev;
+          if (dv > lim) qd = qdPrev + lim;
+          else if (dv < -lim) qd = qdPrev - lim;
         }
+        qdot[lane] = qd; q[lane] = q[lane] + dqv;     // own elements only: no hazard
       }
       w_sync();
-      if (lane < nJ) { qdot[lane] = qd; q[lane] = q[lane] + dqv; }
-      w_sync();
       // integration, FK, collision model, checkState (:730-752)
-      k_fk(c, false);
-      cm = k_collision(c);
+      k_fk(c, fkLane, false);
+      cm = k_collision(c, r_minDist > 0.001 ? r_minDist : 0.001);
       const unsigned fast = w_ballot(lane < nJ && jspeed < AFFK_NO_LIMIT && fabs(qd) > jspeed * 1.0);
       const unsigned viol = w_ballot(lane < nJ && (q[lane] < jqmin || q[lane] > jqmax));
       if (fast) ikRes = AFF_CODE_SPEED;
@@ -1225,8 +1379,8 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
       else if (cm.minB1 >= 0 && cm.minDist < 0.001) { ikRes = AFF_CODE_COLLISION; id0 = cm.minB1; id1 = cm.minB2; }
     }
     if (ikRes != 0) {
-      if (success) { res.first_code = ikRes; res.first_fail_step = iter; }
-      success = 0; res.code = ikRes; res.fail_step = iter; res.fail_id0 = id0; res.fail_id1 = id1;
+      if (success) { r_first_code = ikRes; r_first_fail = iter; }
+      success = 0; r_code = ikRes; r_fail_step = iter; r_id0 = id0; r_id1 = id1;
     }
     // ---- costs (:226-227)
     {
@@ -1241,36 +1395,39 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
       collSum = collSum + cm.cost;
     }
     // ---- geometry of the new state; tracking error (:297-337)
-    w_sync();
-    if (lane < nTasks) k_task_geo(c, tasks + lane, geo + AFFK_GEO * lane, xcur);
+    if (lane < nTasks) k_task_geo(c, c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur);
     w_sync();
     if (success) {
       double* dxe = dxv;   // stacked over all dims here
-      if (lane < nTasks && ((activeMask >> lane) & 1u)) k_task_dx(tasks + lane, geo + AFFK_GEO * lane, xcur, xdes, dxe + ldg(&tasks[lane].xoff));
+      if (lane < nTasks && ((activeMask >> lane) & 1u)) k_task_dx(c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur, xdes, dxe + c.tdesc[8 * lane + TD_XOFF]);
       w_sync();
       double ev = -1.0; int ek = 0x7fffffff;
       if (lane < xdim && ((activeMask >> myTask) & 1u)) { ev = fabs(dxe[lane]); ek = lane; }
-      w_max_keyed(ev, ek);
-      if (ev > err) err = ev;
-      if (err > AFFK_TRACK_MAX) {
-        int etask = -1, edim = -1;
-        if (ev > 0.0) for (int t = 0; t < nTasks; ++t) if (ek >= ldg(&tasks[t].xoff)) { etask = t; edim = ek - ldg(&tasks[t].xoff); }
-        success = 0; res.code = AFF_CODE_TRACKING; res.first_code = AFF_CODE_TRACKING;
-        res.first_fail_step = iter; res.fail_step = iter; res.fail_id0 = etask; res.fail_id1 = edim;
+      if (w_ballot(ev > err)) {        // the running maximum grows
+        w_max_keyed(ev, ek);
+        err = ev;
+        if (err > AFFK_TRACK_MAX) {
+          int etask = -1, edim = -1;
+          for (int t = 0; t < nTasks; ++t) if (ek >= c.tdesc[8 * t + TD_XOFF]) { etask = t; edim = ek - c.tdesc[8 * t + TD_XOFF]; }
+          success = 0; r_code = AFF_CODE_TRACKING; r_first_code = AFF_CODE_TRACKING;
+          r_first_fail = iter; r_fail_step = iter; r_id0 = etask; r_id1 = edim;
+        }
       }
       w_sync();
     }
-    if (cm.minDist < res.min_dist) { res.min_dist = cm.minDist; res.min_dist_b1 = cm.minB1; res.min_dist_b2 = cm.minB2; }
+    if (cm.minDist < r_minDist) { r_minDist = cm.minDist; r_b1 = cm.minB1; r_b2 = cm.minB2; }
     if (qlog && lane < nJ && rows < qrows) qlog[(size_t)rows * nJ + lane] = q[lane];
     rows++;
   }
-  res.jl_cost = jlSum / (double)rows;
-  res.coll_cost = collSum / (double)rows;
-  res.success = success;
-  res.n_steps = rows;
-  res.track_err = err;
-  res.jmask_bits = (uint64_t)jmaskBits;
-  if (lane == 0) P.results[cand] = res;
+  if (lane == 0) {
+    aff_result res;
+    res.idx = cand; res.success = success; res.code = r_code; res.first_code = r_first_code;
+    res.first_fail_step = r_first_fail; res.fail_step = r_fail_step; res.fail_id0 = r_id0; res.fail_id1 = r_id1;
+    res.min_dist_b1 = r_b1; res.min_dist_b2 = r_b2; res.n_steps = rows; res.reserved = 0;
+    res.jmask_bits = (uint64_t)jmaskBits; res.min_dist = r_minDist;
+    res.jl_cost = jlSum / (double)rows; res.coll_cost = collSum / (double)rows; res.track_err = err;
+    P.results[cand] = res;
+  }
 }
 
 // ------------------------------------------------- prologue (once per batch)
@@ -1324,6 +1481,10 @@ AFF_DEV void k_prologue(const KPlan& P)
     double W[12];
     k_compose(W, sh->A_CB, An);
     for (int k = 0; k < 12; ++k) P.sshapeA[12 * s + k] = W[k];
+    // segment record of capsules / spheres: p, d = length * z-axis, r
+    const bool ssl = sh->type == AFF_SHAPE_SSL;
+    for (int k = 0; k < 3; ++k) { P.sseg[8 * s + k] = W[k]; P.sseg[8 * s + 3 + k] = ssl ? sh->ext[2] * W[9 + k] : 0.0; }
+    P.sseg[8 * s + 6] = sh->ext[0]; P.sseg[8 * s + 7] = 0.0;
   }
   w_sync();
   for (int b = lane; b < P.nStatBodies; b += 32) {

@@ -18,6 +18,7 @@ double w_shfl_xor(double v, int mask);
 int w_shfl_xor(int v, int mask);
 unsigned w_ballot(int pred);
 template <class T> static inline T ldg(const T* p) { return *p; }
+template <class T> static inline T ldg_pair(const T* p) { return *p; }
 static inline int w_popc(unsigned v) { return __builtin_popcount(v); }
 static inline int w_ffs(unsigned v) { return __builtin_ffs((int)v); }
 
@@ -32,6 +33,15 @@ AFF_DEV double w_shfl_xor(double v, int mask) { return __shfl_xor_sync(0xfffffff
 AFF_DEV int w_shfl_xor(int v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
 AFF_DEV unsigned w_ballot(int pred) { return __ballot_sync(0xffffffffu, pred); }
 template <class T> AFF_DEV T ldg(const T* p) { return __ldg(p); }
+// 16-byte record through the read-only path in one LDG.128
+template <class T> AFF_DEV T ldg_pair(const T* p)
+{
+  static_assert(sizeof(T) == 16, "ldg_pair needs a 16-byte record");
+  const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+  T r;
+  *reinterpret_cast<int4*>(&r) = v;
+  return r;
+}
 AFF_DEV int w_popc(unsigned v) { return __popc(v); }
 AFF_DEV int w_ffs(unsigned v) { return __ffs((int)v); }
 

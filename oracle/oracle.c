@@ -605,28 +605,33 @@ int oracle_right_inverse(int m, int n, const double* J, const double* w,
       if (i == k) acc = acc + lambda;
       L[i * m + k] = acc;
     }
+  /* Cholesky with reciprocal pivots: L[i][j] = t * (1 / L[j][j]); the substitutions multiply by the
+   * stored reciprocals as well (one division per column instead of one per entry). */
+  double* invd = (double*)malloc(sizeof(double) * (size_t)(m + 1));
   for (int j = 0; j < m && ok; ++j) {
     double s = L[j * m + j];
     for (int k = 0; k < j; ++k) s = fma(-L[j * m + k], L[j * m + k], s);
     if (!(s > 0.0)) { ok = 0; break; }
     const double ljj = sqrt(s);
+    const double inv = 1.0 / ljj;
     L[j * m + j] = ljj;
+    invd[j] = inv;
     for (int i = j + 1; i < m; ++i) {
       double t = L[i * m + j];
       for (int k = 0; k < j; ++k) t = fma(-L[i * m + k], L[j * m + k], t);
-      L[i * m + j] = t / ljj;
+      L[i * m + j] = t * inv;
     }
   }
   if (ok) {
     for (int i = 0; i < m; ++i) {
       double s = y[i];
       for (int k = 0; k < i; ++k) s = fma(-L[i * m + k], y[k], s);
-      y[i] = s / L[i * m + i];
+      y[i] = s * invd[i];
     }
     for (int i = m - 1; i >= 0; --i) {
       double s = y[i];
       for (int k = m - 1; k > i; --k) s = fma(-L[k * m + i], y[k], s);   /* column-oriented order */
-      y[i] = s / L[i * m + i];
+      y[i] = s * invd[i];
     }
     for (int j = 0; j < n; ++j) {
       double acc = 0.0;
@@ -634,6 +639,7 @@ int oracle_right_inverse(int m, int n, const double* J, const double* w,
       dq[j] = fma(w[j], acc, -v[j]);
     }
   }
+  free(invd);
   free(v); free(L); free(y);
   return ok;
 }

@@ -91,14 +91,14 @@ extern "C" int emu_predict_batch(const aff_scene_desc* scene, const aff_task_des
   if (rc != AFF_OK) { if (errbuf && errlen) { std::strncpy(errbuf, e.c_str(), errlen - 1); errbuf[errlen - 1] = 0; } return rc; }
   KPlan P = H.plan;
   std::vector<double> statA(12 * (size_t)(P.nStatic + 1)), statSC(2 * (size_t)P.nStatic + 2), dynSC(2 * (size_t)P.nDyn + 2),
-      sshapeA(12 * (size_t)P.nStatShapes + 12), sbodyAABB(6 * (size_t)P.nStatBodies + 6);
+      sshapeA(12 * (size_t)P.nStatShapes + 12), sbodyAABB(6 * (size_t)P.nStatBodies + 6), sseg(8 * (size_t)P.nStatShapes + 8);
   std::vector<aff_result> results(nCands);
   P.jq_init = H.jq_init.data(); P.jq0 = H.jq0.data(); P.jq_min = H.jq_min.data(); P.jq_max = H.jq_max.data();
   P.jspeed = H.jspeed.data(); P.jacc = H.jacc.data(); P.jwjl = H.jwjl.data(); P.jwmetric = H.jwmetric.data();
   P.j_node = H.j_node.data(); P.j_type = H.j_type.data(); P.dyn = H.dyn.data(); P.stat = H.stat.data();
-  P.statA = statA.data(); P.statSC = statSC.data(); P.dynSC = dynSC.data(); P.rounds = H.rounds.data();
+  P.statA = statA.data(); P.statSC = statSC.data(); P.dynSC = dynSC.data(); P.fkprog = H.fkprog.data(); P.statpar_ref = H.statpar_ref.data(); P.obj_parent_slot = H.obj_parent_slot.data(); P.obj_parent_tree = H.obj_parent_tree.data(); P.dyn_under = H.dyn_under.data(); P.dyn_chain = H.dyn_chain.data(); P.dynT = H.dynT.data(); P.dynQ = H.dynQ.data();
   P.dshape = H.dshape.data(); P.dbody = H.dbody.data(); P.sshape = H.sshape.data(); P.sbody = H.sbody.data();
-  P.sshapeA = sshapeA.data(); P.sbodyAABB = sbodyAABB.data(); P.always = H.always.data();
+  P.sshapeA = sshapeA.data(); P.sbodyAABB = sbodyAABB.data(); P.pairsSS = H.pairsSS.data(); P.pairsSB = H.pairsSB.data(); P.sseg = sseg.data();
   P.obj_node = H.obj_node.data(); P.obj_body = H.obj_body.data(); P.obj_q6 = H.obj_q6.data();
   P.tasks = H.tasks.data(); P.vias = H.vias.data(); P.acts = H.acts.data(); P.gcons = H.gcons.data(); P.cands = H.cands.data();
   P.results = results.data();
@@ -111,7 +111,7 @@ extern "C" int emu_predict_batch(const aff_scene_desc* scene, const aff_task_des
     out[i] = results[i];
   }
   if (getenv("AFF_EMU_VERBOSE"))
-    std::fprintf(stderr, "emu: nDyn %d nStatic %d rounds %d dynShapes %d dynBodies %d statBodies %d always %d warp smem %zu B\n",
-                 P.nDyn, P.nStatic, P.nRounds, P.nDynShapes, P.nDynBodies, P.nStatBodies, P.nAlways, H.smemBytesPerWarp);
+    std::fprintf(stderr, "emu: nDyn %d nStatic %d rounds %d dynShapes %d dynBodies %d statBodies %d pairs SS %d SB %d warp smem %zu B\n",
+                 P.nDyn, P.nStatic, P.nRounds, P.nDynShapes, P.nDynBodies, P.nStatBodies, P.nSS, P.nSB, H.smemBytesPerWarp);
   return AFF_OK;
 }
