@@ -93,13 +93,20 @@ struct KCtx
   int* tdesc;        // [nTasks][8] kind, eff, ref, frame, axis, xoff, dim, n_joints
   int lane;
   // re-parentable objects (warp-uniform)
-  int objParentSlot[AFFK_MAX_OBJ];
-  int objParentDynamic[AFFK_MAX_OBJ];
-  unsigned objChain[AFFK_MAX_OBJ];
-  int objTree[AFFK_MAX_OBJ];
-  int objMode[AFFK_MAX_OBJ];    // 0 per-shape flags, 1 all on, 2 all off
+  // (two explicit slots instead of arrays: a dynamically indexed member array would push the whole
+  //  context, pointers included, into local memory)
+  int objParentSlot0, objParentSlot1;
+  int objParentDynamic0, objParentDynamic1;
+  unsigned objChain0, objChain1;
+  int objTree0, objTree1;
+  int objMode0, objMode1;       // 0 per-shape flags, 1 all on, 2 all off
   unsigned objHasRel;
 };
+#if AFFK_MAX_OBJ != 2
+#error "object state is written out for two slots"
+#endif
+#define OBJ_GET(c, f, s) ((s) ? (c).f##1 : (c).f##0)
+#define OBJ_SET(c, f, s, v) do { if (s) (c).f##1 = (v); else (c).f##0 = (v); } while (0)
 
 AFF_DEV const double* k_slot(const KCtx& c, int slot) { return c.nodes + 12 * slot; }
 
@@ -125,7 +132,7 @@ AFF_DEV void k_jac_cols(const KCtx& c, const KJointFrame& jf, int slot, const do
 AFF_DEV void k_object_from_q6(const KCtx& c, int n, int slot)
 {
   double A[12];
-  const double* Pp = k_slot(c, c.objParentSlot[slot]);
+  const double* Pp = k_slot(c, OBJ_GET(c, objParentSlot, slot));
   for (int e = 0; e < 12; ++e) A[e] = Pp[e];
   const double* q6 = c.sm + c.P->o_objq6 + 6 * slot;
   for (int k = 0; k < 6; ++k) k_apply_joint(A, k, q6[k]);
@@ -198,11 +205,11 @@ AFF_DEV void k_fk(const KCtx& c, const KFkLane& L, bool init)
       bool doCompose = true, tShared = false;
       if (kind == AFFK_NODE_OBJECT) {
         const int slot = (int)KFK_QIDX(w);
-        Pp = nodes + 12 * c.objParentSlot[slot];
+        Pp = nodes + 12 * OBJ_GET(c, objParentSlot, slot);
         if ((c.objHasRel >> slot) & 1u) tShared = true;
         else {
           doCompose = false;
-          if ((init || c.objParentDynamic[slot]) && L.e == 0) k_object_from_q6(c, n, slot);
+          if ((init || OBJ_GET(c, objParentDynamic, slot)) && L.e == 0) k_object_from_q6(c, n, slot);
         }
       }
       if (doCompose) {
@@ -661,7 +668,7 @@ struct KCollResult { double minDist; int minB1, minB2; double cost; };
 AFF_DEV bool k_dshape_active(const KCtx& c, const KShape* sh, int toggleSlotPlus1)
 {
   if (toggleSlotPlus1) {
-    const int mode = c.objMode[toggleSlotPlus1 - 1];
+    const int mode = OBJ_GET(c, objMode, toggleSlotPlus1 - 1);
     if (mode == 1) return true;
     if (mode == 2) return false;
   }
@@ -740,8 +747,8 @@ AFF_DEV bool k_pair_live(const KCtx& c, int meta, const double* baabb, double th
   const int sa = KP_SLOT_A(meta), sb = KP_SLOT_B(meta);
   bool actA = KP_ACT_A(meta), actB = KP_ACT_B(meta);
   int ta = KP_TREE_A(meta), tb = KP_TREE_B(meta);
-  if (sa) { const int mode = c.objMode[sa - 1]; if (mode == 1) actA = true; else if (mode == 2) actA = false; ta = c.objTree[sa - 1]; }
-  if (sb) { const int mode = c.objMode[sb - 1]; if (mode == 1) actB = true; else if (mode == 2) actB = false; tb = c.objTree[sb - 1]; }
+  if (sa) { const int mode = OBJ_GET(c, objMode, sa - 1); if (mode == 1) actA = true; else if (mode == 2) actA = false; ta = OBJ_GET(c, objTree, sa - 1); }
+  if (sb) { const int mode = OBJ_GET(c, objMode, sb - 1); if (mode == 1) actB = true; else if (mode == 2) actB = false; tb = OBJ_GET(c, objTree, sb - 1); }
   if (!actA || !actB) return false;
   if (ta < 0 && tb < 0) return false;
   if (ta >= 0 && tb >= 0) return ta != tb;
@@ -832,7 +839,7 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
       }
     }
     for (int q = 0; q < 3; ++q) { baabb[6 * lane + q] = mn[q]; baabb[6 * lane + 3 + q] = mx[q]; }
-    btree[lane] = act ? (os ? c.objTree[os - 1] : ldg(&b->tree)) : -2;
+    btree[lane] = act ? (os ? OBJ_GET(c, objTree, os - 1) : ldg(&b->tree)) : -2;
   }
   w_sync();
   // 3. tree AABBs
@@ -1031,16 +1038,17 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
   w_sync();
   // ---- objects
   c.objHasRel = 0u;
-  for (int s = 0; s < AFFK_MAX_OBJ; ++s) { c.objParentSlot[s] = 0; c.objParentDynamic[s] = 0; c.objChain[s] = 0u; c.objTree[s] = -1; c.objMode[s] = 0; }
+  c.objParentSlot0 = c.objParentSlot1 = 0; c.objParentDynamic0 = c.objParentDynamic1 = 0; c.objChain0 = c.objChain1 = 0u;
+  c.objTree0 = c.objTree1 = -1; c.objMode0 = c.objMode1 = 0;
   for (int s = 0; s < P.nObj; ++s) {
     const int ps = ldg(&P.obj_parent_slot[s]);
-    c.objParentSlot[s] = ps;
-    c.objParentDynamic[s] = ps < P.nDyn;
-    c.objChain[s] = c.chain[ps];                      // held in a hand at start: the hand's chain
-    c.objTree[s] = ldg(&P.obj_parent_tree[s]);
+    OBJ_SET(c, objParentSlot, s, ps);
+    OBJ_SET(c, objParentDynamic, s, ps < P.nDyn);
+    OBJ_SET(c, objChain, s, c.chain[ps]);             // held in a hand at start: the hand's chain
+    OBJ_SET(c, objTree, s, ldg(&P.obj_parent_tree[s]));
   }
   w_sync();
-  for (int i = lane; i < P.nDyn; i += 32) { const int uo = ldg(&P.dyn_under[i]); if (uo) c.chain[i] = ldg(&P.dyn_chain[i]) | c.objChain[uo - 1]; }
+  for (int i = lane; i < P.nDyn; i += 32) { const int uo = ldg(&P.dyn_under[i]); if (uo) c.chain[i] = ldg(&P.dyn_chain[i]) | OBJ_GET(c, objChain, uo - 1); }
   if (lane < 6) {
     for (int s = 0; s < P.nObj; ++s)
       sm[P.o_objq6 + 6 * s + lane] = (ldg(&C.pose_slot) == s) ? ldg(&C.pose_q6[lane]) : ldg(&P.obj_q6[6 * s + lane]);
@@ -1087,7 +1095,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
 
   unsigned activeMask = 0u, prevMask = 0u, jmaskBits = 0u;
   unsigned emask = ~(P.rbj_static_chain);
-  for (int s = 0; s < P.nObj; ++s) emask &= ~c.objChain[s];
+  emask &= ~(c.objChain0 | c.objChain1);
   double tnow = 0.0, qFilt = 0.0, err = 0.0, jlSum = 0.0, collSum = 0.0, endTime = ldg(&C.end_abs);
   const double endAbs = ldg(&C.end_abs);
   const double motionDuration = endAbs - ldg(&C.start_abs);
@@ -1143,19 +1151,19 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
             sm[P.o_objrel + 12 * slot + lane] = v;
           }
           c.objHasRel |= 1u << slot;
-          c.objParentSlot[slot] = ps;
-          c.objParentDynamic[slot] = ps < P.nDyn;
-          c.objChain[slot] = c.chain[ps];
+          OBJ_SET(c, objParentSlot, slot, ps);
+          OBJ_SET(c, objParentDynamic, slot, ps < P.nDyn);
+          { const unsigned ch = c.chain[ps]; OBJ_SET(c, objChain, slot, ch); }
           const int pt = ldg(&gcons[k].parent_tree);
-          c.objTree[slot] = (pt <= -2) ? c.objTree[-2 - pt] : pt;
+          { const int tr = (pt <= -2) ? OBJ_GET(c, objTree, -2 - pt) : pt; OBJ_SET(c, objTree, slot, tr); }
           w_sync();
-          for (int i = lane; i < P.nDyn; i += 32) if (ldg(&P.dyn_under[i]) == slot + 1) c.chain[i] = ldg(&P.dyn_chain[i]) | c.objChain[slot];
+          for (int i = lane; i < P.nDyn; i += 32) if (ldg(&P.dyn_under[i]) == slot + 1) c.chain[i] = ldg(&P.dyn_chain[i]) | OBJ_GET(c, objChain, slot);
           emask = ~(P.rbj_static_chain);
-          for (int s = 0; s < P.nObj; ++s) emask &= ~c.objChain[s];
+          emask &= ~(c.objChain0 | c.objChain1);
           gfired |= 1u << k;
         }
       } else {
-        if (tc - tnow < 0.0) { c.objMode[slot] = ldg(&gcons[k].on) ? 1 : 2; gfired |= 1u << k; }
+        if (tc - tnow < 0.0) { const int md = ldg(&gcons[k].on) ? 1 : 2; OBJ_SET(c, objMode, slot, md); gfired |= 1u << k; }
       }
     }
     // activation points
