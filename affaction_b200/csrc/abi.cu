@@ -83,7 +83,8 @@ struct aff_batch
   affk::HostPlan host;
   KPlan plan{};
   DevBuf<double> jq_init, jq0, jq_min, jq_max, jspeed, jacc, jwjl, jwmetric, obj_q6, statA, statSC, dynSC, sshapeA, sbodyAABB, qlog;
-  DevBuf<int32_t> j_node, j_type, fkprog, statpar_ref, obj_parent_slot, obj_parent_tree, dyn_under, obj_node, obj_body;
+  DevBuf<KFkEntry> fktab;
+  DevBuf<int32_t> j_node, j_type, statpar_ref, obj_parent_slot, obj_parent_tree, dyn_under, obj_node, obj_body;
   DevBuf<uint32_t> dyn_chain;
   DevBuf<double> dynT, dynQ;
   DevBuf<KPair> pairsSS, pairsSB;
@@ -100,7 +101,7 @@ struct aff_batch
   {
     jq_init.release(); jq0.release(); jq_min.release(); jq_max.release(); jspeed.release(); jacc.release(); jwjl.release();
     jwmetric.release(); obj_q6.release(); statA.release(); statSC.release(); dynSC.release(); sshapeA.release();
-    sbodyAABB.release(); qlog.release(); j_node.release(); j_type.release(); fkprog.release(); statpar_ref.release(); obj_parent_slot.release(); obj_parent_tree.release(); dyn_under.release(); dyn_chain.release(); dynT.release(); dynQ.release(); pairsSS.release(); pairsSB.release(); sseg.release();
+    sbodyAABB.release(); qlog.release(); j_node.release(); j_type.release(); fktab.release(); statpar_ref.release(); obj_parent_slot.release(); obj_parent_tree.release(); dyn_under.release(); dyn_chain.release(); dynT.release(); dynQ.release(); pairsSS.release(); pairsSB.release(); sseg.release();
     obj_node.release(); obj_body.release(); dyn.release(); stat.release(); dshape.release(); sshape.release();
     dbody.release(); sbody.release(); tasks.release(); vias.release(); acts.release(); gcons.release(); cands.release();
     results.release();
@@ -149,7 +150,7 @@ static int uploadBatch(aff_batch* b, cudaStream_t st)
   P = H.plan;
 #define UP(name) do { CUDA_TRY(b->name.upload(H.name, st)); b->h2dBytes += H.name.size() * sizeof(H.name[0]); } while (0)
   UP(jq_init); UP(jq0); UP(jq_min); UP(jq_max); UP(jspeed); UP(jacc); UP(jwjl); UP(jwmetric); UP(obj_q6);
-  UP(j_node); UP(j_type); UP(fkprog); UP(statpar_ref); UP(obj_parent_slot); UP(obj_parent_tree); UP(dyn_under); UP(dyn_chain); UP(dynT); UP(dynQ); UP(pairsSS); UP(pairsSB); UP(obj_node); UP(obj_body);
+  UP(j_node); UP(j_type); UP(fktab); UP(statpar_ref); UP(obj_parent_slot); UP(obj_parent_tree); UP(dyn_under); UP(dyn_chain); UP(dynT); UP(dynQ); UP(pairsSS); UP(pairsSB); UP(obj_node); UP(obj_body);
   UP(dyn); UP(stat); UP(dshape); UP(sshape); UP(dbody); UP(sbody);
   UP(tasks); UP(vias); UP(acts); UP(gcons); UP(cands);
 #undef UP
@@ -168,7 +169,7 @@ static int uploadBatch(aff_batch* b, cudaStream_t st)
   }
   P.jq_init = b->jq_init.p; P.jq0 = b->jq0.p; P.jq_min = b->jq_min.p; P.jq_max = b->jq_max.p; P.jspeed = b->jspeed.p;
   P.jacc = b->jacc.p; P.jwjl = b->jwjl.p; P.jwmetric = b->jwmetric.p; P.j_node = b->j_node.p; P.j_type = b->j_type.p;
-  P.dyn = b->dyn.p; P.stat = b->stat.p; P.statA = b->statA.p; P.statSC = b->statSC.p; P.dynSC = b->dynSC.p; P.fkprog = b->fkprog.p; P.statpar_ref = b->statpar_ref.p; P.obj_parent_slot = b->obj_parent_slot.p; P.obj_parent_tree = b->obj_parent_tree.p; P.dyn_under = b->dyn_under.p; P.dyn_chain = b->dyn_chain.p; P.dynT = b->dynT.p; P.dynQ = b->dynQ.p;
+  P.dyn = b->dyn.p; P.stat = b->stat.p; P.statA = b->statA.p; P.statSC = b->statSC.p; P.dynSC = b->dynSC.p; P.fktab = b->fktab.p; P.statpar_ref = b->statpar_ref.p; P.obj_parent_slot = b->obj_parent_slot.p; P.obj_parent_tree = b->obj_parent_tree.p; P.dyn_under = b->dyn_under.p; P.dyn_chain = b->dyn_chain.p; P.dynT = b->dynT.p; P.dynQ = b->dynQ.p;
   P.dshape = b->dshape.p; P.dbody = b->dbody.p; P.sshape = b->sshape.p; P.sbody = b->sbody.p; P.sshapeA = b->sshapeA.p;
   P.sbodyAABB = b->sbodyAABB.p; P.pairsSS = b->pairsSS.p; P.pairsSB = b->pairsSB.p; P.sseg = b->sseg.p; P.obj_node = b->obj_node.p; P.obj_body = b->obj_body.p; P.obj_q6 = b->obj_q6.p;
   P.tasks = b->tasks.p; P.vias = b->vias.p; P.acts = b->acts.p; P.gcons = b->gcons.p; P.cands = b->cands.p;

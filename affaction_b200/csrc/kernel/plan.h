@@ -55,6 +55,7 @@ struct KShape
   int32_t active0;     // RCSSHAPE_COMPUTE_DISTANCE at start
   int32_t node;        // dynamic shapes: shared-memory slot of the owning body; static shapes: node reference
   int32_t pad;
+  double bound;        // radius of a sphere around the shape's centre that contains it (culling only)
   double ext[3];
   double A_CB[12];
 };
@@ -78,6 +79,9 @@ struct KShapeBody
 // dynamic; KP_SWAP says it is the SECOND argument in ascending-body-id order.
 // Segment-box/cylinder list: `a` is the segment, `b` the box or cylinder.
 struct __attribute__((aligned(16))) KPair { int32_t a, b, key, meta; };
+
+// One lane's work in one FK round (see FKOP_* in rollout.cuh).
+struct __attribute__((aligned(32))) KFkEntry { uint32_t w0, w1; double t0, t1, t2; };
 
 struct KTask
 {
@@ -131,7 +135,7 @@ struct KPlan
   double* statA;                   // [nStatic*12] world transforms   (written by the prologue)
   double* statSC;                  // [nStatic*2]  sin/cos of constant joints
   double* dynSC;                   // [nDyn*2]     sin/cos of constant joints on dynamic nodes
-  const int32_t* fkprog;           // [nRounds*2] packed FK program words: two nodes per round (KFK_* in rollout.cuh)
+  const KFkEntry* fktab;           // [nRounds*32] per-lane FK table
   const double* dynT;              // [nDyn*12] fixed transform of each dynamic node
   const double* dynQ;              // [nDyn] value of constant joints
   const int32_t* statpar_ref;      // [nStatPar] static nodes copied into shared memory as parents

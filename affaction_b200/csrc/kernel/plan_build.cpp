@@ -245,16 +245,40 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     const int nD = (int)H.dyn.size();
     H.dynT.resize(12 * (size_t)std::max(nD, 1)); H.dynQ.resize((size_t)std::max(nD, 1));
     for (int n = 0; n < nD; ++n) { std::memcpy(&H.dynT[12 * n], H.dyn[n].T, sizeof(double) * 12); H.dynQ[n] = H.dyn[n].qconst; }
-    H.fkprog.assign(H.rounds.size(), 255);
-    for (size_t i = 0; i < H.rounds.size(); ++i) {
-      const int n = H.rounds[i];
-      if (n < 0) continue;
-      const KNode& nd = H.dyn[n];
-      const int pslot = slotOfRef(nd.parent);
-      const int ident = (nd.kind == AFFK_NODE_OBJECT) ? 0 : nd.identityT;
-      H.fkprog[i] = (int32_t)((uint32_t)n | ((uint32_t)pslot << 8) | ((uint32_t)nd.kind << 16) | ((uint32_t)nd.jtype << 18) |
-                              ((uint32_t)ident << 21) | ((uint32_t)(nd.qidx & 63) << 22));
-    }
+    // per-lane FK table
+    const int nR = (int)H.rounds.size() / 2;
+    KFkEntry idle; std::memset(&idle, 0, sizeof(idle));
+    H.fktab.assign((size_t)nR * 32, idle);
+    for (int r = 0; r < nR; ++r)
+      for (int grp = 0; grp < 2; ++grp) {
+        const int n = H.rounds[2 * r + grp];
+        if (n < 0) continue;
+        const KNode& nd = H.dyn[n];
+        const int pslot = slotOfRef(nd.parent);
+        for (int e = 0; e < 12; ++e) {
+          const int lane = grp * 12 + e;
+          KFkEntry& en = H.fktab[(size_t)r * 32 + lane];
+          const int row = e < 3 ? -1 : (e - 3) / 3, col = e < 3 ? e : (e - 3) % 3;
+          const int tb = e < 3 ? 0 : 3 + 3 * row;
+          en.t0 = nd.T[tb]; en.t1 = nd.T[tb + 1]; en.t2 = nd.T[tb + 2];
+          uint32_t op = 2, partner = (uint32_t)lane, pbase = (uint32_t)(12 * pslot), dst = (uint32_t)(12 * n + e), w1 = 0;
+          if (nd.kind == AFFK_NODE_OBJECT) { op = 6; w1 = (uint32_t)(nd.qidx & 3) | ((uint32_t)n << 8); }
+          else if (nd.kind == AFFK_NODE_FIXED) { if (nd.identityT) { op = 1; pbase = (uint32_t)(12 * pslot + e); } }
+          else {
+            const bool isRot = nd.jtype >= AFF_JNT_ROT_X;
+            const int d = isRot ? nd.jtype - AFF_JNT_ROT_X : nd.jtype;
+            if (isRot && e >= 3) {
+              const int a = (d + 1) % 3, b = (d + 2) % 3;
+              if (row == a) { op = 3; partner = (uint32_t)(grp * 12 + 3 + 3 * b + col); }
+              else if (row == b) { op = 4; partner = (uint32_t)(grp * 12 + 3 + 3 * a + col); }
+            } else if (!isRot && e < 3) { op = 5; partner = (uint32_t)(grp * 12 + 3 + 3 * d + e); }
+            w1 = (nd.kind == AFFK_NODE_JOINT_IK) ? (uint32_t)(nd.qidx & 63) : (0x80u | ((uint32_t)n << 8));
+          }
+          if (pbase > 4095u || dst > 4095u) { err = "FK table: node array too large"; return AFF_ERR_CAPACITY; }
+          en.w0 = pbase | (dst << 12) | (op << 24) | (partner << 27);
+          en.w1 = w1;
+        }
+      }
   }
   // objects below objects (a connect parent under another object) would need a dynamic schedule
   for (int b : objBodies) if (S.parent[b] >= 0 && underObj[S.parent[b]]) { err = "objects nested in objects are not supported"; return AFF_ERR_UNSUPPORTED; }
@@ -274,6 +298,12 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
       sh.type = S.stype[s]; sh.active0 = S.sdist[s]; sh.node = bodyRef[b];
       std::memcpy(sh.ext, &S.ext[3 * s], sizeof(double) * 3);
       std::memcpy(sh.A_CB, &S.A_CB[12 * s], sizeof(double) * 12);
+      // bounding radius about the shape centre (segment midpoint / frame origin); used for culling with a margin only
+      if (sh.type == AFF_SHAPE_SSL) sh.bound = 0.5 * std::fabs(sh.ext[2]) + sh.ext[0];
+      else if (sh.type == AFF_SHAPE_SPHERE) sh.bound = sh.ext[0];
+      else if (sh.type == AFF_SHAPE_BOX) sh.bound = 0.5 * std::sqrt(sh.ext[0] * sh.ext[0] + sh.ext[1] * sh.ext[1] + sh.ext[2] * sh.ext[2]);
+      else sh.bound = std::sqrt(sh.ext[0] * sh.ext[0] + 0.25 * sh.ext[2] * sh.ext[2]);
+      sh.bound *= 1.0 + 1.0e-12;
       if (sh.active0) sb.any_active0 = 1;
       dst.push_back(sh);
     }

@@ -140,109 +140,69 @@ AFF_DEV void k_object_from_q6(const KCtx& c, int n, int slot)
   for (int e = 0; e < 12; ++e) out[e] = A[e];
 }
 
-// Per-lane constants of the element-parallel FK (lane -> HTr element e of group grp).
-struct KFkLane
-{
-  int tBase;       // first T element of the 3-term product
-  int pCol;        // column offset into the parent's rot rows (P[3+pCol], P[6+pCol], P[9+pCol])
-  int isOrg;       // e < 3: add P[e]
-  int e;           // element index, 12 = idle lane
-  unsigned rot;    // per rotation axis d: bits [7d..7d+4] partner lane, [7d+5] role A, [7d+6] role B
-  unsigned trans;  // per translation axis d: bits [5d..5d+4] partner lane (valid for e < 3)
-};
-
-AFF_DEV KFkLane k_fk_lane(int lane)
-{
-  KFkLane L;
-  const int grp = lane / 12, e = (grp < 2) ? lane % 12 : 12;
-  L.e = e; L.isOrg = e < 3; L.rot = 0u; L.trans = 0u;
-  if (e < 3) { L.tBase = 0; L.pCol = e; }
-  else if (e < 12) { L.tBase = 3 + 3 * ((e - 3) / 3); L.pCol = (e - 3) % 3; }
-  else { L.tBase = 0; L.pCol = 0; }
-  for (int d = 0; d < 3; ++d) {
-    unsigned partner = (unsigned)lane, ra = 0u, rb = 0u;
-    if (e >= 3 && e < 12) {
-      const int a = (d + 1) % 3, b = (d + 2) % 3, row = (e - 3) / 3, col = (e - 3) % 3;
-      if (row == a) { ra = 1u; partner = (unsigned)(grp * 12 + 3 + 3 * b + col); }
-      else if (row == b) { rb = 1u; partner = (unsigned)(grp * 12 + 3 + 3 * a + col); }
-    }
-    L.rot |= (partner | (ra << 5) | (rb << 6)) << (7 * d);
-    const unsigned tp = (e < 3) ? (unsigned)(grp * 12 + 3 + 3 * d + e) : (unsigned)lane;
-    L.trans |= tp << (5 * d);
-  }
-  return L;
-}
-
-// FK program word (plan_build.cpp): one per (round, group)
-#define KFK_NODE(w) ((w) & 255)               /* 255 = empty slot */
-#define KFK_PARENT(w) (((w) >> 8) & 255)      /* shared-memory slot of the parent */
-#define KFK_KIND(w) (((w) >> 16) & 3)
-#define KFK_JTYPE(w) (((w) >> 18) & 7)
-#define KFK_IDENT(w) (((w) >> 21) & 1)
-#define KFK_QIDX(w) (((w) >> 22) & 63)
+// FK table entry, one per (round, lane): everything lane `l` needs to produce its HTr element of
+// the node scheduled in its group this round (plan_build.cpp: buildFkTable).
+//   w0: bits 0-11 parent element base (doubles from the node array), 12-23 destination element,
+//       24-26 op, 27-31 partner lane
+//   w1: bits 0-5 jacobi index (IK joints) | bits 8-15 dynamic node (constant joints, objects)
+//   t0..t2: the three entries of the node's fixed transform this lane multiplies with
+// Element e of T o P:  org: P[e] + T0 P[3+e] + T1 P[6+e] + T2 P[9+e];  rot(i,j): T[i][0] P[3+j] + T[i][1] P[6+j] + T[i][2] P[9+j]
+#define FKOP_IDLE 0
+#define FKOP_COPY 1      /* identity transform: copy the parent's element            */
+#define FKOP_FIXED 2     /* compose only                                            */
+#define FKOP_ROT_A 3     /* compose, then ra' = c ra + s rb  (partner holds rb)      */
+#define FKOP_ROT_B 4     /* compose, then rb' = c rb - s ra  (partner holds ra)      */
+#define FKOP_TRANS 5     /* compose, then org += q * axis    (partner holds axis)    */
+#define FKOP_OBJECT 6    /* re-parentable object: transform and parent are run-time  */
 
 // RcsGraph_setState for the dynamic nodes: 12 lanes per node (one per HTr element), two nodes
 // per round on the host-built schedule; all parents are shared-memory slots.
-AFF_DEV void k_fk(const KCtx& c, const KFkLane& L, bool init)
+AFF_DEV void k_fk(const KCtx& c, bool init)
 {
   const KPlan& P = *c.P;
   double* sn = c.sm + P.o_sn; double* cs = c.sm + P.o_cs;
   const double* q = c.sm + P.o_q;
   double* nodes = c.nodes;
-  if (c.lane < P.nJ) { double s, co; aff_sincos(q[c.lane], &s, &co); sn[c.lane] = s; cs[c.lane] = co; }
+  const int lane = c.lane;
+  if (lane < P.nJ) { double s, co; aff_sincos(q[lane], &s, &co); sn[lane] = s; cs[lane] = co; }
   w_sync();
-  const int grp = c.lane / 12;
-  for (int r = 0; r < P.nRounds; ++r) {
-    const unsigned w = (grp < 2) ? (unsigned)ldg(&P.fkprog[2 * r + grp]) : 255u;
-    const int n = (int)KFK_NODE(w);
-    double val = 0.0;
-    const int kind = (int)KFK_KIND(w), jtype = (int)KFK_JTYPE(w);
-    bool store = false;
-    double s = 0.0, co = 1.0, qv = 0.0;
-    if (n != 255 && L.e < 12) {
-      const double* Pp = nodes + 12 * (int)KFK_PARENT(w);
-      const double* T = P.dynT + 12 * n;
-      bool doCompose = true, tShared = false;
-      if (kind == AFFK_NODE_OBJECT) {
-        const int slot = (int)KFK_QIDX(w);
-        Pp = nodes + 12 * OBJ_GET(c, objParentSlot, slot);
-        if ((c.objHasRel >> slot) & 1u) tShared = true;
-        else {
-          doCompose = false;
-          if ((init || OBJ_GET(c, objParentDynamic, slot)) && L.e == 0) k_object_from_q6(c, n, slot);
-        }
+  const int e = lane % 12;
+  const KFkEntry* tab = P.fktab + lane;
+  for (int r = 0; r < P.nRounds; ++r, tab += 32) {
+    const KFkEntry en = ldg_fk(tab);
+    const int op = (int)((en.w0 >> 24) & 7u);
+    const int pbase = (int)(en.w0 & 4095u), dst = (int)((en.w0 >> 12) & 4095u);
+    const int partner = (int)(en.w0 >> 27);
+    double val = 0.0, s = 0.0, co = 1.0;
+    bool store = op != FKOP_IDLE;
+    if (op == FKOP_COPY) val = nodes[pbase];
+    else if (op >= FKOP_FIXED && op <= FKOP_TRANS) {
+      const int col = (e < 3) ? e : (e - 3) % 3;
+      const double* Pp = nodes + pbase;           // pbase already points at the parent node
+      const double acc0 = (e < 3) ? Pp[e] : 0.0;
+      val = fma(en.t2, Pp[9 + col], fma(en.t1, Pp[6 + col], fma(en.t0, Pp[3 + col], acc0)));
+      if (op != FKOP_FIXED) {
+        if (en.w1 & 0x80u) { const int n = (int)((en.w1 >> 8) & 255u); s = ldg(&P.dynSC[2 * n]); co = ldg(&P.dynSC[2 * n + 1]); if (op == FKOP_TRANS) s = ldg(&P.dynQ[n]); }
+        else { const int qi = (int)(en.w1 & 63u); s = (op == FKOP_TRANS) ? q[qi] : sn[qi]; co = cs[qi]; }
       }
-      if (doCompose) {
-        store = true;
-        if (KFK_IDENT(w)) val = Pp[L.e];
-        else {
-          const double acc0 = L.isOrg ? Pp[L.e] : 0.0;
-          double t0, t1, t2;
-          if (tShared) { const double* R = c.sm + P.o_objrel + 12 * (int)KFK_QIDX(w); t0 = R[L.tBase]; t1 = R[L.tBase + 1]; t2 = R[L.tBase + 2]; }
-          else { t0 = ldg(&T[L.tBase]); t1 = ldg(&T[L.tBase + 1]); t2 = ldg(&T[L.tBase + 2]); }
-          val = fma(t2, Pp[9 + L.pCol], fma(t1, Pp[6 + L.pCol], fma(t0, Pp[3 + L.pCol], acc0)));
-        }
-        if (kind == AFFK_NODE_JOINT_IK) { const int qi = (int)KFK_QIDX(w); s = sn[qi]; co = cs[qi]; qv = q[qi]; }
-        else if (kind == AFFK_NODE_JOINT_CONST) { s = ldg(&P.dynSC[2 * n]); co = ldg(&P.dynSC[2 * n + 1]); qv = ldg(&P.dynQ[n]); }
+    } else if (op == FKOP_OBJECT) {
+      const int slot = (int)(en.w1 & 3u), n = (int)((en.w1 >> 8) & 255u);
+      if ((c.objHasRel >> slot) & 1u) {
+        const double* Pp = nodes + 12 * OBJ_GET(c, objParentSlot, slot);
+        const double* R = c.sm + P.o_objrel + 12 * slot;
+        const int col = (e < 3) ? e : (e - 3) % 3, tb = (e < 3) ? 0 : 3 + 3 * ((e - 3) / 3);
+        const double acc0 = (e < 3) ? Pp[e] : 0.0;
+        val = fma(R[tb + 2], Pp[9 + col], fma(R[tb + 1], Pp[6 + col], fma(R[tb], Pp[3 + col], acc0)));
+      } else {
+        store = false;
+        if ((init || OBJ_GET(c, objParentDynamic, slot)) && e == 0) k_object_from_q6(c, n, slot);
       }
     }
-    const bool isJoint = store && (kind == AFFK_NODE_JOINT_IK || kind == AFFK_NODE_JOINT_CONST);
-    const bool isRot = jtype >= AFF_JNT_ROT_X;
-    const int d = isRot ? jtype - AFF_JNT_ROT_X : jtype;
-    const unsigned ri = (L.rot >> (7 * d)) & 127u;
-    const int partner = isJoint ? (isRot ? (int)(ri & 31u) : (int)((L.trans >> (5 * d)) & 31u)) : c.lane;
     const double other = w_shfl(val, partner);
-    if (store) {
-      if (isJoint) {
-        if (isRot) {
-          if (ri & 32u) val = fma(s, other, co * val);             // ra' = c ra + s rb
-          else if (ri & 64u) val = fma(co, val, -(s * other));     // rb' = c rb - s ra
-        } else if (L.isOrg) {
-          val = fma(qv, other, val);
-        }
-      }
-      nodes[12 * n + L.e] = val;
-    }
+    if (op == FKOP_ROT_A) val = fma(s, other, co * val);
+    else if (op == FKOP_ROT_B) val = fma(co, val, -(s * other));
+    else if (op == FKOP_TRANS) val = fma(s, other, val);
+    if (store) nodes[dst] = val;
     w_sync();
   }
 }
@@ -806,6 +766,7 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
         const double len = ldg(&sh->ext[2]);
         for (int e = 0; e < 3; ++e) { const double ax = k_compose_elem(sh->A_CB, An, 9 + e); W[9 + e] = ax; W[3 + e] = len * ax; }
       } else { W[3] = 0.0; W[4] = 0.0; W[5] = 0.0; }
+      W[6] = ldg(&sh->ext[0]); W[7] = ldg(&sh->bound);
     } else {
       for (int e = 0; e < 12; ++e) W[e] = k_compose_elem(sh->A_CB, An, e);
     }
@@ -889,21 +850,29 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
   // 5. narrow phase over the precompiled, type-sorted shape-pair lists
   KPairAcc acc;
   acc.best = DBL_MAX; acc.bestKey = 0x7fffffff; acc.nCostly = 0;
+  // A pair whose bounding spheres are farther apart than `need` cannot become the minimum the caller
+  // looks at, cannot collide and cannot cost (thr <= 1 mm <= need): its exact distance is skipped.
+  const double cullMargin = 1.0e-9;
   // 5a. segment - segment (capsules, spheres)
   for (int base = 0; base < P.nSS; base += 32) {
     const int i = base + lane;
-    double d = DBL_MAX; int key = 0x7fffffff, meta = 0; bool on = false;
+    double d = DBL_MAX; int key = 0x7fffffff; bool on = false;
     if (i < P.nSS) {
       const KPair pr = ldg_pair(&P.pairsSS[i]);
-      meta = pr.meta; key = pr.key;
-      on = k_pair_live(c, meta, baabb, thr);
-      if (on) {
+      key = pr.key;
+      if (k_pair_live(c, pr.meta, baabb, thr)) {
         const double* A = shp + 12 * pr.a;
-        const double rA = ldg(&P.dshape[pr.a].ext[0]);
-        double pB[3], dB[3], rB;
-        if (pr.b >= 0) { const double* B = shp + 12 * pr.b; for (int k = 0; k < 3; ++k) { pB[k] = B[k]; dB[k] = B[3 + k]; } rB = ldg(&P.dshape[pr.b].ext[0]); }
-        else { const double* B = P.sseg + 8 * (-1 - pr.b); for (int k = 0; k < 3; ++k) { pB[k] = ldg(&B[k]); dB[k] = ldg(&B[3 + k]); } rB = ldg(&B[6]); }
-        d = KP_SWAP(meta) ? (k_seg_seg(pB, dB, A, A + 3) - rB) - rA : (k_seg_seg(A, A + 3, pB, dB) - rA) - rB;
+        const double rA = A[6];
+        double pB[3], dB[3], rB, bB;
+        if (pr.b >= 0) { const double* B = shp + 12 * pr.b; for (int k = 0; k < 3; ++k) { pB[k] = B[k]; dB[k] = B[3 + k]; } rB = B[6]; bB = B[7]; }
+        else { const double* B = P.sseg + 8 * (-1 - pr.b); for (int k = 0; k < 3; ++k) { pB[k] = ldg(&B[k]); dB[k] = ldg(&B[3 + k]); } rB = ldg(&B[6]); bB = ldg(&B[7]); }
+        double cd2 = 0.0;
+        for (int k = 0; k < 3; ++k) { const double dc = (A[k] + 0.5 * A[3 + k]) - (pB[k] + 0.5 * dB[k]); cd2 += dc * dc; }
+        const double lim = need + (A[7] + bB) + cullMargin;
+        if (!(cd2 >= lim * lim)) {
+          on = true;
+          d = KP_SWAP(pr.meta) ? (k_seg_seg(pB, dB, A, A + 3) - rB) - rA : (k_seg_seg(A, A + 3, pB, dB) - rA) - rB;
+        }
       }
     }
     k_pair_account(acc, on, d, key, thr, ckey, cdist);
@@ -911,24 +880,32 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
   // 5b. segment - box and segment - cylinder (the segment is always the first argument)
   for (int base = 0; base < P.nSB; base += 32) {
     const int i = base + lane;
-    double d = DBL_MAX; int key = 0x7fffffff, meta = 0; bool on = false;
+    double d = DBL_MAX; int key = 0x7fffffff; bool on = false;
     if (i < P.nSB) {
       const KPair pr = ldg_pair(&P.pairsSB[i]);
-      meta = pr.meta; key = pr.key;
-      on = k_pair_live(c, meta, baabb, thr);
-      if (on) {
+      key = pr.key;
+      if (k_pair_live(c, pr.meta, baabb, thr)) {
         // a = segment shape (dynamic >= 0 / static < 0), b = box or cylinder shape
-        double pS[3], dS[3], rS, F[12], ext[3]; int typeB;
-        if (pr.a >= 0) { const double* A = shp + 12 * pr.a; for (int k = 0; k < 3; ++k) { pS[k] = A[k]; dS[k] = A[3 + k]; } rS = ldg(&P.dshape[pr.a].ext[0]); }
-        else { const double* A = P.sseg + 8 * (-1 - pr.a); for (int k = 0; k < 3; ++k) { pS[k] = ldg(&A[k]); dS[k] = ldg(&A[3 + k]); } rS = ldg(&A[6]); }
-        if (pr.b >= 0) { const double* B = shp + 12 * pr.b; for (int e = 0; e < 12; ++e) F[e] = B[e]; const KShape* sb = P.dshape + pr.b; typeB = ldg(&sb->type); for (int k = 0; k < 3; ++k) ext[k] = ldg(&sb->ext[k]); }
-        else { const int si = -1 - pr.b; for (int e = 0; e < 12; ++e) F[e] = ldg(&P.sshapeA[12 * si + e]); const KShape* sb = P.sshape + si; typeB = ldg(&sb->type); for (int k = 0; k < 3; ++k) ext[k] = ldg(&sb->ext[k]); }
-        double rel[3], pl[3], dl[3];
-        for (int k = 0; k < 3; ++k) rel[k] = pS[k] - F[k];
-        k_mulv(pl, F + 3, rel);
-        k_mulv(dl, F + 3, dS);
-        if (typeB == AFF_SHAPE_BOX) { const double h[3] = {0.5 * ext[0], 0.5 * ext[1], 0.5 * ext[2]}; d = k_seg_box(pl, dl, h) - rS; }
-        else d = k_seg_cyl(pl, dl, 0.5 * ext[2], ext[0]) - rS;
+        double pS[3], dS[3], rS, bS, cB[3], bB;
+        if (pr.a >= 0) { const double* A = shp + 12 * pr.a; for (int k = 0; k < 3; ++k) { pS[k] = A[k]; dS[k] = A[3 + k]; } rS = A[6]; bS = A[7]; }
+        else { const double* A = P.sseg + 8 * (-1 - pr.a); for (int k = 0; k < 3; ++k) { pS[k] = ldg(&A[k]); dS[k] = ldg(&A[3 + k]); } rS = ldg(&A[6]); bS = ldg(&A[7]); }
+        if (pr.b >= 0) { const double* B = shp + 12 * pr.b; for (int k = 0; k < 3; ++k) cB[k] = B[k]; bB = ldg(&P.dshape[pr.b].bound); }
+        else { const double* B = P.sseg + 8 * (-1 - pr.b); for (int k = 0; k < 3; ++k) cB[k] = ldg(&B[k]); bB = ldg(&B[7]); }
+        double cd2 = 0.0;
+        for (int k = 0; k < 3; ++k) { const double dc = (pS[k] + 0.5 * dS[k]) - cB[k]; cd2 += dc * dc; }
+        const double lim = need + (bS + bB) + cullMargin;
+        if (!(cd2 >= lim * lim)) {
+          on = true;
+          double F[12], ext[3]; int typeB;
+          if (pr.b >= 0) { const double* B = shp + 12 * pr.b; for (int e = 0; e < 12; ++e) F[e] = B[e]; const KShape* sb = P.dshape + pr.b; typeB = ldg(&sb->type); for (int k = 0; k < 3; ++k) ext[k] = ldg(&sb->ext[k]); }
+          else { const int si = -1 - pr.b; for (int e = 0; e < 12; ++e) F[e] = ldg(&P.sshapeA[12 * si + e]); const KShape* sb = P.sshape + si; typeB = ldg(&sb->type); for (int k = 0; k < 3; ++k) ext[k] = ldg(&sb->ext[k]); }
+          double rel[3], pl[3], dl[3];
+          for (int k = 0; k < 3; ++k) rel[k] = pS[k] - F[k];
+          k_mulv(pl, F + 3, rel);
+          k_mulv(dl, F + 3, dS);
+          if (typeB == AFF_SHAPE_BOX) { const double h[3] = {0.5 * ext[0], 0.5 * ext[1], 0.5 * ext[2]}; d = k_seg_box(pl, dl, h) - rS; }
+          else d = k_seg_cyl(pl, dl, 0.5 * ext[2], ext[0]) - rS;
+        }
       }
     }
     k_pair_account(acc, on, d, key, thr, ckey, cdist);
@@ -1054,11 +1031,10 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
       sm[P.o_objq6 + 6 * s + lane] = (ldg(&C.pose_slot) == s) ? ldg(&C.pose_q6[lane]) : ldg(&P.obj_q6[6 * s + lane]);
   }
   if (lane < xdim) { st[3 * lane] = 0.0; st[3 * lane + 1] = 0.0; st[3 * lane + 2] = 0.0; xdes[lane] = 0.0; }
-  const KFkLane fkLane = k_fk_lane(lane);
   w_sync();
 
   // ---- initial state
-  k_fk(c, fkLane, true);
+  k_fk(c, true);
   const int nSteps = ldg(&C.n_steps);
   const int qrows = P.qlog_rows;
   double* qlog = P.qlog ? P.qlog + (size_t)cand * qrows * nJ : nullptr;
@@ -1378,7 +1354,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
       }
       w_sync();
       // integration, FK, collision model, checkState (:730-752)
-      k_fk(c, fkLane, false);
+      k_fk(c, false);
       cm = k_collision(c, r_minDist > 0.001 ? r_minDist : 0.001);
       const unsigned fast = w_ballot(lane < nJ && jspeed < AFFK_NO_LIMIT && fabs(qd) > jspeed * 1.0);
       const unsigned viol = w_ballot(lane < nJ && (q[lane] < jqmin || q[lane] > jqmax));
@@ -1492,7 +1468,7 @@ AFF_DEV void k_prologue(const KPlan& P)
     // segment record of capsules / spheres: p, d = length * z-axis, r
     const bool ssl = sh->type == AFF_SHAPE_SSL;
     for (int k = 0; k < 3; ++k) { P.sseg[8 * s + k] = W[k]; P.sseg[8 * s + 3 + k] = ssl ? sh->ext[2] * W[9 + k] : 0.0; }
-    P.sseg[8 * s + 6] = sh->ext[0]; P.sseg[8 * s + 7] = 0.0;
+    P.sseg[8 * s + 6] = sh->ext[0]; P.sseg[8 * s + 7] = sh->bound;
   }
   w_sync();
   for (int b = lane; b < P.nStatBodies; b += 32) {

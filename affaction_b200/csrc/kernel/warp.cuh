@@ -19,6 +19,7 @@ int w_shfl_xor(int v, int mask);
 unsigned w_ballot(int pred);
 template <class T> static inline T ldg(const T* p) { return *p; }
 template <class T> static inline T ldg_pair(const T* p) { return *p; }
+template <class T> static inline T ldg_fk(const T* p) { return *p; }
 static inline int w_popc(unsigned v) { return __builtin_popcount(v); }
 static inline int w_ffs(unsigned v) { return __builtin_ffs((int)v); }
 
@@ -40,6 +41,17 @@ template <class T> AFF_DEV T ldg_pair(const T* p)
   const int4 v = __ldg(reinterpret_cast<const int4*>(p));
   T r;
   *reinterpret_cast<int4*>(&r) = v;
+  return r;
+}
+// 32-byte record through the read-only path in two LDG.128
+template <class T> AFF_DEV T ldg_fk(const T* p)
+{
+  static_assert(sizeof(T) == 32, "ldg_fk needs a 32-byte record");
+  const int4 a = __ldg(reinterpret_cast<const int4*>(p));
+  const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+  T r;
+  reinterpret_cast<int4*>(&r)[0] = a;
+  reinterpret_cast<int4*>(&r)[1] = b;
   return r;
 }
 AFF_DEV int w_popc(unsigned v) { return __popc(v); }

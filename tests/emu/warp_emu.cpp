@@ -96,7 +96,7 @@ extern "C" int emu_predict_batch(const aff_scene_desc* scene, const aff_task_des
   P.jq_init = H.jq_init.data(); P.jq0 = H.jq0.data(); P.jq_min = H.jq_min.data(); P.jq_max = H.jq_max.data();
   P.jspeed = H.jspeed.data(); P.jacc = H.jacc.data(); P.jwjl = H.jwjl.data(); P.jwmetric = H.jwmetric.data();
   P.j_node = H.j_node.data(); P.j_type = H.j_type.data(); P.dyn = H.dyn.data(); P.stat = H.stat.data();
-  P.statA = statA.data(); P.statSC = statSC.data(); P.dynSC = dynSC.data(); P.fkprog = H.fkprog.data(); P.statpar_ref = H.statpar_ref.data(); P.obj_parent_slot = H.obj_parent_slot.data(); P.obj_parent_tree = H.obj_parent_tree.data(); P.dyn_under = H.dyn_under.data(); P.dyn_chain = H.dyn_chain.data(); P.dynT = H.dynT.data(); P.dynQ = H.dynQ.data();
+  P.statA = statA.data(); P.statSC = statSC.data(); P.dynSC = dynSC.data(); P.fktab = H.fktab.data(); P.statpar_ref = H.statpar_ref.data(); P.obj_parent_slot = H.obj_parent_slot.data(); P.obj_parent_tree = H.obj_parent_tree.data(); P.dyn_under = H.dyn_under.data(); P.dyn_chain = H.dyn_chain.data(); P.dynT = H.dynT.data(); P.dynQ = H.dynQ.data();
   P.dshape = H.dshape.data(); P.dbody = H.dbody.data(); P.sshape = H.sshape.data(); P.sbody = H.sbody.data();
   P.sshapeA = sshapeA.data(); P.sbodyAABB = sbodyAABB.data(); P.pairsSS = H.pairsSS.data(); P.pairsSB = H.pairsSB.data(); P.sseg = sseg.data();
   P.obj_node = H.obj_node.data(); P.obj_body = H.obj_body.data(); P.obj_q6 = H.obj_q6.data();
