@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cfloat>
 #include <cstdio>
 #include <cstring>
@@ -15,6 +17,7 @@
 #include "kernel/rollout.cuh"
 
 #define AFF_WARPS_PER_BLOCK 4
+#define AFF_BLOCKS_PER_SM 4     // register budget: 65536 / (4 * 128) = 128 per thread (5 blocks at 96 registers spill too much: measured slower)
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -27,7 +30,7 @@ __global__ void __launch_bounds__(32) aff_prologue_kernel(const KPlan P)
 }
 
 // Persistent rollout kernel: one warp per candidate, warps stride over the batch.
-__global__ void __launch_bounds__(32 * AFF_WARPS_PER_BLOCK) aff_rollout_kernel(const KPlan P)
+__global__ void __launch_bounds__(32 * AFF_WARPS_PER_BLOCK, AFF_BLOCKS_PER_SM) aff_rollout_kernel(const KPlan P)
 {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5;
@@ -188,9 +191,17 @@ int aff_batch_create(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, c
   aff_batch* b = new aff_batch;
   b->scene = s;
   std::string e;
+  const auto tb0 = std::chrono::steady_clock::now();
   int rc = affk::buildPlan(s->model, tasks, n_tasks, cons, n_cons, cands, n_cands, o, b->host, e);
   if (rc != AFF_OK) { delete b; return fail(rc, "aff_batch_create: " + e); }
+  const auto tb1 = std::chrono::steady_clock::now();
   rc = uploadBatch(b, 0);
+  if (getenv("AFF_TIMING")) {
+    cudaStreamSynchronize(0);
+    const auto tb2 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "aff_batch_create: plan %.1f ms, alloc + H2D %.1f ms (%.1f MB)\n", std::chrono::duration<double, std::milli>(tb1 - tb0).count(),
+                 std::chrono::duration<double, std::milli>(tb2 - tb1).count(), b->h2dBytes / 1e6);
+  }
   if (rc != AFF_OK) { b->release(); delete b; return rc; }
   // launch geometry: persistent blocks, as many as fit per SM
   cudaDeviceProp prop;
@@ -271,12 +282,21 @@ int aff_batch_fetch_q(aff_batch* b, size_t cand, double* out, size_t max_rows)
 int aff_predict_batch(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, const aff_constraint* cons, size_t n_cons,
                       const aff_candidate* cands, size_t n_cands, const aff_opts* opts, aff_result* out)
 {
+  static const bool timing = getenv("AFF_TIMING") != nullptr;   // AFF_TIMING=1: per-stage wall clock on stderr
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t0 = now();
   aff_batch* b = nullptr;
   int rc = aff_batch_create(s, tasks, n_tasks, cons, n_cons, cands, n_cands, opts, &b);
   if (rc != AFF_OK) return rc;
+  const auto t1 = now();
   rc = aff_batch_launch(b, nullptr);
   if (rc == AFF_OK) rc = aff_batch_results(b, nullptr, out, n_cands);
+  const auto t2 = now();
   aff_batch_destroy(b);
+  const auto t3 = now();
+  if (timing) std::fprintf(stderr, "aff_predict_batch: %zu candidates: create (plan + H2D) %.1f ms, kernels + D2H %.1f ms, destroy %.1f ms\n",
+                           n_cands, ms(t0, t1), ms(t1, t2), ms(t2, t3));
   return rc;
 }
 

@@ -26,6 +26,7 @@
 #define AFFK_MAX_PAIRS 512    // precompiled shape pairs per type list
 #define AFFK_MAX_VIA_UNK 6    // unknown polynomial coefficients per 1-D window
 #define AFFK_MAX_ROUNDS 40    // FK schedule rounds
+#define AFFK_VIA_LANES 16     // trajectory dimensions solved at the same time (8 would fit a fifth block per SM, but two passes cost more)
 #define AFFK_VIA_STRIDE 49    // doubles of solver scratch per trajectory lane (6*7 matrix + 6 solution, odd stride)
 
 // node reference: >= 0 dynamic node, -1 world, <= -2 static node (-2 - idx)

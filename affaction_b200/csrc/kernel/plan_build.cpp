@@ -544,19 +544,22 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   P.nStatPar = (int)H.statpar_ref.size();
   if (P.nDyn + P.nStatPar > 250) { err = "too many FK node slots"; return AFF_ERR_CAPACITY; }
   P.o_node = take(12 * std::max(P.nDyn + P.nStatPar, 1));
-  P.o_q = take(32); P.o_qdot = take(32); P.o_dH = take(32); P.o_dq = take(32); P.o_sn = take(32); P.o_cs = take(32);
-  P.o_dx = take(AFFK_MAX_XDIM);
-  P.o_st = take(3 * std::max(H.maxXdim, 1));
-  P.o_xdes = take(AFFK_MAX_XDIM); P.o_xcur = take(AFFK_MAX_XDIM);
-  P.o_geo = take(12 * AFFK_MAX_TASKS);
+  int maxTasks = 1;
+  for (const KCand& kc : H.cands) maxTasks = std::max(maxTasks, kc.n_tasks);
+  const int nJe = (S.nJ + 1) & ~1, xde = (std::max(H.maxXdim, 1) + 1) & ~1;
+  P.o_q = take(nJe); P.o_qdot = take(nJe); P.o_dH = take(nJe); P.o_dq = take(nJe); P.o_sn = take(nJe); P.o_cs = take(nJe);
+  P.o_dx = take(xde);
+  P.o_st = take(3 * xde);
+  P.o_xdes = take(xde); P.o_xcur = take(xde);
+  P.o_geo = take(12 * maxTasks);
   P.o_objrel = take(12 * AFFK_MAX_OBJ); P.o_objq6 = take(6 * AFFK_MAX_OBJ);
   P.o_chain = take((P.nDyn + P.nStatPar + 1) / 2 + 1);      // uint32 per slot
-  P.o_tdesc = take(4 * AFFK_MAX_TASKS);                      // 8 ints per task
-  P.o_rmask = take(AFFK_MAX_XDIM / 2);                       // uint32 per J row
+  P.o_tdesc = take(4 * maxTasks);                            // 8 ints per task
+  P.o_rmask = take(xde / 2);                                 // uint32 per J row
   // union region: trajectory solver scratch | J, L, rhs | collision scratch
   const int uBase = o;
   P.JS = (S.nJ | 1); P.LS = (H.maxXdim | 1);
-  const int uTraj = AFFK_VIA_STRIDE * std::max(H.maxXdim, 1);
+  const int uTraj = AFFK_VIA_STRIDE * std::min(std::max(H.maxXdim, 1), AFFK_VIA_LANES);
   const int mRows = std::max(H.maxXdim, 1);
   const int uIk = mRows * P.JS + mRows * P.LS + mRows;
   // live list (2*MAX_NEAR ints) + body trees (MAX_DBODY ints) + costly-pair scratch (32 ints + 32 doubles)

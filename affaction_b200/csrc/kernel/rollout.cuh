@@ -1088,19 +1088,24 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
     // the start of the next step unless the task switches on in this one, so only then is it computed.
     const double tnext = tnow + dt;
     const int ah = w_shfl(actHead, myTask < 0 ? 0 : myTask), ae = w_shfl(actEnd, myTask < 0 ? 0 : myTask);
-    if (lane < xdim) {
-      const bool active = (activeMask >> myTask) & 1u;
-      // does an activation point of my task fire in this step and switch it on?
-      bool switchesOn = false;
-      for (int k = ah; k < ae; ++k) { if (!(ldg(&acts[k].t) - tnext < AFFK_TRAJ_EPS)) break; switchesOn = ldg(&acts[k].on) != 0; }
-      if (active || switchesOn) {
-        double s3[3];
-        if (!active) { s3[0] = xcur[lane]; s3[1] = 0.0; s3[2] = 0.0; }
-        else { s3[0] = st[3 * lane]; s3[1] = st[3 * lane + 1]; s3[2] = st[3 * lane + 2]; }
-        k_via_step(s3, vias + viaHead, viaEnd - viaHead, tnow, dt, sm + P.o_scratch + AFFK_VIA_STRIDE * lane);
-        st[3 * lane] = s3[0]; st[3 * lane + 1] = s3[1]; st[3 * lane + 2] = s3[2];
-        xdes[lane] = s3[0];
+    // eight dimensions at a time: the solver scratch (AFFK_VIA_STRIDE doubles per lane) is the largest
+    // user of the shared union region
+    for (int batch = 0; batch < xdim; batch += AFFK_VIA_LANES) {
+      if (lane >= batch && lane < batch + AFFK_VIA_LANES && lane < xdim) {
+        const bool active = (activeMask >> myTask) & 1u;
+        // does an activation point of my task fire in this step and switch it on?
+        bool switchesOn = false;
+        for (int k = ah; k < ae; ++k) { if (!(ldg(&acts[k].t) - tnext < AFFK_TRAJ_EPS)) break; switchesOn = ldg(&acts[k].on) != 0; }
+        if (active || switchesOn) {
+          double s3[3];
+          if (!active) { s3[0] = xcur[lane]; s3[1] = 0.0; s3[2] = 0.0; }
+          else { s3[0] = st[3 * lane]; s3[1] = st[3 * lane + 1]; s3[2] = st[3 * lane + 2]; }
+          k_via_step(s3, vias + viaHead, viaEnd - viaHead, tnow, dt, sm + P.o_scratch + AFFK_VIA_STRIDE * (lane - batch));
+          st[3 * lane] = s3[0]; st[3 * lane + 1] = s3[1]; st[3 * lane + 2] = s3[2];
+          xdes[lane] = s3[0];
+        }
       }
+      w_sync();
     }
     tnow = tnext;
     // graph constraints

@@ -10,6 +10,7 @@
 #if defined(AFF_EMULATE)
 
 #define AFF_DEV static inline
+#define AFF_NOINLINE static
 int w_lane();
 void w_sync();
 double w_shfl(double v, int src);
@@ -26,6 +27,7 @@ static inline int w_ffs(unsigned v) { return __builtin_ffs((int)v); }
 #else
 
 #define AFF_DEV __device__ __forceinline__
+#define AFF_NOINLINE __device__ __noinline__
 AFF_DEV int w_lane() { return (int)(threadIdx.x & 31u); }
 AFF_DEV void w_sync() { __syncwarp(); }
 AFF_DEV double w_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }

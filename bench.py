@@ -119,7 +119,7 @@ def run_reference(args, rank, world):
         return
     threads = os.cpu_count() or 1
     scene = ab.HostScene()
-    sample = max(len(VARIANTS), 12 * threads)      # a few seconds per step
+    sample = max(len(VARIANTS), 60 * threads)      # ~5-10 s per step
     for _ in range(args.warmup):
         cpu_arm(ab, scene, len(VARIANTS) * threads, threads)
     total, secs = 0, 0.0
@@ -245,7 +245,7 @@ def run_cuda(args, rank, local_rank, world):
         cpu = None
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
-            v, secs, n = cpu_arm(ab, scene, max(len(VARIANTS), 16 * threads), threads)
+            v, secs, n = cpu_arm(ab, scene, max(len(VARIANTS), 120 * threads), threads)   # ~10-30 s of CPU work
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "%d rollouts of the same workload in %.1f s (CPU oracle, %d threads)" % (n, secs, threads)}
         line = {
