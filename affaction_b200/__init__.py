@@ -77,7 +77,7 @@ ABI_SYMBOLS = [
 ]
 HOST_SYMBOLS = [
     "aff_host_last_error", "aff_host_scene_load", "aff_host_scene_destroy", "aff_host_scene_desc", "aff_host_num_bodies",
-    "aff_host_num_ik_joints", "aff_host_body_id", "aff_host_body_name", "aff_host_ik_joint_name", "aff_host_scene_connect",
+    "aff_host_num_ik_joints", "aff_host_body_id", "aff_host_body_name", "aff_host_ik_joint_name", "aff_host_scene_connect", "aff_host_scene_set_ik_state",
     "aff_host_scene_device", "aff_host_batch_create", "aff_host_batch_destroy", "aff_host_batch_clear",
     "aff_host_batch_add_action", "aff_host_batch_add_perturbed", "aff_host_batch_num_tasks", "aff_host_batch_num_constraints",
     "aff_host_batch_num_candidates", "aff_host_batch_tasks", "aff_host_batch_constraints", "aff_host_batch_candidates",
@@ -109,7 +109,7 @@ def lib():
         "aff_host_last_error": (cstr, []), "aff_host_scene_load": (vp, [cstr]), "aff_host_scene_destroy": (None, [vp]),
         "aff_host_scene_desc": (vp, [vp]), "aff_host_num_bodies": (i32, [vp]), "aff_host_num_ik_joints": (i32, [vp]),
         "aff_host_body_id": (i32, [vp, cstr]), "aff_host_body_name": (cstr, [vp, i32]),
-        "aff_host_ik_joint_name": (cstr, [vp, i32]), "aff_host_scene_connect": (i32, [vp, cstr, cstr]),
+        "aff_host_ik_joint_name": (cstr, [vp, i32]), "aff_host_scene_connect": (i32, [vp, cstr, cstr]), "aff_host_scene_set_ik_state": (i32, [vp, vp, i32]),
         "aff_host_scene_device": (vp, [vp, i32]), "aff_host_batch_create": (vp, []), "aff_host_batch_destroy": (None, [vp]),
         "aff_host_batch_clear": (None, [vp]), "aff_host_batch_add_action": (i32, [vp, vp, cstr, dbl, dbl]),
         "aff_host_batch_add_perturbed": (i32, [vp, vp, cstr, sz, C.c_uint64, dbl]),
@@ -182,6 +182,13 @@ class HostScene:
         rc = lib().aff_host_scene_connect(self.h, child.encode(), parent.encode())
         if rc != AFF_OK:
             raise AffError("connect failed: %s" % lib().aff_host_last_error().decode())
+
+    def set_ik_state(self, q):
+        import numpy as np
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        rc = lib().aff_host_scene_set_ik_state(self.h, q.ctypes.data_as(C.c_void_p), len(q))
+        if rc != AFF_OK:
+            raise AffError("set_ik_state failed: %s" % lib().aff_host_last_error().decode())
 
     def device_scene(self, device=0):
         p = lib().aff_host_scene_device(self.h, device)

@@ -10,6 +10,7 @@
 
 #include "ActionBase.h"
 #include "ActionGet.h"
+#include "ActionPut.h"
 #include "TrajectoryPredictor.h"
 #include "affpredict_host.h"
 
@@ -80,6 +81,18 @@ int aff_host_scene_connect(aff_host_scene* s, const char* child, const char* par
     if (s->device) { aff_scene_destroy(s->device); s->device = nullptr; }
     return AFF_OK;
   } catch (const std::exception& e) { g_hostError = e.what(); return AFF_ERR_INVALID; }
+}
+
+// Start state for the next action of a sequence: the joint values a finished rollout ended with
+// (jacobi order, e.g. the last row of aff_batch_fetch_q).
+int aff_host_scene_set_ik_state(aff_host_scene* s, const double* q, int n)
+{
+  if (!s || !q || n != s->graph.nJ) { g_hostError = "set_ik_state: wrong number of joint values"; return AFF_ERR_INVALID; }
+  for (Joint& j : s->graph.joints) if (j.jacobiIndex >= 0) j.q_init = q[j.jacobiIndex];
+  s->graph.computeForwardKinematics();
+  s->graph.toDesc();
+  if (s->device) { aff_scene_destroy(s->device); s->device = nullptr; }
+  return AFF_OK;
 }
 
 aff_scene* aff_host_scene_device(aff_host_scene* s, int device)
@@ -236,9 +249,10 @@ std::unique_ptr<ActionBase> ActionFactory::create(const ActionScene& domain, con
   std::vector<std::string> params(words.begin() + 1, words.end());
   std::unique_ptr<ActionBase> a;
   if (name == "get") a.reset(new ActionGet(domain, graph, params));
+  else if (name == "put") a.reset(new ActionPut(domain, graph, params));
   else
     throw ActionException("ERROR: REASON: Action '" + name + "' is not part of the GPU predict path" +
-                          " SUGGESTION: Use one of: get", ActionException::ParamNotFound);
+                          " SUGGESTION: Use one of: get, put", ActionException::ParamNotFound);
   a->setName(name);
   a->setActionParams(params);
   return a;

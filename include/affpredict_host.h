@@ -34,6 +34,9 @@ const char* aff_host_body_name(const aff_host_scene* s, int id);
 const char* aff_host_ik_joint_name(const aff_host_scene* s, int jacobi_index);
 /* Re-parent a body keeping its world pose (state left by a finished get). */
 int aff_host_scene_connect(aff_host_scene* s, const char* child, const char* parent);
+/* Set the unconstrained joints (jacobi order, n = aff_host_num_ik_joints) to the state a
+ * finished rollout ended in: start state of the next action of a sequence. */
+int aff_host_scene_set_ik_state(aff_host_scene* s, const double* q, int n);
 /* Device-side scene handle (created on first use). NULL on CUDA failure. */
 aff_scene* aff_host_scene_device(aff_host_scene* s, int device);
 

@@ -34,3 +34,18 @@ def test_emulated_kernel_perturbed_candidate(scene):
     (emu,), _ = eb.predict(scene, b, opts, first=1, count=1)
     assert ref.code == -4                     # a colliding candidate with several pairs in contact
     assert emu.as_tuple() == ref.as_tuple()
+
+
+def test_emulated_kernel_put_candidate(built):
+    """`put` after `get`: object starts in the hand (six rigid-body dofs under a moving parent),
+    refFrame tasks, BoxInterval task regions, re-parenting onto a static surface."""
+    from chain_util import scene_after_get
+    scene = scene_after_get("italian_seasoning_bowl")
+    b = ab.HostBatch(scene)
+    assert b.add_action("put italian_seasoning_bowl table") == 6
+    opts = ab.default_opts(log_q=True)
+    ref, q_ref = ob.predict(scene, b, 2, opts, log_q=True)
+    (emu,), q_emu = eb.predict(scene, b, opts, first=2, count=1, log_q=True, n_steps=ref.n_steps - 1)
+    assert ref.code == -4
+    assert emu.as_tuple() == ref.as_tuple()
+    assert np.array_equal(q_emu[0], q_ref)

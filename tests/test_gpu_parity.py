@@ -118,3 +118,20 @@ def test_host_predict_messages(scene):
     assert res[0].success == 1 and msgs[0].startswith("SUCCESS")
     assert res[1].success == 0 and msgs[1].startswith("ERROR")
     assert "command: get fresh_tomatoes" in msgs[1]
+
+
+def test_put_after_get_matches_oracle(built):
+    """BASELINE.json configs[1] stand-in: `put` with its location candidates,
+    chained on the final state of the ranked-first `get` candidate."""
+    from chain_util import scene_after_get
+    scene = scene_after_get("italian_seasoning_bowl")
+    for cmd, n_expected in (("put italian_seasoning_bowl table", 6), ("put italian_seasoning_bowl shelf", 1)):
+        batch = ab.HostBatch(scene)
+        assert batch.add_action(cmd) == n_expected
+        opts = ab.default_opts(log_q=True)
+        dev = ab.DeviceBatch(scene, batch, opts)
+        dev.launch()
+        worst = _compare(scene, batch, opts, dev, range(n_expected))
+        assert worst == 0.0
+    res, msgs = batch.predict(sort=True)
+    assert len(res) == 1

@@ -116,3 +116,29 @@ def test_rank_is_lesser_with_idx_tiebreak(built):
         r.idx, r.success, r.jl_cost, r.coll_cost = i, s, jl, co
         rs.append(r)
     assert ab.rank(rs) == [3, 1, 2, 4, 0]
+
+
+def test_put_candidates_after_get(built):
+    """SURVEY 8(d) config 2 stand-in: `put <object> table` after a successful get gives the six
+    Supportables with extents (g_pizza.xml:56-64), each with a BoxInterval task region."""
+    from chain_util import scene_after_get
+    scene = scene_after_get("italian_seasoning_bowl")
+    b = ab.HostBatch(scene)
+    assert b.add_action("put italian_seasoning_bowl table") == 6
+    tasks, cands = _tasks(b), _cands(b)
+    for c in cands:
+        tl = tasks[c.first_task:c.first_task + c.n_tasks]
+        assert c.n_tasks == 10                                   # ActionPut::createTasksXML
+        assert [t.has_region for t in tl].count(1) == 2          # X and Y of the object on the surface
+        assert tl[1].ref_frame >= 0 and tl[1].ref_frame != tl[1].ref_body   # refFrame = surface, refBdy = object
+        reg = [t for t in tl if t.has_region][0]
+        assert (reg.region_min, reg.region_max, reg.region_dx_scaling) == (-0.05, 0.05, 0.0)
+    cons = _cons(b)[cands[0].first_constraint:cands[0].first_constraint + cands[0].n_constraints]
+    t_put = 0.05 + 0.66 * 10.0
+    assert any(c.kind == 2 and abs(c.t - t_put) < 1e-12 for c in cons)      # ConnectBodyConstraint(t_put, object, surface)
+    b2 = ab.HostBatch(scene)
+    assert b2.add_action("put italian_seasoning_bowl shelf") == 1           # the free extent-less shelf position
+    with pytest.raises(ab.AffError, match="not held in the hand"):
+        ab.HostBatch(scene).add_action("put tomato_sauce_bottle table")
+    with pytest.raises(ab.AffError, match="already full|holding|cannot be grasped|SUCCESS"):
+        ab.HostBatch(scene).add_action("get italian_seasoning_bowl")
