@@ -19,6 +19,9 @@ PIZZA_SCENE = os.path.join(DATA_DIR, "pizza.affscene")
 AFF_OK = 0
 AFF_MAX_TASK_JOINTS = 8
 
+# enums of include/affpredict.h
+TASK_XYZ, TASK_X, TASK_Y, TASK_Z, TASK_POLAR, TASK_INCLINATION, TASK_JOINTS = range(7)
+CON_VIA, CON_ACTIVATION, CON_CONNECT, CON_COLLISION = range(4)
 CODE_NAMES = {0: "ok", -1: "singular", -2: "speed", -3: "joint_limit", -4: "collision", -5: "tracking", -6: "initial_state"}
 
 

@@ -33,16 +33,16 @@ void ActivationSet::add(double t, double x, double xd, double xdd, int flag, con
   entries.push_back(e);
 }
 
-void ActivationSet::addPositionConstraint(double t, double x, double y, double z, const std::string& task)
+void ActivationSet::addPositionConstraint(double t, double x, double y, double z, const std::string& task, int flag)
 {
   const double v[3] = {x, y, z};
-  for (int i = 0; i < 3; ++i) add(t, v[i], 0.0, 0.0, 7, task + " " + std::to_string(i));
+  for (int i = 0; i < 3; ++i) add(t, v[i], 0.0, 0.0, flag, task + " " + std::to_string(i));
 }
 
-void ActivationSet::addPolarConstraint(double t, double phi, double theta, const std::string& task)
+void ActivationSet::addPolarConstraint(double t, double phi, double theta, const std::string& task, int flag)
 {
-  add(t, phi, 0.0, 0.0, 7, task + " 0");
-  add(t, theta, 0.0, 0.0, 7, task + " 1");
+  add(t, phi, 0.0, 0.0, flag, task + " 0");
+  add(t, theta, 0.0, 0.0, flag, task + " 1");
 }
 
 void ActivationSet::addVectorConstraint(double t, const std::vector<double>& x, const std::string& task)

@@ -58,8 +58,8 @@ public:
   void addActivation(double t, bool switchesOn, double horizon, const std::string& taskName);
   // add(t, x, xd, xdd, flag, "taskName dim")
   void add(double t, double x, double xd, double xdd, int flag, const std::string& trajNameND);
-  void addPositionConstraint(double t, double x, double y, double z, const std::string& task);   // tropic::PositionConstraint
-  void addPolarConstraint(double t, double phi, double theta, const std::string& task);          // tropic::PolarConstraint
+  void addPositionConstraint(double t, double x, double y, double z, const std::string& task, int flag = 7);   // tropic::PositionConstraint
+  void addPolarConstraint(double t, double phi, double theta, const std::string& task, int flag = 7);          // tropic::PolarConstraint
   void addVectorConstraint(double t, const std::vector<double>& x, const std::string& task);     // tropic::VectorConstraint
   void addConnectBodyConstraint(double t, const std::string& child, const std::string& parent);  // tropic::ConnectBodyConstraint
   void addCollisionModelConstraint(double t, const std::string& body, bool switchOn);            // tropic::CollisionModelConstraint

@@ -24,10 +24,10 @@
 #define AFFK_MAX_DBODY 16     // shape bodies on dynamic nodes
 #define AFFK_MAX_NEAR 64      // body pairs found by the AABB test in one step
 #define AFFK_MAX_PAIRS 512    // precompiled shape pairs per type list
-#define AFFK_MAX_VIA_UNK 6    // unknown polynomial coefficients per 1-D window
+#define AFFK_MAX_VIA_UNK 12   // capacity: unknown polynomial coefficients per 1-D window (KPlan::via_unk is the batch's bound)
 #define AFFK_MAX_ROUNDS 40    // FK schedule rounds
+#define AFFK_HORIZON 1.0       // trajectory horizon, src/ActionBase.cpp:137
 #define AFFK_VIA_LANES 16     // trajectory dimensions solved at the same time (8 would fit a fifth block per SM, but two passes cost more)
-#define AFFK_VIA_STRIDE 49    // doubles of solver scratch per trajectory lane (6*7 matrix + 6 solution, odd stride)
 
 // node reference: >= 0 dynamic node, -1 world, <= -2 static node (-2 - idx)
 #define AFFK_WORLD (-1)
@@ -163,7 +163,8 @@ struct KPlan
   // shared-memory layout of one warp, in doubles from the warp base
   int32_t o_node, o_q, o_qdot, o_dH, o_dq, o_sn, o_cs, o_J, o_L, o_rhs, o_dx, o_st, o_xdes, o_xcur, o_geo,
           o_objrel, o_objq6, o_shp, o_baabb, o_taabb, o_scratch, o_live, o_chain, o_tdesc, o_rmask, warp_doubles;
-  int32_t JS, LS;                  // row strides of J and L (odd: conflict-free column access)
+  int32_t JS, LS;
+  int32_t via_unk, via_stride;     // largest trajectory window of the batch (constrained values); solver scratch per lane (odd)                  // row strides of J and L (odd: conflict-free column access)
 
   aff_opts opts;
   aff_result* results;             // [nCands]

@@ -428,6 +428,7 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   H.cands.resize(nCands);
   H.vias.reserve(nConsIn); H.acts.reserve(nConsIn);
   std::vector<std::pair<int, int>> order;   // (sort key, constraint index)
+  int maxViaUnk = 0;
   for (size_t i = 0; i < nCands; ++i) {
     const aff_candidate& c = candsIn[i];
     KCand& kc = H.cands[i];
@@ -454,7 +455,7 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     H.maxSteps = std::max(H.maxSteps, kc.n_steps);
     // vias by (dimension, time), stable in insertion order
     kc.first_via = (int)H.vias.size();
-    int unknowns[AFFK_MAX_XDIM];
+    int unknowns[AFFK_MAX_XDIM];   // per dimension, whole trajectory
     for (int d = 0; d < xdim; ++d) unknowns[d] = 0;
     order.clear();
     for (int k = 0; k < c.n_constraints; ++k) {
@@ -481,7 +482,21 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
         }
       }
     }
-    for (int d = 0; d < xdim; ++d) if (unknowns[d] > AFFK_MAX_VIA_UNK) { err = "a trajectory has more than 6 constrained values"; return AFF_ERR_CAPACITY; }
+    // Largest window any step can see: with constraint i the next one to come (tnow <= t_i), the
+    // window ends at the first full constraint at least one horizon later (k_via_step).
+    for (int d = 0; d < xdim; ++d) {
+      const KVia* v = H.vias.data() + kc.first_via + kc.via_off[d];
+      const int n = kc.via_off[d + 1] - kc.via_off[d];
+      for (int i = 0; i < n; ++i) {
+        int G = -1, lastFull = -1;
+        for (int j = i; j < n; ++j) if (v[j].flag == 7) { lastFull = j; if (v[j].t - v[i].t >= AFFK_HORIZON) { G = j; break; } }
+        if (G < 0) G = lastFull >= 0 ? lastFull : n - 1;
+        int K = 0;
+        for (int j = i; j <= G; ++j) K += popcount3(v[j].flag);
+        maxViaUnk = std::max(maxViaUnk, K);
+      }
+    }
+    if (maxViaUnk > AFFK_MAX_VIA_UNK) { err = "a trajectory window has more than 12 constrained values"; return AFF_ERR_CAPACITY; }
     // activations by (task, time)
     kc.first_act = (int)H.acts.size();
     order.clear();
@@ -559,7 +574,9 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   // union region: trajectory solver scratch | J, L, rhs | collision scratch
   const int uBase = o;
   P.JS = (S.nJ | 1); P.LS = (H.maxXdim | 1);
-  const int uTraj = AFFK_VIA_STRIDE * std::min(std::max(H.maxXdim, 1), AFFK_VIA_LANES);
+  P.via_unk = std::max(maxViaUnk, 1);
+  P.via_stride = (P.via_unk * (P.via_unk + 1) + P.via_unk) | 1;   // matrix + solution, odd stride
+  const int uTraj = P.via_stride * std::min(std::max(H.maxXdim, 1), AFFK_VIA_LANES);
   const int mRows = std::max(H.maxXdim, 1);
   const int uIk = mRows * P.JS + mRows * P.LS + mRows;
   // live list (2*MAX_NEAR ints) + body trees (MAX_DBODY ints) + costly-pair scratch (32 ints + 32 doubles)

@@ -27,7 +27,6 @@
 
 #define AFFK_TRACK_MAX 0.05      // MAX_TRACKING_ERROR, src/TrajectoryPredictor.cpp:50
 #define AFFK_TRAJ_EPS 1.0e-8
-#define AFFK_HORIZON 1.0         // src/ActionBase.cpp:137
 #define AFFK_NO_LIMIT 1.0e300
 #define AFFK_GOLDEN_ITERS 48
 
@@ -210,7 +209,7 @@ AFF_DEV void k_fk(const KCtx& c, bool init)
 // ------------------------------------------------------------ via-point step
 // One receding-horizon step of a 1-D via-point trajectory (the oracle's
 // oracle_via_step): window selection, reduced polynomial system, evaluation.
-AFF_DEV void k_via_step(double* st, const KVia* vias, int n, double tnow, double dt, double* A)
+AFF_DEV void k_via_step(double* st, const KVia* vias, int n, double tnow, double dt, double* A, int maxUnk)
 {
   if (n <= 0) { st[1] = 0.0; st[2] = 0.0; return; }
   int G = -1, lastFull = -1;
@@ -222,7 +221,7 @@ AFF_DEV void k_via_step(double* st, const KVia* vias, int n, double tnow, double
   for (int i = 0; i <= G; ++i) {
     const int flag = ldg(&vias[i].flag);
     const int add = (flag & 1) + ((flag >> 1) & 1) + ((flag >> 2) & 1);
-    if (K + add > AFFK_MAX_VIA_UNK) break;
+    if (K + add > maxUnk) break;
     K += add; nwin = i + 1;
   }
   if (K == 0) { st[1] = 0.0; st[2] = 0.0; return; }
@@ -266,7 +265,7 @@ AFF_DEV void k_via_step(double* st, const KVia* vias, int n, double tnow, double
       for (int k = cI + 1; k < S; ++k) A[r * S + k] = fma(-f, A[cI * S + k], A[r * S + k]);
     }
   }
-  double* sol = A + AFFK_MAX_VIA_UNK * (AFFK_MAX_VIA_UNK + 1);   // AFFK_MAX_VIA_UNK doubles after the matrix
+  double* sol = A + maxUnk * (maxUnk + 1);   // maxUnk doubles after the matrix
   for (int r = K - 1; r >= 0; --r) {
     double sacc = A[r * S + K];
     for (int k = r + 1; k < K; ++k) sacc = fma(-A[r * S + k], sol[k], sacc);
@@ -1088,7 +1087,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
     // the start of the next step unless the task switches on in this one, so only then is it computed.
     const double tnext = tnow + dt;
     const int ah = w_shfl(actHead, myTask < 0 ? 0 : myTask), ae = w_shfl(actEnd, myTask < 0 ? 0 : myTask);
-    // eight dimensions at a time: the solver scratch (AFFK_VIA_STRIDE doubles per lane) is the largest
+    // eight dimensions at a time: the solver scratch (via_stride doubles per lane) is the largest
     // user of the shared union region
     for (int batch = 0; batch < xdim; batch += AFFK_VIA_LANES) {
       if (lane >= batch && lane < batch + AFFK_VIA_LANES && lane < xdim) {
@@ -1100,7 +1099,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
           double s3[3];
           if (!active) { s3[0] = xcur[lane]; s3[1] = 0.0; s3[2] = 0.0; }
           else { s3[0] = st[3 * lane]; s3[1] = st[3 * lane + 1]; s3[2] = st[3 * lane + 2]; }
-          k_via_step(s3, vias + viaHead, viaEnd - viaHead, tnow, dt, sm + P.o_scratch + AFFK_VIA_STRIDE * (lane - batch));
+          k_via_step(s3, vias + viaHead, viaEnd - viaHead, tnow, dt, sm + P.o_scratch + P.via_stride * (lane - batch), P.via_unk);
           st[3 * lane] = s3[0]; st[3 * lane + 1] = s3[1]; st[3 * lane + 2] = s3[2];
           xdes[lane] = s3[0];
         }

@@ -135,3 +135,25 @@ def test_put_after_get_matches_oracle(built):
         assert worst == 0.0
     res, msgs = batch.predict(sort=True)
     assert len(res) == 1
+
+
+def test_pour_after_get_matches_oracle(built):
+    """BASELINE.json configs[3] stand-in: the shipped sequence
+    `get tomato_sauce_bottle; pour tomato_sauce_bottle pizza_dough; put tomato_sauce_bottle shelf`
+    (g_scenario_pizza.xml:39) chained action by action.  The pour is a 20 s rollout (2555 steps) with
+    trajectory windows of eight constrained values; the bottle rides in the hand as a plain rigid body."""
+    from chain_util import scene_after_get
+    scene = scene_after_get("tomato_sauce_bottle", require_success=False)
+    for cmd in ("pour tomato_sauce_bottle pizza_dough", "put tomato_sauce_bottle shelf"):
+        batch = ab.HostBatch(scene)
+        n = batch.add_action(cmd)
+        assert n >= 1
+        opts = ab.default_opts(log_q=True)
+        dev = ab.DeviceBatch(scene, batch, opts)
+        dev.launch()
+        if cmd.startswith("pour"):
+            assert dev.num_steps(0) == 2555
+        assert _compare(scene, batch, opts, dev, range(n)) == 0.0
+        if cmd.startswith("pour"):
+            # next action starts where this one ended
+            scene.set_ik_state(dev.fetch_q(0)[-1])

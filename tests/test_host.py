@@ -1,6 +1,7 @@
 """CPU tier: host shim = scene loading, candidate generation, descriptors."""
 import ctypes as C
 
+import numpy as np
 import pytest
 
 import affaction_b200 as ab
@@ -142,3 +143,41 @@ def test_put_candidates_after_get(built):
         ab.HostBatch(scene).add_action("put tomato_sauce_bottle table")
     with pytest.raises(ab.AffError, match="already full|holding|cannot be grasped|SUCCESS"):
         ab.HostBatch(scene).add_action("get italian_seasoning_bowl")
+
+
+def test_pour_after_get(built):
+    """SURVEY 8(d) config 4 stand-in: `pour tomato_sauce_bottle pizza_dough` from the state the get
+    leaves behind.  One candidate, 20 s, five tasks (src/ActionPour.cpp:247-279), the timing
+    ladder t_prep / t_up / t_down / t_end of :303-341."""
+    from chain_util import scene_after_get
+    scene = scene_after_get("tomato_sauce_bottle", require_success=False)
+    b = ab.HostBatch(scene)
+    assert b.add_action("pour tomato_sauce_bottle pizza_dough") == 1
+    tasks, cands = _tasks(b), _cands(b)
+    c = cands[0]
+    tl = tasks[c.first_task:c.first_task + c.n_tasks]
+    assert [t.kind for t in tl] == [ab.TASK_XYZ, ab.TASK_POLAR, ab.TASK_POLAR, ab.TASK_X, ab.TASK_Z]
+    tip, glas, base = scene.body_id("tomato_sauce_bottle_tip"), scene.body_id("pizza_dough_pour"), scene.body_id("base_footprint")
+    assert (tl[0].effector, tl[0].ref_body, tl[0].ref_frame) == (tip, glas, base)
+    assert b.task_name(0, 0) == "tomato_sauce_bottle_tip-pizza_dough_pour-base_footprint-XYZ"
+    assert b.task_name(0, 4) == ""            # the reference never names taskGlasPosZ
+    cons = _cons(b)[c.first_constraint:c.first_constraint + c.n_constraints]
+    t0, dur = 0.05, 20.0
+    t_prep, t_up, t_down, t_end = t0 + 0.15 * dur, t0 + 0.45 * dur, t0 + 0.9 * dur, t0 + dur
+    via = [(k.task, k.dim, round(k.t, 9), k.flag) for k in cons if k.kind == ab.CON_VIA]
+    assert (0, 1, round(t_prep, 9), 7) in via and (0, 2, round(t_prep, 9), 7) in via
+    assert (0, 0, round(t_up, 9), 7) in via and (0, 2, round(t_down, 9), 1) in via and (0, 1, round(t_end, 9), 7) in via
+    assert (1, 0, round(t_prep, 9), 1) in via and (1, 0, round(t_up, 9), 7) in via
+    phi = {round(k.t, 9): k.x for k in cons if k.kind == ab.CON_VIA and k.task == 1 and k.dim == 0}
+    assert phi[round(t_up, 9)] == pytest.approx(np.deg2rad(150.0)) and phi[round(t_end, 9)] == pytest.approx(np.deg2rad(10.0))
+    acts = [(k.task, round(k.t, 9), k.flag) for k in cons if k.kind == ab.CON_ACTIVATION]
+    assert sorted(a[0] for a in acts) == [0, 0, 1, 1]     # the glass stands on the table: its tasks stay off
+    assert not any(k.kind in (ab.CON_CONNECT, ab.CON_COLLISION) for k in cons)
+    # the window before t_up holds 3 + 1 + 1 + 3 constrained values: more than a quintic
+    import oracle_binding as ob
+    assert ob.oracle_lib().oracle_num_steps(b.constraints_ptr, b.candidate_ptr(0), C.byref(ab.default_opts())) == 2555
+    for cmd, msg in (("pour tomato_sauce_bottle", "less than two parameters"), ("pour bbq_sauce_bottle pizza_dough", "not held in a hand"),
+                     ("pour tomato_sauce_bottle table", "not a container that can be poured into"),
+                     ("pour tomato_sauce_bottle pizza_dough 2.0", "overflow"), ("pour tomato_sauce_bottle pizza_dough -1", "negative value")):
+        with pytest.raises(ab.AffError, match=msg):
+            ab.HostBatch(scene).add_action(cmd)
