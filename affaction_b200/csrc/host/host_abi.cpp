@@ -9,6 +9,7 @@
 #include <string>
 
 #include "ActionBase.h"
+#include "ActionComposite.h"
 #include "ActionGet.h"
 #include "ActionPour.h"
 #include "ActionPut.h"
@@ -251,10 +252,11 @@ std::unique_ptr<ActionBase> ActionFactory::create(const ActionScene& domain, con
   std::unique_ptr<ActionBase> a;
   if (name == "get") a.reset(new ActionGet(domain, graph, params));
   else if (name == "put") a.reset(new ActionPut(domain, graph, params));
+  else if (name == "double_get") a.reset(new ActionDoubleGet(domain, graph, params));
   else if (name == "pour") a.reset(new ActionPour(domain, graph, params));
   else
     throw ActionException("ERROR: REASON: Action '" + name + "' is not part of the GPU predict path" +
-                          " SUGGESTION: Use one of: get, put, pour", ActionException::ParamNotFound);
+                          " SUGGESTION: Use one of: get, put, pour, double_get", ActionException::ParamNotFound);
   a->setName(name);
   a->setActionParams(params);
   return a;

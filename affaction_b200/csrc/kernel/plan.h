@@ -16,12 +16,12 @@
 
 #define AFFK_MAX_NJ 32        // IK joints: one lane each
 #define AFFK_MAX_DYN 40       // dynamic nodes
-#define AFFK_MAX_XDIM 24      // stacked task dimensions of one candidate
-#define AFFK_MAX_TASKS 12     // tasks of one candidate
+#define AFFK_MAX_XDIM 32      // stacked task dimensions of one candidate
+#define AFFK_MAX_TASKS 16     // tasks of one candidate
 #define AFFK_MAX_M 16         // task rows active at the same time
 #define AFFK_MAX_OBJ 2        // re-parentable objects per candidate
-#define AFFK_MAX_DSHAPE 20    // shapes on dynamic nodes
-#define AFFK_MAX_DBODY 16     // shape bodies on dynamic nodes
+#define AFFK_MAX_DSHAPE 40    // shapes on dynamic nodes
+#define AFFK_MAX_DBODY 32     // shape bodies on dynamic nodes
 #define AFFK_MAX_NEAR 64      // body pairs found by the AABB test in one step
 #define AFFK_MAX_PAIRS 512    // precompiled shape pairs per type list
 #define AFFK_MAX_VIA_UNK 12   // capacity: unknown polynomial coefficients per 1-D window (KPlan::via_unk is the batch's bound)

@@ -157,3 +157,16 @@ def test_pour_after_get_matches_oracle(built):
         if cmd.startswith("pour"):
             # next action starts where this one ended
             scene.set_ik_state(dev.fetch_q(0)[-1])
+
+
+@pytest.mark.parametrize("objects", ["italian_seasoning_bowl garlic_bowl", "italian_seasoning_bowl tomato_sauce_bottle",
+                                     "mushrooms_bowl italian_seasoning_bowl"])
+def test_double_get_matches_oracle(scene, objects):
+    """BASELINE.json configs[2] stand-in: both arms move in one rollout,
+    14 tasks / up to 26 task dimensions, two objects re-parented."""
+    batch = ab.HostBatch(scene)
+    assert batch.add_action("double_get " + objects) == 1
+    opts = ab.default_opts(log_q=True)
+    dev = ab.DeviceBatch(scene, batch, opts)
+    dev.launch()
+    assert _compare(scene, batch, opts, dev, [0]) == 0.0

@@ -181,3 +181,27 @@ def test_pour_after_get(built):
                      ("pour tomato_sauce_bottle pizza_dough 2.0", "overflow"), ("pour tomato_sauce_bottle pizza_dough -1", "negative value")):
         with pytest.raises(ab.AffError, match=msg):
             ab.HostBatch(scene).add_action(cmd)
+
+
+def test_double_get_is_the_union_of_two_gets(scene):
+    """ActionDoubleGet = two ActionGets on the best hand pairing, tasks
+    unioned, trajectories merged, one candidate (src/ActionComposite.cpp:86-122,171-255)."""
+    b = ab.HostBatch(scene)
+    assert b.add_action("double_get italian_seasoning_bowl tomato_sauce_bottle") == 1
+    names = [b.task_name(0, k) for k in range(b.n_tasks)]
+    assert len(names) == 14 and len(set(names)) == 14
+    # the bowl stands right of the robot, the bottle left: closest pairing
+    assert names[0] == "italian_seasoning_bowl-hand_right_pincergrasp-XYZ"
+    assert names[7] == "tomato_sauce_bottle-hand_left_powergrasp-XYZ"
+    single = ab.HostBatch(scene)
+    single.add_action("get italian_seasoning_bowl hand_right")
+    single.add_action("get tomato_sauce_bottle hand_left")
+    n_single = single.n_constraints
+    assert b.n_constraints == n_single                      # merged, nothing dropped
+    kinds = sorted(k.kind for k in _cons(b))
+    assert kinds.count(ab.CON_CONNECT) == 2                 # both objects end up in a hand
+    for cmd, msg in (("double_get italian_seasoning_bowl", "1 arguments, but 2 are expected"),
+                     ("double_get fresh_tomatoes italian_seasoning_bowl", "Object fresh_tomatoes is unknown"),
+                     ("double_get italian_seasoning_bowl nothing", "Object nothing is unknown")):
+        with pytest.raises(ab.AffError, match=msg):
+            ab.HostBatch(scene).add_action(cmd)
