@@ -84,7 +84,7 @@ HOST_SYMBOLS = [
     "aff_host_scene_device", "aff_host_batch_create", "aff_host_batch_destroy", "aff_host_batch_clear",
     "aff_host_batch_add_action", "aff_host_batch_add_perturbed", "aff_host_batch_num_tasks", "aff_host_batch_num_constraints",
     "aff_host_batch_num_candidates", "aff_host_batch_tasks", "aff_host_batch_constraints", "aff_host_batch_candidates",
-    "aff_host_batch_task_name", "aff_host_predict", "aff_host_format_message",
+    "aff_host_batch_task_name", "aff_host_predict", "aff_host_format_message", "aff_host_check_trajectory",
 ]
 
 
@@ -122,6 +122,7 @@ def lib():
         "aff_host_batch_task_name": (cstr, [vp, sz, i32]),
         "aff_host_predict": (i32, [vp, vp, dbl, i32, i32, vp, vp, sz]),
         "aff_host_format_message": (i32, [vp, vp, vp, dbl, vp, sz]),
+        "aff_host_check_trajectory": (i32, [vp, vp, sz, i32, i32, i32, dbl, i32, vp, vp, vp, vp, vp, vp, sz, vp, sz]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -277,6 +278,24 @@ class HostBatch:
             raise AffError("aff_host_predict: %s / %s" % (lib().aff_host_last_error().decode(), lib().aff_last_error().decode()))
         out = [msgs.raw[i * msg_len:(i + 1) * msg_len].split(b"\0", 1)[0].decode() for i in range(n)]
         return list(res), out
+
+    def check_trajectory(self, cand=0, simulate_only=False, estop=False, check_enabled=True, dt=0.01, device=0, max_rows=4096):
+        """TrajectoryComponent::onCheckAndSetTrajectory / onSimulateTrajectory on one candidate.
+        Returns a dict with the events the component publishes and the prediction array."""
+        import numpy as np
+        nJ = self.scene.nJ
+        q = np.zeros((max_rows, nJ))
+        ar, ok, st = C.c_int(0), C.c_int(0), C.c_int(0)
+        quality = C.c_double(0.0)
+        raw = Result()
+        msg = C.create_string_buffer(1024)
+        rows = lib().aff_host_check_trajectory(self.scene.h, self.h, cand, 1 if simulate_only else 0, 1 if estop else 0,
+                                               1 if check_enabled else 0, dt, device, C.byref(ar), C.byref(ok), C.byref(quality),
+                                               C.byref(st), C.byref(raw), msg, 1024, q.ctypes.data, max_rows)
+        if rows < 0:
+            raise AffError("aff_host_check_trajectory: %s / %s" % (lib().aff_host_last_error().decode(), lib().aff_last_error().decode()))
+        return {"action_result": bool(ar.value), "ok": bool(ok.value), "quality": quality.value, "set_trajectory": bool(st.value),
+                "message": msg.value.decode(), "raw": raw, "q": q[:min(rows, max_rows)].copy()}
 
     def format_message(self, result, dt=0.01):
         buf = C.create_string_buffer(1024)

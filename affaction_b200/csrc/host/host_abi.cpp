@@ -13,6 +13,7 @@
 #include "ActionGet.h"
 #include "ActionPour.h"
 #include "ActionPut.h"
+#include "TrajectoryComponent.h"
 #include "TrajectoryPredictor.h"
 #include "affpredict_host.h"
 
@@ -234,6 +235,45 @@ int aff_host_format_message(aff_host_scene* s, aff_host_batch* b, const aff_resu
   std::strncpy(out, p.message.c_str(), n - 1);
   out[n - 1] = '\0';
   return (int)p.message.size();
+}
+
+// TrajectoryComponent on one candidate of a batch: its task list plays the runtime controller's,
+// its constraints the trajectory to check.
+int aff_host_check_trajectory(aff_host_scene* s, aff_host_batch* b, size_t cand, int mode, int estop, int checkEnabled,
+                              double dt, int device, int* actionResult, int* ok, double* quality, int* setTrajectory,
+                              aff_result* rawOut, char* message, size_t msgLen, double* qOut, size_t maxRows)
+{
+  try {
+    if (cand >= b->batch.candidates.size()) { g_hostError = "check_trajectory: candidate out of range"; return AFF_ERR_INVALID; }
+    aff_scene* dev = aff_host_scene_device(s, device);
+    if (!dev) return AFF_ERR_CUDA;
+    // rebuild TaskSpec-free: the component works on descriptors already resolved against the graph
+    const aff_candidate& c = b->batch.candidates[cand];
+    CandidateBatch one;
+    one.tasks.assign(b->batch.tasks.begin() + c.first_task, b->batch.tasks.begin() + c.first_task + c.n_tasks);
+    one.constraints.assign(b->batch.constraints.begin() + c.first_constraint, b->batch.constraints.begin() + c.first_constraint + c.n_constraints);
+    aff_candidate c1 = c;
+    c1.first_task = 0; c1.first_constraint = 0;
+    one.candidates.push_back(c1);
+    one.taskNames.push_back(b->batch.taskNames[cand]);
+    TrajectoryComponent comp(dev, s->graph, dt);
+    if (estop) comp.onEmergencyStop();
+    comp.onEnableTrajectoryCheck(checkEnabled != 0);
+    const TrajectoryComponent::CheckOutcome out = mode == 1 ? comp.onSimulateTrajectory(one) : comp.onCheckAndSetTrajectory(one);
+    if (actionResult) *actionResult = out.publishActionResult ? 1 : 0;
+    if (ok) *ok = out.actionOk ? 1 : 0;
+    if (quality) *quality = out.quality;
+    if (setTrajectory) *setTrajectory = out.publishSetTrajectory ? 1 : 0;
+    if (rawOut && out.checked) *rawOut = out.result.raw;
+    if (message && msgLen > 0) { std::strncpy(message, out.message.c_str(), msgLen - 1); message[msgLen - 1] = '\0'; }
+    int rows = 0, cols = 0;
+    const std::vector<double>& q = comp.getPredictionArray(&rows, &cols);
+    if (qOut) std::memcpy(qOut, q.data(), sizeof(double) * std::min((size_t)rows, maxRows) * cols);
+    return rows;
+  } catch (const std::exception& e) {
+    g_hostError = e.what();
+    return AFF_ERR_CUDA;
+  }
 }
 
 }   // extern "C"

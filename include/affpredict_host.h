@@ -63,6 +63,16 @@ int aff_host_predict(aff_host_scene* s, aff_host_batch* b, double dt, int sort_r
                      aff_result* raw_out, char* messages, size_t msg_stride);
 int aff_host_format_message(aff_host_scene* s, aff_host_batch* b, const aff_result* r, double dt, char* out, size_t n);
 
+/* Second call site: TrajectoryComponent::checkerThread (reference src/TrajectoryComponent.cpp:346-399)
+ * on candidate `cand` of the batch = "the runtime controller's tasks + one trajectory".
+ * mode 0: onCheckAndSetTrajectory, 1: onSimulateTrajectory; estop / check_enabled are the component's
+ * two switches.  Outputs: *action_result = 1 if "ActionResult" is published (then *ok, *quality and
+ * message hold its arguments), *set_trajectory = 1 if "SetTrajectory" is published.  q_out (may be
+ * NULL) receives up to max_rows rows of the prediction array; returns rows available or <0. */
+int aff_host_check_trajectory(aff_host_scene* s, aff_host_batch* b, size_t cand, int mode, int estop, int check_enabled,
+                              double dt, int device, int* action_result, int* ok, double* quality, int* set_trajectory,
+                              aff_result* raw_out, char* message, size_t msg_len, double* q_out, size_t max_rows);
+
 #ifdef __cplusplus
 }
 #endif

@@ -170,3 +170,35 @@ def test_double_get_matches_oracle(scene, objects):
     dev = ab.DeviceBatch(scene, batch, opts)
     dev.launch()
     assert _compare(scene, batch, opts, dev, [0]) == 0.0
+
+
+def test_trajectory_component_recheck(scene):
+    """SURVEY 8(f) rank 2: the pre-execution re-check (TrajectoryComponent::checkerThread,
+    src/TrajectoryComponent.cpp:346-399) = the same rollout at batch 1, with the events the component
+    publishes and the prediction array for the ghost animation."""
+    batch = ab.HostBatch(scene)
+    assert batch.add_action("get fresh_tomatoes") == 2
+    opts = ab.default_opts(log_q=True)
+    verdicts = []
+    for cand in range(2):
+        ref, q_ref = ob.predict(scene, batch, cand, opts, log_q=True)
+        verdicts.append(ref.success)
+        out = batch.check_trajectory(cand)                    # onCheckAndSetTrajectory
+        assert out["raw"].as_tuple() == ref.as_tuple()
+        assert np.array_equal(out["q"], q_ref)
+        if ref.success:
+            assert out["set_trajectory"] and not out["action_result"]
+        else:
+            assert out["action_result"] and not out["ok"] and not out["set_trajectory"]
+            assert out["message"] == batch.format_message(ref)
+        sim = batch.check_trajectory(cand, simulate_only=True)   # onSimulateTrajectory
+        assert not sim["set_trajectory"] and sim["action_result"] and sim["ok"] == bool(ref.success)
+        if ref.success:
+            assert sim["message"] == "SUCCESS DEVELOPER: Simulated trajectory is valid"
+            assert sim["quality"] == 1.0 / (1.0 + ref.jl_cost)
+    assert sorted(verdicts) == [0, 1]
+    stop = batch.check_trajectory(0, estop=True)
+    assert stop["action_result"] and not stop["ok"] and stop["message"] == "FATAL_ERROR REASON: Emergency-Stop triggered"
+    assert len(stop["q"]) == 0
+    off = batch.check_trajectory(1, check_enabled=False)
+    assert off["set_trajectory"] and not off["action_result"] and len(off["q"]) == 0
