@@ -17,7 +17,9 @@
 #include "kernel/rollout.cuh"
 
 #define AFF_WARPS_PER_BLOCK 4
+#ifndef AFF_BLOCKS_PER_SM
 #define AFF_BLOCKS_PER_SM 4     // register budget: 65536 / (4 * 128) = 128 per thread (5 blocks at 96 registers spill too much: measured slower)
+#endif
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }

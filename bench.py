@@ -42,6 +42,12 @@ UNIT = "rollouts/s"
 L2_FLUSH_BYTES = 256 << 20
 
 
+# candidate tables read once (tasks, via points, activations, graph constraints, candidate record) + 88-byte verdict
+ALGORITHMIC_BYTES_PER_ROLLOUT = 2300 + 88
+# dram__bytes_read.sum + dram__bytes_write.sum of one aff_rollout_kernel launch / rollouts in it (profiles/r1_summary.md)
+NCU_DRAM_BYTES_PER_ROLLOUT = 5320
+
+
 def algorithmic_flops_per_rollout():
     """FP64 flops one full-length rollout needs (FMA = 2), counted per step from
     the problem dimensions of the pizza-scene `get` workload; the terms are
@@ -241,6 +247,14 @@ def run_cuda(args, rank, local_rank, world):
         flops = algorithmic_flops_per_rollout() * n_local
         avg_kernel_s = (sum(kernel_ms) / len(kernel_ms)) * 1e-3
         achieved = flops / avg_kernel_s * 1e-12
+        per_launch = n_local // len(VARIANTS)
+        hbm_peak, hbm_src = 6553.9, "fallback (MEASURED_PEAKS.json missing)"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except (OSError, KeyError, ValueError):
+            pass
+        hbm_achieved = ALGORITHMIC_BYTES_PER_ROLLOUT * n_local / avg_kernel_s * 1e-9
         # bounded CPU sample on the box's host cores (N=1 only)
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -261,9 +275,15 @@ def run_cuda(args, rank, local_rank, world):
                     "steps": e2e_steps, "call": "aff_predict_batch (plan compile + H2D + kernels + D2H, pageable host buffers)"},
             "gpu_launches": launches * world,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None,
-                         "traffic": None, "kernel": "aff_rollout_kernel",
+                         "traffic": NCU_DRAM_BYTES_PER_ROLLOUT * per_launch, "traffic_unit": "bytes per launch (dram read + write, "
+                         "ncu --set full capture profiles/r1_summary.md: 5.3 KB per rollout) - FP64 work does not scale with it",
+                         "kernel": "aff_rollout_kernel",
                          "flops_per_rollout": algorithmic_flops_per_rollout(), "peak_source": "DFMA microbenchmark measured in this run "
                          "(MEASURED_PEAKS.json holds no FP64 figure)", "kernel_ms_per_step": sum(kernel_ms) / len(kernel_ms)},
+            # the same kernel against the HBM roof, to show why that roof does not bound it
+            "roofline_hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": hbm_achieved / hbm_peak, "algorithmic_bytes_per_rollout": ALGORITHMIC_BYTES_PER_ROLLOUT,
+                             "peak_source": hbm_src},
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
         }
