@@ -11,7 +11,7 @@ int TaskSpec::dim() const
 {
   if (controlVariable == "XYZ") return 3;
   if (controlVariable == "POLAR") return 2;
-  if (controlVariable == "Joints") return (int)jnts.size();
+  if (controlVariable == "Joints" || controlVariable == "Joint") return (int)jnts.size();
   return 1;
 }
 
@@ -50,10 +50,10 @@ void ActivationSet::addVectorConstraint(double t, const std::vector<double>& x, 
   for (size_t i = 0; i < x.size(); ++i) add(t, x[i], 0.0, 0.0, 7, task + " " + std::to_string(i));
 }
 
-void ActivationSet::addConnectBodyConstraint(double t, const std::string& child, const std::string& parent)
+void ActivationSet::addConnectBodyConstraint(double t, const std::string& child, const std::string& parent, bool identityTransform)
 {
   Entry e{};
-  e.kind = AFF_CON_CONNECT; e.t = t; e.bodyA = child; e.bodyB = parent; e.flag = 1;
+  e.kind = AFF_CON_CONNECT; e.t = t; e.bodyA = child; e.bodyB = parent; e.flag = 1; e.dim = identityTransform ? 1 : 0;
   entries.push_back(e);
 }
 
@@ -107,7 +107,7 @@ void CandidateBatch::append(const Graph& graph, const std::vector<TaskSpec>& spe
     else if (cv == "Z") t.kind = AFF_TASK_Z;
     else if (cv == "POLAR") t.kind = AFF_TASK_POLAR;
     else if (cv == "Inclination") t.kind = AFF_TASK_INCLINATION;
-    else if (cv == "Joints") t.kind = AFF_TASK_JOINTS;
+    else if (cv == "Joints" || cv == "Joint") t.kind = AFF_TASK_JOINTS;
     else throw ActionException("ERROR: controlVariable '" + cv + "' is not supported by the GPU predictor", ActionException::ParamInvalid);
     t.effector = bodyId(graph, s.effector, s.name.c_str());
     t.ref_body = bodyId(graph, s.refBdy, s.name.c_str());
@@ -156,6 +156,22 @@ std::string ActionBase::getActionCommand() const
   std::string cmd = actionName;
   for (const auto& p : actionParams) { cmd += " "; cmd += p; }
   return cmd;
+}
+
+const Capability* getGraspingCapability(const Graph& graph, const Manipulator* hand, int objBody)
+{
+  for (const Capability& c : hand->capabilities)
+    if (c.isGrasp() && graph.getBodyByName(c.frame) == graph.bodies[objBody].parent) return &c;
+  return nullptr;
+}
+
+const AffordanceEntity* raycastSurface(const ActionScene& domain, const Graph& graph, int objBody)
+{
+  double mn[3], mx[3], dMin = 0.0;
+  if (!graph.computeBodyAABB(objBody, mn, mx)) return nullptr;
+  const double from[3] = {0.5 * (mn[0] + mx[0]), 0.5 * (mn[1] + mx[1]), mn[2] - 1.0e-8}, dir[3] = {0.0, 0.0, -1.0};
+  const int below = graph.closestRigidBodyInDirection(from, dir, &dMin);
+  return below >= 0 ? domain.getAffordanceEntity(graph.bodies[below].name) : nullptr;
 }
 
 void ActionBase::appendTo(CandidateBatch& batch, const Graph& graph, double duration, double dt) const

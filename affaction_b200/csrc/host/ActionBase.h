@@ -61,7 +61,8 @@ public:
   void addPositionConstraint(double t, double x, double y, double z, const std::string& task, int flag = 7);   // tropic::PositionConstraint
   void addPolarConstraint(double t, double phi, double theta, const std::string& task, int flag = 7);          // tropic::PolarConstraint
   void addVectorConstraint(double t, const std::vector<double>& x, const std::string& task);     // tropic::VectorConstraint
-  void addConnectBodyConstraint(double t, const std::string& child, const std::string& parent);  // tropic::ConnectBodyConstraint
+  void addConnectBodyConstraint(double t, const std::string& child, const std::string& parent,
+                                bool identityTransform = false);  // tropic::ConnectBodyConstraint (+ setConnectTransform(identity))
   void addCollisionModelConstraint(double t, const std::string& body, bool switchOn);            // tropic::CollisionModelConstraint
   void add(const ActivationSet& other);
   std::vector<Entry> entries;
@@ -112,6 +113,12 @@ protected:
   std::string actionName;
   std::vector<std::string> actionParams;
 };
+
+// Manipulator::getGraspingCapability: the grasp capability whose frame parents the object, or null.
+const Capability* getGraspingCapability(const Graph& graph, const Manipulator* hand, int objBody);
+// ActionBase::raycastSurface (reference src/ActionBase.cpp:271-313): the entity straight below the
+// bottom of the object's bounding box, or null.
+const AffordanceEntity* raycastSurface(const ActionScene& domain, const Graph& graph, int objBody);
 
 // name -> constructor registry (reference src/ActionFactory.h:61-105).
 class ActionFactory

@@ -31,14 +31,6 @@ ActionPut::ActionPut(const ActionScene& domain, const Graph& graph, std::vector<
   init(domain, graph, params[0], params.size() > 1 ? params[1] : std::string());
 }
 
-// Manipulator::getGraspingCapability: the grasp capability whose frame parents the object
-static const Capability* graspingCapability(const Graph& graph, const Manipulator* hand, int objBody)
-{
-  for (const Capability& c : hand->capabilities)
-    if (c.isGrasp() && graph.getBodyByName(c.frame) == graph.bodies[objBody].parent) return &c;
-  return nullptr;
-}
-
 // Manipulator::getGrasp (reference src/Manipulator.cpp:301-345): the object's affordance frame closest to
 // the grasp frame.  The reference's angular term reads (org[2], rot[0][0], rot[0][1]) of each frame as a
 // vector (it takes the address of org[2]); that is restated as written.
@@ -88,7 +80,7 @@ void ActionPut::init(const ActionScene& domain, const Graph& graph, const std::s
   for (const Manipulator* m : domain.getOccupiedManipulators(graph)) if (m->name != graspingHand->name) usedManipulators.push_back(m->name);
 
   const int objBody = graph.getBodyByName(objName);
-  const Capability* graspCap = graspingCapability(graph, graspingHand, objBody);
+  const Capability* graspCap = getGraspingCapability(graph, graspingHand, objBody);
   if (!graspCap) throw ActionException("ERROR REASON: cannot tell how the " + objectToPut + " is held", ActionException::UnknownError);
   isPincerGrasped = graspCap->classType == Capability::Type::PincergraspCapability;
   graspFrame = graspCap->frame;
@@ -101,13 +93,7 @@ void ActionPut::init(const ActionScene& domain, const Graph& graph, const std::s
     throw ActionException("ERROR REASON: The surface " + surfaceToPutOn + " to put the " + objectToPut +
                           " on is unknown. SUGGESTION: Use an object name that is defined in the environment", ActionException::ParamNotFound);
   if (!surface) {
-    // raycastSurface (src/ActionBase.cpp:271-313): straight down from the bottom of the object's AABB
-    double mn[3], mx[3], dMin = 0.0;
-    if (graph.computeBodyAABB(objBody, mn, mx)) {
-      const double from[3] = {0.5 * (mn[0] + mx[0]), 0.5 * (mn[1] + mx[1]), mn[2] - 1.0e-8}, dir[3] = {0.0, 0.0, -1.0};
-      const int below = graph.closestRigidBodyInDirection(from, dir, &dMin);
-      if (below >= 0) surface = domain.getAffordanceEntity(graph.bodies[below].name);
-    }
+    surface = raycastSurface(domain, graph, objBody);
     if (!surface)
       throw ActionException("ERROR REASON: There is nothing under the " + objectToPut + " where I can put it on. SUGGESTION: Specify another object to put it on",
                             ActionException::KinematicallyImpossible);

@@ -73,6 +73,12 @@ bool Manipulator::isEmpty(const Graph& graph) const
   return true;
 }
 
+const ModelState* ActionScene::getModelState(const std::string& name, int timeStamp) const
+{
+  for (const ModelState& m : modelStates) if (m.name == name && m.timeStamp == timeStamp) return &m;
+  return nullptr;
+}
+
 void ActionScene::parse(const std::vector<std::string>& lines)
 {
   AffordanceEntity* ent = nullptr;
@@ -117,6 +123,8 @@ void ActionScene::parse(const std::vector<std::string>& lines)
       is >> m.name >> m.type >> nf >> nc;
       manipulators.push_back(m); man = &manipulators.back();
     }
+    else if (tok == "modelstate") { ModelState m; size_t n; is >> m.name >> m.timeStamp >> n; modelStates.push_back(m); }
+    else if (tok == "msjoint") { std::string j; double v; is >> j >> v; if (!modelStates.empty()) modelStates.back().joints.emplace_back(j, v); }
     else if (tok == "finger") { std::string j; is >> j; if (man) man->fingerJoints.push_back(j); }
     else if (tok == "cap") {
       if (!man) throw std::runtime_error("cap line outside manipulator");

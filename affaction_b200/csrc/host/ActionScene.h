@@ -62,6 +62,14 @@ struct Manipulator
   bool isEmpty(const Graph& graph) const;
 };
 
+// One <model_state model=".." time_stamp=".."> of the graph file: joint name -> value (rad / m).
+struct ModelState
+{
+  std::string name;
+  int timeStamp = 0;
+  std::vector<std::pair<std::string, double>> joints;
+};
+
 using AffCapPair = std::tuple<const Affordance*, const Capability*>;
 using AffAffPair = std::tuple<const Affordance*, const Affordance*>;
 
@@ -80,8 +88,12 @@ public:
   const Manipulator* getGraspingHand(const Graph& graph, const AffordanceEntity* entity) const;
   const AffordanceEntity* getParentAffordanceEntity(const Graph& graph, const AffordanceEntity* child) const;
 
+  // RcsGraph_getModelStateFromXML: the named state, or null
+  const ModelState* getModelState(const std::string& name, int timeStamp) const;
+
   std::vector<AffordanceEntity> entities;
   std::vector<Manipulator> manipulators;
+  std::vector<ModelState> modelStates;
 };
 
 // match<T>(object, hand): every (affordance of type T or derived) x (capability

@@ -10,7 +10,9 @@
 
 #include "ActionBase.h"
 #include "ActionComposite.h"
+#include "ActionDrop.h"
 #include "ActionGet.h"
+#include "ActionPose.h"
 #include "ActionPour.h"
 #include "ActionPut.h"
 #include "TrajectoryComponent.h"
@@ -293,10 +295,12 @@ std::unique_ptr<ActionBase> ActionFactory::create(const ActionScene& domain, con
   if (name == "get") a.reset(new ActionGet(domain, graph, params));
   else if (name == "put") a.reset(new ActionPut(domain, graph, params));
   else if (name == "double_get") a.reset(new ActionDoubleGet(domain, graph, params));
+  else if (name == "drop") a.reset(new ActionDrop(domain, graph, params));
+  else if (name == "pose") a.reset(new ActionPose(domain, graph, params));
   else if (name == "pour") a.reset(new ActionPour(domain, graph, params));
   else
     throw ActionException("ERROR: REASON: Action '" + name + "' is not part of the GPU predict path" +
-                          " SUGGESTION: Use one of: get, put, pour, double_get", ActionException::ParamNotFound);
+                          " SUGGESTION: Use one of: get, put, pour, drop, pose, double_get", ActionException::ParamNotFound);
   a->setName(name);
   a->setActionParams(params);
   return a;

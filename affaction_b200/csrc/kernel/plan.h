@@ -17,7 +17,7 @@
 #define AFFK_MAX_NJ 32        // IK joints: one lane each
 #define AFFK_MAX_DYN 40       // dynamic nodes
 #define AFFK_MAX_XDIM 32      // stacked task dimensions of one candidate
-#define AFFK_MAX_TASKS 16     // tasks of one candidate
+#define AFFK_MAX_TASKS 32     // tasks of one candidate
 #define AFFK_MAX_M 16         // task rows active at the same time
 #define AFFK_MAX_OBJ 2        // re-parentable objects per candidate
 #define AFFK_MAX_DSHAPE 40    // shapes on dynamic nodes
@@ -99,6 +99,7 @@ struct KTask
 
 struct KVia { double t, x, xd, xdd; int32_t flag; int32_t pad; };
 struct KAct { double t, horizon; int32_t on; int32_t pad; };
+// on: collision toggle direction; for a connect, 1 = the relative transform is the identity
 // parent_tree: broad-phase tree of the new parent, or -2-s if the parent hangs below object s
 struct KGraphCon { double t; int32_t kind; int32_t on; int32_t slot; int32_t parent; int32_t parent_slot; int32_t parent_tree; };
 

@@ -525,7 +525,7 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     kc.first_gcon = (int)H.gcons.size();
     for (int k = 0; k < c.n_constraints; ++k) {
       if (cc[k].kind != AFF_CON_CONNECT && cc[k].kind != AFF_CON_COLLISION) continue;
-      KGraphCon g; g.t = cc[k].t; g.kind = cc[k].kind; g.on = cc[k].flag ? 1 : 0; g.slot = objSlotOfBody[cc[k].body_a];
+      KGraphCon g; g.t = cc[k].t; g.kind = cc[k].kind; g.on = (cc[k].kind == AFF_CON_CONNECT) ? (cc[k].dim == 1 ? 1 : 0) : (cc[k].flag ? 1 : 0); g.slot = objSlotOfBody[cc[k].body_a];
       g.parent = (cc[k].kind == AFF_CON_CONNECT) ? bodyRef[cc[k].body_b] : AFFK_WORLD;
       g.parent_slot = (cc[k].kind == AFF_CON_CONNECT) ? slotOfRef(g.parent) : 0;
       g.parent_tree = -1;

@@ -1118,10 +1118,12 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
           const int on = ldg(&P.obj_node[slot]);
           w_sync();
           if (lane < 12) {
-            // HTr_invTransform: child relative to the new parent
+            // HTr_invTransform: child relative to the new parent; or the identity the constraint
+            // was given (setConnectTransform): the child then sits on the parent frame
             const double* Cc = k_slot(c, on); const double* Pp = k_slot(c, ps);
             double v;
-            if (lane < 3) {
+            if (ldg(&gcons[k].on)) v = (lane == 3 || lane == 7 || lane == 11) ? 1.0 : 0.0;
+            else if (lane < 3) {
               const double d0 = Cc[0] - Pp[0], d1 = Cc[1] - Pp[1], d2 = Cc[2] - Pp[2];
               v = fma(Pp[3 + 3 * lane + 2], d2, fma(Pp[3 + 3 * lane + 1], d1, Pp[3 + 3 * lane] * d0));
             } else {

@@ -72,7 +72,8 @@ enum {
 enum {
   AFF_CON_VIA = 0,        /* a1->add(t, x, xd, xdd, flag, "task dim")             */
   AFF_CON_ACTIVATION = 1, /* a1->addActivation(t, on, horizon, task)               */
-  AFF_CON_CONNECT = 2,    /* tropic::ConnectBodyConstraint(t, child, parent)       */
+  AFF_CON_CONNECT = 2,    /* tropic::ConnectBodyConstraint(t, child, parent); dim = 1:
+                           * setConnectTransform(HTr_identity()), the child jumps onto the parent frame */
   AFF_CON_COLLISION = 3   /* tropic::CollisionModelConstraint(t, body, on)         */
 };
 

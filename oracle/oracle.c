@@ -263,12 +263,15 @@ static int joint_moves_body(const Graph* g, int jid, int body)
 
 /* tropic::ConnectBodyConstraint: re-parent `child` under `parent` keeping its
  * world pose; the six rigid-body dofs are replaced by the relative transform. */
-static int graph_connect(Graph* g, int child, int parent)
+static int graph_connect(Graph* g, int child, int parent, int identity)
 {
   if (child < 0 || parent < 0 || child >= g->nB || parent >= g->nB || !g->d->body_rbj[child]) return -1;
   /* frame at the end of the rigid-body joints = body frame when A_BP is identity */
   HTr rel;
   htr_relative(&rel, &g->A_BI[child], &g->A_BI[parent]);
+  if (identity) {   /* cbc->setConnectTransform(HTr_identity()), e.g. src/ActionDrop.cpp:237-239 */
+    for (int i = 0; i < 3; ++i) { rel.org[i] = 0.0; for (int j = 0; j < 3; ++j) rel.rot[i][j] = (i == j) ? 1.0 : 0.0; }
+  }
   g->rel[child] = rel;
   g->has_rel[child] = 1;
   g->parent[child] = parent;
@@ -1186,7 +1189,7 @@ static double tc_step(TrajCtrl* tc, Graph* g, double dt)
     const aff_constraint* c = &tc->gcon[k];
     if (tc->gfired[k]) continue;
     if (c->kind == AFF_CON_CONNECT) {
-      if (c->t - tc->tnow < TRAJ_EPS) { graph_connect(g, c->body_a, c->body_b); tc->gfired[k] = 1; }
+      if (c->t - tc->tnow < TRAJ_EPS) { graph_connect(g, c->body_a, c->body_b, c->dim == 1); tc->gfired[k] = 1; }
     } else if (c->kind == AFF_CON_COLLISION) {
       /* toggleTime -= dt; fires when toggleTime < 0 (CollisionModelConstraint.h:101-105) */
       if (c->t - tc->tnow < 0.0) {

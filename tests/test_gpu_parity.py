@@ -202,3 +202,30 @@ def test_trajectory_component_recheck(scene):
     assert len(stop["q"]) == 0
     off = batch.check_trajectory(1, check_enabled=False)
     assert off["set_trajectory"] and not off["action_result"] and len(off["q"]) == 0
+
+
+def test_drop_after_get_matches_oracle(built):
+    """`drop`: seven surface candidates, 805 steps each, the object re-parented
+    with an identity connect transform at the end."""
+    from chain_util import scene_after_get
+    scene = scene_after_get("italian_seasoning_bowl")
+    batch = ab.HostBatch(scene)
+    n = batch.add_action("drop italian_seasoning_bowl table")
+    assert n == 7
+    n += batch.add_action("drop italian_seasoning_bowl")          # surface found by the ray cast
+    opts = ab.default_opts(log_q=True)
+    dev = ab.DeviceBatch(scene, batch, opts)
+    dev.launch()
+    assert dev.num_steps(0) == 805
+    assert _compare(scene, batch, opts, dev, range(n)) == 0.0
+
+
+@pytest.mark.parametrize("state", ["TableCalibration", "TableCalibration_140", "Default"])
+def test_pose_matches_oracle(scene, state):
+    """`pose`: 20 one-joint tasks, a 20 x 20 right inverse every step."""
+    batch = ab.HostBatch(scene)
+    assert batch.add_action("pose " + state) == 1
+    opts = ab.default_opts(log_q=True)
+    dev = ab.DeviceBatch(scene, batch, opts)
+    dev.launch()
+    assert _compare(scene, batch, opts, dev, [0]) == 0.0

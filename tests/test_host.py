@@ -205,3 +205,52 @@ def test_double_get_is_the_union_of_two_gets(scene):
                      ("double_get italian_seasoning_bowl nothing", "Object nothing is unknown")):
         with pytest.raises(ab.AffError, match=msg):
             ab.HostBatch(scene).add_action(cmd)
+
+
+def test_drop_candidates_after_get(built):
+    """ActionDrop has one solution per Supportable of the surface
+    (src/ActionDrop.cpp:134-150), runs 3 s and places the object onto the surface frame with an
+    identity ConnectBodyConstraint (:236-239)."""
+    from chain_util import scene_after_get
+    scene = scene_after_get("italian_seasoning_bowl")
+    b = ab.HostBatch(scene)
+    assert b.add_action("drop italian_seasoning_bowl table") == 7
+    tasks, cands, cons = _tasks(b), _cands(b), _cons(b)
+    surfaces = set()
+    for c in cands:
+        tl = tasks[c.first_task:c.first_task + c.n_tasks]
+        assert [t.kind for t in tl] == [ab.TASK_INCLINATION, ab.TASK_XYZ, ab.TASK_JOINTS]
+        assert tl[0].axis == 1 and tl[0].effector == tl[1].effector == scene.body_id("hand_right_pincergrasp")
+        cc = cons[c.first_constraint:c.first_constraint + c.n_constraints]
+        conn = [k for k in cc if k.kind == ab.CON_CONNECT]
+        assert len(conn) == 1 and conn[0].dim == 1 and conn[0].t == pytest.approx(0.05 + 3.0)
+        assert conn[0].body_a == scene.body_id("italian_seasoning_bowl")
+        surfaces.add(scene.body_name(conn[0].body_b))
+        incl = [k for k in cc if k.kind == ab.CON_VIA and k.task == 0]
+        assert len(incl) == 1 and incl[0].x == pytest.approx(np.pi / 2) and incl[0].t == pytest.approx(0.05 + 1.5)
+    assert len(surfaces) == 7 and "table" in surfaces
+    assert b.task_name(0, 0) == "hand_right-InclinationY"
+    with pytest.raises(ab.AffError, match="no hand is grasping the object"):
+        ab.HostBatch(scene).add_action("drop tomato_sauce_bottle")
+    with pytest.raises(ab.AffError, match="not found in scene"):
+        ab.HostBatch(scene).add_action("drop nothing")
+
+
+def test_pose_tasks(scene):
+    """ActionPose (src/ActionPose.cpp:54-144): one Joint task per unconstrained joint of the model
+    state, a single full constraint at t_end, tasks switched off half a second later."""
+    b = ab.HostBatch(scene)
+    assert b.add_action("pose TableCalibration") == 1
+    tasks, cons = _tasks(b), _cons(b)
+    assert len(tasks) == 20 and all(t.kind == ab.TASK_JOINTS and t.n_joints == 1 for t in tasks)
+    assert b.task_name(0, 0) == "j2s7s300_joint_1_right" and b.task_name(0, 19) == "j2s7s300_joint_finger_3_left"
+    via = [k for k in cons if k.kind == ab.CON_VIA]
+    assert len(via) == 20 and all(k.flag == 7 and k.t == pytest.approx(10.05) for k in via)
+    assert via[0].x == pytest.approx(np.deg2rad(31.807518)) and via[7].x == pytest.approx(np.deg2rad(10.0))
+    acts = [k for k in cons if k.kind == ab.CON_ACTIVATION]
+    assert sorted(set(round(k.t, 9) for k in acts)) == [0.05, 10.55]
+    assert ab.HostBatch(scene).add_action("pose TableCalibration_140 0") == 1
+    with pytest.raises(ab.AffError, match="Model state with name not found: Nowhere"):
+        ab.HostBatch(scene).add_action("pose Nowhere")
+    with pytest.raises(ab.AffError, match="Model state with name not found"):
+        ab.HostBatch(scene).add_action("pose TableCalibration 3")

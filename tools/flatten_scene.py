@@ -75,6 +75,7 @@ class Flattener:
         self.bodies = []          # dicts in document order
         self.body_index = {}
         self.model_states = []    # (model, [(joint, deg)])
+        self.model_state_stamps = []
         self.broadphase = None
         self.entities = []
         self.manipulators = []
@@ -130,6 +131,7 @@ class Flattener:
                 if top:
                     js = [(j.get("joint"), float(j.get("position"))) for j in ch if j.tag == "joint_state"]
                     self.model_states.append((ch.get("model"), js))
+                    self.model_state_stamps.append(int(ch.get("time_stamp", "0")))
             elif tag == "BroadPhase":
                 if top:
                     self.broadphase = {
@@ -310,6 +312,14 @@ class Flattener:
                 w("finger %s\n" % fj)
             for c in m["caps"]:
                 w("cap %s %s\n" % (c["cls"], c["frame"]))
+        # every <model_state> by name and time stamp (RcsGraph_getModelStateFromXML: the "pose" action)
+        jmap = {j["name"]: j for b in self.bodies for j in b["joints"]}
+        w("modelstates %d\n" % len(self.model_states))
+        for (model, js), stamp in zip(self.model_states, self.model_state_stamps):
+            known = [(jn, v) for jn, v in js if jn in jmap]
+            w("modelstate %s %d %d\n" % (model, stamp, len(known)))
+            for jn, v in known:
+                w("msjoint %s %s\n" % (jn, repr(math.radians(v) if jmap[jn]["type"] >= 3 else v)))
         w("end\n")
 
 
