@@ -16,7 +16,9 @@
 #include "kernel/plan_build.h"
 #include "kernel/rollout.cuh"
 
+#ifndef AFF_WARPS_PER_BLOCK
 #define AFF_WARPS_PER_BLOCK 4
+#endif
 #ifndef AFF_BLOCKS_PER_SM
 #define AFF_BLOCKS_PER_SM 4     // register budget: 65536 / (4 * 128) = 128 per thread (5 blocks at 96 registers spill too much: measured slower)
 #endif
@@ -209,8 +211,11 @@ int aff_batch_create(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, c
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
   b->smemBytes = b->host.smemBytesPerWarp * AFF_WARPS_PER_BLOCK;
+  // tuning experiments only (tools/try_variants.sh): extra dynamic shared memory per block, preferred carve-out in percent
+  if (const char* pad = getenv("AFF_TUNE_SMEM_PAD")) b->smemBytes += (size_t)atoi(pad);
   if (b->smemBytes > (size_t)prop.sharedMemPerBlockOptin) { b->release(); delete b; return fail(AFF_ERR_CAPACITY, "aff_batch_create: rollout state does not fit in shared memory"); }
   CUDA_TRY(cudaFuncSetAttribute(aff_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smemBytes));
+  if (const char* co = getenv("AFF_TUNE_CARVEOUT")) CUDA_TRY(cudaFuncSetAttribute(aff_rollout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co)));
   int perSM = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, aff_rollout_kernel, 32 * AFF_WARPS_PER_BLOCK, b->smemBytes));
   if (perSM < 1) perSM = 1;
