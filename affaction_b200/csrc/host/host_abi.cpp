@@ -11,6 +11,7 @@
 #include "ActionBase.h"
 #include "ActionComposite.h"
 #include "ActionDrop.h"
+#include "ActionFingerPush.h"
 #include "ActionGet.h"
 #include "ActionPose.h"
 #include "ActionPour.h"
@@ -297,10 +298,11 @@ std::unique_ptr<ActionBase> ActionFactory::create(const ActionScene& domain, con
   else if (name == "double_get") a.reset(new ActionDoubleGet(domain, graph, params));
   else if (name == "drop") a.reset(new ActionDrop(domain, graph, params));
   else if (name == "pose") a.reset(new ActionPose(domain, graph, params));
+  else if (name == "finger_push" || name == "poke") a.reset(new ActionFingerPush(domain, graph, params));
   else if (name == "pour") a.reset(new ActionPour(domain, graph, params));
   else
     throw ActionException("ERROR: REASON: Action '" + name + "' is not part of the GPU predict path" +
-                          " SUGGESTION: Use one of: get, put, pour, drop, pose, double_get", ActionException::ParamNotFound);
+                          " SUGGESTION: Use one of: get, put, pour, drop, pose, finger_push, double_get", ActionException::ParamNotFound);
   a->setName(name);
   a->setActionParams(params);
   return a;

@@ -229,3 +229,16 @@ def test_pose_matches_oracle(scene, state):
     dev = ab.DeviceBatch(scene, batch, opts)
     dev.launch()
     assert _compare(scene, batch, opts, dev, [0]) == 0.0
+
+
+def test_finger_push_matches_oracle(built):
+    """`finger_push` with a finger and, after a get, with the held bottle's tip as the tool."""
+    from chain_util import scene_after_get
+    for scene, cmd in ((ab.HostScene(), "finger_push oven"), (scene_after_get("tomato_sauce_bottle", require_success=False), "poke oven tomato_sauce_bottle")):
+        batch = ab.HostBatch(scene)
+        assert batch.add_action(cmd) == 1
+        opts = ab.default_opts(log_q=True)
+        dev = ab.DeviceBatch(scene, batch, opts)
+        dev.launch()
+        assert dev.num_steps(0) == 2155
+        assert _compare(scene, batch, opts, dev, [0]) == 0.0

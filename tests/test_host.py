@@ -254,3 +254,24 @@ def test_pose_tasks(scene):
         ab.HostBatch(scene).add_action("pose Nowhere")
     with pytest.raises(ab.AffError, match="Model state with name not found"):
         ab.HostBatch(scene).add_action("pose TableCalibration 3")
+
+
+def test_finger_push_tasks(scene):
+    """ActionFingerPush (src/ActionFingerPush.cpp:67-306): closest free finger onto the object's
+    PointPushable frame, 16 s, five-point timing ladder."""
+    b = ab.HostBatch(scene)
+    assert b.add_action("finger_push oven") == 1
+    tasks, cons = _tasks(b), _cons(b)
+    assert [t.kind for t in tasks] == [ab.TASK_XYZ, ab.TASK_POLAR, ab.TASK_JOINTS]
+    assert tasks[0].ref_body == tasks[1].ref_body == scene.body_id("oven_switch")
+    assert b.task_name(0, 0).startswith("PushButton-XYZ-hand_") and b.task_name(0, 2).endswith("_fingers")
+    t0, dur = 0.05, 16.0
+    z = sorted((round(k.t, 9), k.x) for k in cons if k.kind == ab.CON_VIA and k.task == 0 and k.dim == 2)
+    assert z == [(round(t0 + 0.5 * dur, 9), 0.05), (round(t0 + 0.7 * dur, 9), 0.0), (round(t0 + 0.8 * dur, 9), -0.03), (round(t0 + dur, 9), 0.1)]
+    fingers = [k.x for k in cons if k.kind == ab.CON_VIA and k.task == 2]
+    assert fingers == [1.32] * 6
+    assert ab.HostBatch(scene).add_action("poke oven") == 1
+    for cmd, msg in (("finger_push table", "is not switchable"), ("finger_push nothing", "is unknown"),
+                     ("finger_push oven table", "cannot be used to switch something on")):
+        with pytest.raises(ab.AffError, match=msg):
+            ab.HostBatch(scene).add_action(cmd)
