@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdint>
 #include <cstdlib>
 #include <cfloat>
 #include <cstdio>
@@ -62,6 +63,7 @@ __global__ void aff_dfma_peak_kernel(double* out, int iters)
 struct aff_scene
 {
   int device = 0;
+  int smCount = 0, smemOptin = 0;     // queried once: cudaGetDeviceProperties costs milliseconds per call
   affk::SceneModel model;
 };
 
@@ -141,6 +143,11 @@ int aff_scene_create(const aff_scene_desc* desc, int device, aff_scene** out)
   if (device < 0 || device >= n) return fail(AFF_ERR_CUDA, "aff_scene_create: CUDA device " + std::to_string(device) + " not present (no CPU fallback)");
   aff_scene* s = new aff_scene;
   s->device = device;
+  if (cudaDeviceGetAttribute(&s->smCount, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&s->smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) {
+    delete s;
+    return fail(AFF_ERR_CUDA, "aff_scene_create: cannot query the device");
+  }
   const std::string e = s->model.init(desc);
   if (!e.empty()) { delete s; return fail(AFF_ERR_INVALID, "aff_scene_create: " + e); }
   *out = s;
@@ -208,19 +215,17 @@ int aff_batch_create(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, c
   }
   if (rc != AFF_OK) { b->release(); delete b; return rc; }
   // launch geometry: persistent blocks, as many as fit per SM
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
   b->smemBytes = b->host.smemBytesPerWarp * AFF_WARPS_PER_BLOCK;
   // tuning experiments only (tools/try_variants.sh): extra dynamic shared memory per block, preferred carve-out in percent
   if (const char* pad = getenv("AFF_TUNE_SMEM_PAD")) b->smemBytes += (size_t)atoi(pad);
-  if (b->smemBytes > (size_t)prop.sharedMemPerBlockOptin) { b->release(); delete b; return fail(AFF_ERR_CAPACITY, "aff_batch_create: rollout state does not fit in shared memory"); }
+  if (b->smemBytes > (size_t)s->smemOptin) { b->release(); delete b; return fail(AFF_ERR_CAPACITY, "aff_batch_create: rollout state does not fit in shared memory"); }
   CUDA_TRY(cudaFuncSetAttribute(aff_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smemBytes));
   if (const char* co = getenv("AFF_TUNE_CARVEOUT")) CUDA_TRY(cudaFuncSetAttribute(aff_rollout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co)));
   int perSM = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, aff_rollout_kernel, 32 * AFF_WARPS_PER_BLOCK, b->smemBytes));
   if (perSM < 1) perSM = 1;
   const int blocksNeeded = (int)((n_cands + AFF_WARPS_PER_BLOCK - 1) / AFF_WARPS_PER_BLOCK);
-  b->grid = std::max(1, std::min(blocksNeeded, perSM * prop.multiProcessorCount));
+  b->grid = std::max(1, std::min(blocksNeeded, perSM * s->smCount));
   CUDA_TRY(cudaStreamSynchronize(0));
   *out = b;
   return AFF_OK;
@@ -292,18 +297,63 @@ int aff_predict_batch(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, 
   static const bool timing = getenv("AFF_TIMING") != nullptr;   // AFF_TIMING=1: per-stage wall clock on stderr
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  if (!s || !out) return fail(AFF_ERR_INVALID, "aff_predict_batch: null argument");
   const auto t0 = now();
-  aff_batch* b = nullptr;
-  int rc = aff_batch_create(s, tasks, n_tasks, cons, n_cons, cands, n_cands, opts, &b);
-  if (rc != AFF_OK) return rc;
+  // Large batches go through in chunks of whole waves of the persistent grid: the host compiles and
+  // uploads chunk k+1 (default stream) while the kernels of chunk k run on their own stream.
+  CUDA_TRY(cudaSetDevice(s->device));
+  size_t wave = (size_t)s->smCount * AFF_BLOCKS_PER_SM * AFF_WARPS_PER_BLOCK;
+  std::vector<aff_batch*> parts;
+  std::vector<size_t> first;
+  cudaStream_t ks = nullptr;
+  int rc = AFF_OK;
+  double planMs = 0.0;
+  auto cleanup = [&]() { for (aff_batch* p : parts) aff_batch_destroy(p); if (ks) cudaStreamDestroy(ks); };
+  if (n_cands > 2 * wave) { if (cudaStreamCreateWithFlags(&ks, cudaStreamNonBlocking) != cudaSuccess) { ks = nullptr; wave = n_cands; } }
+  else wave = n_cands;
+  for (size_t off = 0; off < n_cands && rc == AFF_OK;) {
+    size_t cnt = std::min(wave, n_cands - off);
+    if (n_cands - off - cnt < wave / 2) cnt = n_cands - off;        // no short last chunk
+    const auto tp = now();
+    aff_batch* b = nullptr;
+    if (cnt == n_cands) rc = aff_batch_create(s, tasks, n_tasks, cons, n_cons, cands, cnt, opts, &b);
+    else {
+      // only the slices of the task / constraint tables this chunk refers to
+      int32_t t0i = INT32_MAX, t1i = 0, c0i = INT32_MAX, c1i = 0;
+      for (size_t i = 0; i < cnt; ++i) {
+        const aff_candidate& c = cands[off + i];
+        t0i = std::min(t0i, c.first_task); t1i = std::max(t1i, c.first_task + c.n_tasks);
+        c0i = std::min(c0i, c.first_constraint); c1i = std::max(c1i, c.first_constraint + c.n_constraints);
+      }
+      if (t0i < 0 || c0i < 0 || (size_t)t1i > n_tasks || (size_t)c1i > n_cons) { rc = fail(AFF_ERR_INVALID, "aff_predict_batch: candidate refers outside the tables"); break; }
+      std::vector<aff_candidate> local(cands + off, cands + off + cnt);
+      for (aff_candidate& c : local) { c.first_task -= t0i; c.first_constraint -= c0i; }
+      rc = aff_batch_create(s, tasks + t0i, (size_t)(t1i - t0i), cons + c0i, (size_t)(c1i - c0i), local.data(), cnt, opts, &b);
+    }
+    planMs += ms(tp, now());
+    if (rc != AFF_OK) break;
+    parts.push_back(b);
+    first.push_back(off);
+    if (parts.size() == 1 && ks) {
+      // the first chunk tells how many rollouts are resident at once with this batch's shared-memory footprint
+      const size_t resident = (size_t)b->grid * AFF_WARPS_PER_BLOCK;
+      if (resident > 0 && resident < wave) wave = resident;
+    }
+    rc = aff_batch_launch(b, ks);
+    off += cnt;
+  }
   const auto t1 = now();
-  rc = aff_batch_launch(b, nullptr);
-  if (rc == AFF_OK) rc = aff_batch_results(b, nullptr, out, n_cands);
+  for (size_t k = 0; k < parts.size() && rc == AFF_OK; ++k) {
+    const size_t cnt = (size_t)parts[k]->plan.nCands;
+    rc = aff_batch_results(parts[k], ks, out + first[k], cnt);
+    for (size_t i = 0; i < cnt; ++i) out[first[k] + i].idx += (int32_t)first[k];
+  }
   const auto t2 = now();
-  aff_batch_destroy(b);
+  const size_t nParts = parts.size();
+  cleanup();
   const auto t3 = now();
-  if (timing) std::fprintf(stderr, "aff_predict_batch: %zu candidates: create (plan + H2D) %.1f ms, kernels + D2H %.1f ms, destroy %.1f ms\n",
-                           n_cands, ms(t0, t1), ms(t1, t2), ms(t2, t3));
+  if (timing) std::fprintf(stderr, "aff_predict_batch: %zu candidates in %zu chunk(s): plan + H2D %.1f ms (overlapped after the first chunk), "
+                           "submit %.1f ms, wait + D2H %.1f ms, destroy %.1f ms\n", n_cands, nParts, planMs, ms(t0, t1), ms(t1, t2), ms(t2, t3));
   return rc;
 }
 

@@ -242,3 +242,17 @@ def test_finger_push_matches_oracle(built):
         dev.launch()
         assert dev.num_steps(0) == 2155
         assert _compare(scene, batch, opts, dev, [0]) == 0.0
+
+
+def test_predict_batch_chunks_equal_single_launch(scene):
+    """aff_predict_batch pipelines large batches in chunks of whole waves (plan compile of chunk k+1
+    under the kernels of chunk k): same records, same order, idx = position in the caller's array."""
+    n = 3 * 2368 + 100
+    batch = ab.HostBatch(scene)
+    batch.add_perturbed("get fresh_tomatoes", n, seed0=99)
+    dev = ab.DeviceBatch(scene, batch, ab.default_opts())
+    dev.launch()
+    single = dev.results()
+    chunked = ab.predict_batch(scene, batch)
+    assert [r.idx for r in chunked] == list(range(n))
+    assert [r.as_tuple() for r in chunked] == [r.as_tuple() for r in single]
