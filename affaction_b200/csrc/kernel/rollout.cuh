@@ -303,15 +303,18 @@ AFF_DEV void k_via_step(double* st, const KVia* vias, int n, double tnow, double
 #define TD_DIM 6
 #define TD_NJ 7
 
+// (selects instead of t[k]: a dynamically indexed local array would live in local memory)
+AFF_DEV double k_sel3(const double* v, int k) { return k == 0 ? v[0] : (k == 1 ? v[1] : v[2]); }
+
 AFF_DEV void k_tangent_basis(const double* a, double* e1, double* e2)
 {
   int k = 0;
   double m = fabs(a[0]);
   if (fabs(a[1]) < m) { k = 1; m = fabs(a[1]); }
   if (fabs(a[2]) < m) { k = 2; }
+  const double ak = k_sel3(a, k);
   double t[3];
-  for (int i = 0; i < 3; ++i) t[i] = -(a[k] * a[i]);
-  t[k] = t[k] + 1.0;
+  for (int i = 0; i < 3; ++i) { const double ti = -(ak * a[i]); t[i] = (i == k) ? ti + 1.0 : ti; }
   const double n = sqrt(k_dot(t, t));
   for (int i = 0; i < 3; ++i) e1[i] = t[i] / n;
   k_cross(e2, a, e1);
@@ -334,7 +337,7 @@ AFF_DEV void k_task_geo(const KCtx& c, const int* td, const KTask* tk, double* g
     if (frame >= 0) k_mulv(xr, k_slot(c, frame) + 3, r);
     else { xr[0] = r[0]; xr[1] = r[1]; xr[2] = r[2]; }
     if (kind == AFF_TASK_XYZ) { xcur[xoff] = xr[0]; xcur[xoff + 1] = xr[1]; xcur[xoff + 2] = xr[2]; }
-    else xcur[xoff] = xr[kind - AFF_TASK_X];
+    else xcur[xoff] = k_sel3(xr, kind - AFF_TASK_X);
   } else if (kind == AFF_TASK_POLAR) {
     const double* Ae = k_slot(c, eff);
     const double* aI = Ae + 3 + 3 * axis;
@@ -422,7 +425,7 @@ AFF_DEV unsigned k_task_J(const KCtx& c, const KJointFrame& jf, const int* td, c
     if (kind == AFF_TASK_XYZ) {
       Jrow0[col] = out[0]; Jrow0[Jstride + col] = out[1]; Jrow0[2 * Jstride + col] = out[2];
       nz = (out[0] != 0.0 ? 1u : 0u) | (out[1] != 0.0 ? 2u : 0u) | (out[2] != 0.0 ? 4u : 0u);
-    } else { const double v = out[kind - AFF_TASK_X]; Jrow0[col] = v; nz = v != 0.0 ? 1u : 0u; }
+    } else { const double v = k_sel3(out, kind - AFF_TASK_X); Jrow0[col] = v; nz = v != 0.0 ? 1u : 0u; }
   } else if (kind == AFF_TASK_POLAR) {
     double te[3], re[3], tr[3], rr[3], wI[3], w[3];
     k_jac_cols(c, jf, eff, geo + 9, te, re);
@@ -972,11 +975,17 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
   const int nSlots = P.nDyn + P.nStatPar;
 
   // ---- per-lane constants
-  double jq0 = 0, jqmin = 0, jqmax = 0, jspeed = AFFK_NO_LIMIT, jacc = AFFK_NO_LIMIT, jwjl = 0, jw = 0;
+  // per-joint constants: re-read where they are used (ldg_here), not held in registers
+  const int jl = (lane < nJ) ? lane : 0;
+#define jq0 ldg_here(&P.jq0[jl])
+#define jqmin ldg_here(&P.jq_min[jl])
+#define jqmax ldg_here(&P.jq_max[jl])
+#define jspeed ldg_here(&P.jspeed[jl])
+#define jacc ldg_here(&P.jacc[jl])
+#define jwjl ldg_here(&P.jwjl[jl])
+#define jw ldg_here(&P.jwmetric[jl])
   int jnode = 0, jtype = 0;
   if (lane < nJ) {
-    jq0 = ldg(&P.jq0[lane]); jqmin = ldg(&P.jq_min[lane]); jqmax = ldg(&P.jq_max[lane]);
-    jspeed = ldg(&P.jspeed[lane]); jacc = ldg(&P.jacc[lane]); jwjl = ldg(&P.jwjl[lane]); jw = ldg(&P.jwmetric[lane]);
     jnode = ldg(&P.j_node[lane]); jtype = ldg(&P.j_type[lane]);
     q[lane] = ldg(&P.jq_init[lane]); qdot[lane] = 0.0; wbuf[lane] = jw;
   }
@@ -1419,6 +1428,13 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
     P.results[cand] = res;
   }
 }
+#undef jq0
+#undef jqmin
+#undef jqmax
+#undef jspeed
+#undef jacc
+#undef jwjl
+#undef jw
 
 // ------------------------------------------------- prologue (once per batch)
 // World transforms of the static nodes, world frames / AABBs of the static

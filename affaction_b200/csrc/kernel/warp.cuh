@@ -21,6 +21,7 @@ unsigned w_ballot(int pred);
 template <class T> static inline T ldg(const T* p) { return *p; }
 template <class T> static inline T ldg_pair(const T* p) { return *p; }
 template <class T> static inline T ldg_fk(const T* p) { return *p; }
+static inline double ldg_here(const double* p) { return *p; }
 static inline int w_popc(unsigned v) { return __builtin_popcount(v); }
 static inline int w_ffs(unsigned v) { return __builtin_ffs((int)v); }
 
@@ -36,6 +37,9 @@ AFF_DEV double w_shfl_xor(double v, int mask) { return __shfl_xor_sync(0xfffffff
 AFF_DEV int w_shfl_xor(int v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
 AFF_DEV unsigned w_ballot(int pred) { return __ballot_sync(0xffffffffu, pred); }
 template <class T> AFF_DEV T ldg(const T* p) { return __ldg(p); }
+// A read-only load the compiler may not hoist or keep: per-lane constants that are needed a few times per
+// step are re-read (L1) instead of occupying registers for the whole rollout.
+AFF_DEV double ldg_here(const double* p) { double v; asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
 // 16-byte record through the read-only path in one LDG.128
 template <class T> AFF_DEV T ldg_pair(const T* p)
 {
