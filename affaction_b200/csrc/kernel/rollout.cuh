@@ -898,13 +898,22 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
         const double lim = need + (bS + bB) + cullMargin;
         if (!(cd2 >= lim * lim)) {
           on = true;
-          double F[12], ext[3]; int typeB;
-          if (pr.b >= 0) { const double* B = shp + 12 * pr.b; for (int e = 0; e < 12; ++e) F[e] = B[e]; const KShape* sb = P.dshape + pr.b; typeB = ldg(&sb->type); for (int k = 0; k < 3; ++k) ext[k] = ldg(&sb->ext[k]); }
-          else { const int si = -1 - pr.b; for (int e = 0; e < 12; ++e) F[e] = ldg(&P.sshapeA[12 * si + e]); const KShape* sb = P.sshape + si; typeB = ldg(&sb->type); for (int k = 0; k < 3; ++k) ext[k] = ldg(&sb->ext[k]); }
+          // segment into the box / cylinder frame, one row of the frame at a time (few live registers)
+          const bool dynB = pr.b >= 0;
+          const double* Bs = shp + 12 * (dynB ? pr.b : 0);
+          const double* Bg = P.sshapeA + 12 * (dynB ? 0 : -1 - pr.b);
+          const KShape* sb = dynB ? P.dshape + pr.b : P.sshape + (-1 - pr.b);
           double rel[3], pl[3], dl[3];
-          for (int k = 0; k < 3; ++k) rel[k] = pS[k] - F[k];
-          k_mulv(pl, F + 3, rel);
-          k_mulv(dl, F + 3, dS);
+          for (int k = 0; k < 3; ++k) rel[k] = pS[k] - (dynB ? Bs[k] : ldg(&Bg[k]));
+          for (int i = 0; i < 3; ++i) {
+            const double r0 = dynB ? Bs[3 + 3 * i] : ldg(&Bg[3 + 3 * i]), r1 = dynB ? Bs[4 + 3 * i] : ldg(&Bg[4 + 3 * i]),
+                         r2 = dynB ? Bs[5 + 3 * i] : ldg(&Bg[5 + 3 * i]);
+            pl[i] = fma(r2, rel[2], fma(r1, rel[1], r0 * rel[0]));
+            dl[i] = fma(r2, dS[2], fma(r1, dS[1], r0 * dS[0]));
+          }
+          const int typeB = ldg(&sb->type);
+          double ext[3];
+          for (int k = 0; k < 3; ++k) ext[k] = ldg(&sb->ext[k]);
           if (typeB == AFF_SHAPE_BOX) { const double h[3] = {0.5 * ext[0], 0.5 * ext[1], 0.5 * ext[2]}; d = k_seg_box(pl, dl, h) - rS; }
           else d = k_seg_cyl(pl, dl, 0.5 * ext[2], ext[0]) - rS;
         }
@@ -966,7 +975,8 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
   const int lane = c.lane, nJ = P.nJ;
   const double dt = P.opts.dt;
   const int nTasks = ldg(&C.n_tasks), xdim = ldg(&C.xdim);
-  const KTask* tasks = P.tasks + ldg(&C.first_task);
+  const int taskBase = ldg(&C.first_task);
+#define tasks (P.tasks + taskBase)
   double* q = sm + P.o_q; double* qdot = sm + P.o_qdot; double* vbuf = sm + P.o_dH; double* wbuf = sm + P.o_dq;
   double* J = sm + P.o_J; double* L = sm + P.o_L; double* rhs = sm + P.o_rhs; double* dxv = sm + P.o_dx;
   double* st = sm + P.o_st; double* xdes = sm + P.o_xdes; double* xcur = sm + P.o_xcur; double* geo = sm + P.o_geo;
@@ -1001,14 +1011,18 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
   // task of this lane's dimension
   int myTask = -1;
   if (lane < xdim) for (int t = 0; t < nTasks; ++t) if (lane >= ldg(&tasks[t].xoff)) myTask = t;
-  int viaHead = 0, viaEnd = 0;
-  if (lane < xdim) { viaHead = ldg(&C.via_off[lane]); viaEnd = ldg(&C.via_off[lane + 1]); }
-  const KVia* vias = P.vias + ldg(&C.first_via);
-  int actHead = 0, actEnd = 0, myActive = 0;
-  double lastSwitchT = 0.0, lastSwitchH = -1.0;
-  if (lane < nTasks) { actHead = ldg(&C.act_off[lane]); actEnd = ldg(&C.act_off[lane + 1]); }
-  const KAct* acts = P.acts + ldg(&C.first_act);
-  const KGraphCon* gcons = P.gcons + ldg(&C.first_gcon);
+  int viaHead = 0;      // the ends are re-read from the candidate record where needed
+  // heads and ends are absolute indices into P.vias / P.acts: the table bases come from the constant bank
+  if (lane < xdim) viaHead = ldg(&C.first_via) + ldg(&C.via_off[lane]);
+#define viaEnd (ldg(&C.first_via) + ldg(&C.via_off[(lane < xdim ? lane : 0) + 1]))
+#define vias P.vias
+  int actHead = 0;      // last switch time / horizon / state are those of acts[actHead - 1]
+  if (lane < nTasks) actHead = ldg(&C.first_act) + ldg(&C.act_off[lane]);
+#define actBeginOf(t) (ldg(&C.first_act) + ldg(&C.act_off[t]))
+#define actEndOf(t) (ldg(&C.first_act) + ldg(&C.act_off[(t) + 1]))
+#define acts P.acts
+  const int gconBase = ldg(&C.first_gcon);
+#define gcons (P.gcons + gconBase)
   const int nGcon = ldg(&C.n_gcon);
   unsigned gfired = 0u;
 
@@ -1095,7 +1109,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
     // ---- tc->step(dt): trajectories.  The state of an inactive task's trajectory is overwritten at
     // the start of the next step unless the task switches on in this one, so only then is it computed.
     const double tnext = tnow + dt;
-    const int ah = w_shfl(actHead, myTask < 0 ? 0 : myTask), ae = w_shfl(actEnd, myTask < 0 ? 0 : myTask);
+    const int ah = w_shfl(actHead, myTask < 0 ? 0 : myTask), ae = actEndOf(myTask < 0 ? 0 : myTask);
     // eight dimensions at a time: the solver scratch (via_stride doubles per lane) is the largest
     // user of the shared union region
     for (int batch = 0; batch < xdim; batch += AFFK_VIA_LANES) {
@@ -1158,13 +1172,12 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
       }
     }
     // activation points
+    int myActive = (activeMask >> lane) & 1u;
     if (lane < nTasks) {
-      while (actHead < actEnd && ldg(&acts[actHead].t) - tnow < AFFK_TRAJ_EPS) {
-        myActive = ldg(&acts[actHead].on); lastSwitchT = ldg(&acts[actHead].t); lastSwitchH = ldg(&acts[actHead].horizon);
-        ++actHead;
-      }
+      const int actEnd = actEndOf(lane);
+      while (actHead < actEnd && ldg(&acts[actHead].t) - tnow < AFFK_TRAJ_EPS) { myActive = ldg(&acts[actHead].on); ++actHead; }
     }
-    if (lane < xdim) while (viaHead < viaEnd && ldg(&vias[viaHead].t) - tnow < AFFK_TRAJ_EPS) ++viaHead;
+    if (lane < xdim) { const int ve = viaEnd; while (viaHead < ve && ldg(&vias[viaHead].t) - tnow < AFFK_TRAJ_EPS) ++viaHead; }
     prevMask = activeMask;
     activeMask = w_ballot(lane < nTasks && myActive);
     {
@@ -1174,8 +1187,11 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
     // blending
     double bl = 1.0;
     if (lane < nTasks) {
-      if (actHead < actEnd) { const double h = ldg(&acts[actHead].horizon); if (h > 0.0) bl = k_clip((ldg(&acts[actHead].t) - tnow) / h, 0.0, 1.0); }
-      if (lastSwitchH > 0.0) { const double up = k_clip((tnow - lastSwitchT) / lastSwitchH, 0.0, 1.0); if (up < bl) bl = up; }
+      if (actHead < actEndOf(lane)) { const double h = ldg(&acts[actHead].horizon); if (h > 0.0) bl = k_clip((ldg(&acts[actHead].t) - tnow) / h, 0.0, 1.0); }
+      if (actHead > actBeginOf(lane)) {
+        const double lastSwitchT = ldg(&acts[actHead - 1].t), lastSwitchH = ldg(&acts[actHead - 1].horizon);
+        if (lastSwitchH > 0.0) { const double up = k_clip((tnow - lastSwitchT) / lastSwitchH, 0.0, 1.0); if (up < bl) bl = up; }
+      }
     }
     double blending = w_ballot(bl < 1.0) ? w_min(bl) : 1.0;
     if (activeMask == 0u) blending = 0.0;
@@ -1428,6 +1444,13 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
     P.results[cand] = res;
   }
 }
+#undef viaEnd
+#undef actBeginOf
+#undef actEndOf
+#undef vias
+#undef acts
+#undef gcons
+#undef tasks
 #undef jq0
 #undef jqmin
 #undef jqmax
