@@ -73,7 +73,7 @@ template <class T> struct DevBuf
   cudaError_t upload(const std::vector<T>& v, cudaStream_t s)
   {
     n = v.size();
-    cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(1, n) * sizeof(T));
+    cudaError_t e = cudaMallocAsync((void**)&p, std::max<size_t>(1, n) * sizeof(T), s);
     if (e != cudaSuccess) return e;
     if (n) e = cudaMemcpyAsync(p, v.data(), n * sizeof(T), cudaMemcpyHostToDevice, s);
     return e;
@@ -81,9 +81,11 @@ template <class T> struct DevBuf
   cudaError_t alloc(size_t count)
   {
     n = count;
-    return cudaMalloc((void**)&p, std::max<size_t>(1, n) * sizeof(T));
+    return cudaMallocAsync((void**)&p, std::max<size_t>(1, n) * sizeof(T), 0);
   }
-  void release() { if (p) cudaFree(p); p = nullptr; }
+  // Stream-ordered allocations from the device's default memory pool (kept, not returned to the driver:
+  // see aff_scene_create), so that a predict call per action does not pay cudaMalloc / cudaFree each time.
+  void release() { if (p) cudaFreeAsync(p, 0); p = nullptr; }
 };
 
 struct aff_batch
@@ -106,6 +108,7 @@ struct aff_batch
   int grid = 0; size_t smemBytes = 0; int launches = 0;
   size_t h2dBytes = 0;
   bool prologueDone = false;
+  cudaStream_t lastStream = nullptr; bool launched = false;
   void release()
   {
     jq_init.release(); jq0.release(); jq_min.release(); jq_max.release(); jspeed.release(); jacc.release(); jwjl.release();
@@ -148,6 +151,12 @@ int aff_scene_create(const aff_scene_desc* desc, int device, aff_scene** out)
     delete s;
     return fail(AFF_ERR_CUDA, "aff_scene_create: cannot query the device");
   }
+  {
+    cudaMemPool_t pool;
+    unsigned long long keep = ~0ull;
+    if (cudaSetDevice(device) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   const std::string e = s->model.init(desc);
   if (!e.empty()) { delete s; return fail(AFF_ERR_INVALID, "aff_scene_create: " + e); }
   *out = s;
@@ -179,6 +188,8 @@ static int uploadBatch(aff_batch* b, cudaStream_t st)
   if (P.opts.log_q) {
     P.qlog_rows = H.maxSteps + 1;
     CUDA_TRY(b->qlog.alloc((size_t)P.nCands * P.qlog_rows * P.nJ));
+    // rows a rollout never reaches (initial state invalid) read as zero
+    CUDA_TRY(cudaMemsetAsync(b->qlog.p, 0, sizeof(double) * (size_t)P.nCands * P.qlog_rows * P.nJ, st));
     P.qlog = b->qlog.p;
   }
   P.jq_init = b->jq_init.p; P.jq0 = b->jq0.p; P.jq_min = b->jq_min.p; P.jq_max = b->jq_max.p; P.jspeed = b->jspeed.p;
@@ -234,6 +245,8 @@ int aff_batch_create(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, c
 void aff_batch_destroy(aff_batch* b)
 {
   if (!b) return;
+  // the buffers go back to the pool in stream order of the default stream: wait for the stream that used them
+  if (b->launched) cudaStreamSynchronize(b->lastStream);
   b->release();
   delete b;
 }
@@ -244,6 +257,7 @@ int aff_batch_launch(aff_batch* b, void* stream)
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(cudaSetDevice(b->scene->device));
   b->launches = 0;
+  b->lastStream = st; b->launched = true;
   if (!b->prologueDone) {
     aff_prologue_kernel<<<1, 32, 0, st>>>(b->plan);
     CUDA_TRY(cudaGetLastError());
