@@ -228,6 +228,50 @@ AFF_DEV void k_via_step(double* st, const KVia* vias, int n, double tnow, double
   const double T = ldg(&vias[nwin - 1].t) - tnow;
   const double c0 = st[0], c1 = st[1] * T, c2 = (0.5 * st[2]) * (T * T);
   const int S = K + 1;
+  double* sol = A + maxUnk * (maxUnk + 1);   // maxUnk doubles after the matrix
+  if (K == 3 && nwin == 1) {
+    // The common window: one full constraint, at tau = (t - tnow) / T = 1 exactly.  The system matrix
+    // is then the constant {1 1 1; 3 4 5; 6 12 20}: the same elimination as below, written on a local
+    // array so that the compiler folds the pivoting and the multipliers; only the right-hand side is
+    // computed at run time, with the operations and their order unchanged.
+    const double tau = 1.0, pw1 = 1.0 * tau, pw2 = pw1 * tau;
+    double M[3][4];
+    { double p = pw2; for (int k = 0; k < 3; ++k) { p = p * tau; M[0][k] = p; } }
+    { double p = pw1; for (int k = 0; k < 3; ++k) { p = p * tau; M[1][k] = (double)(k + 3) * p; } }
+    { double p = 1.0; for (int k = 0; k < 3; ++k) { p = p * tau; M[2][k] = (double)((k + 3) * (k + 2)) * p; } }
+    M[0][3] = ldg(&vias[0].x) - fma(c2, pw2, fma(c1, tau, c0));
+    M[1][3] = ldg(&vias[0].xd) * T - fma(2.0 * c2, tau, c1);
+    M[2][3] = ldg(&vias[0].xdd) * (T * T) - 2.0 * c2;
+#pragma unroll
+    for (int cI = 0; cI < 3; ++cI) {
+      int piv = cI;
+      double best = fabs(M[cI][cI]);
+#pragma unroll
+      for (int r = cI + 1; r < 3; ++r) { const double v = fabs(M[r][cI]); if (v > best) { best = v; piv = r; } }
+#pragma unroll
+      for (int r = cI + 1; r < 3; ++r)
+        if (piv == r) {
+#pragma unroll
+          for (int k = cI; k < 4; ++k) { const double tmp = M[cI][k]; M[cI][k] = M[r][k]; M[r][k] = tmp; }
+        }
+      const double p = M[cI][cI];
+#pragma unroll
+      for (int r = cI + 1; r < 3; ++r) {
+        const double f = M[r][cI] / p;
+#pragma unroll
+        for (int k = cI + 1; k < 4; ++k) M[r][k] = fma(-f, M[cI][k], M[r][k]);
+      }
+    }
+    double sl[3];
+#pragma unroll
+    for (int r = 2; r >= 0; --r) {
+      double sacc = M[r][3];
+#pragma unroll
+      for (int k = r + 1; k < 3; ++k) sacc = fma(-M[r][k], sl[k], sacc);
+      sl[r] = sacc / M[r][r];
+    }
+    sol[0] = sl[0]; sol[1] = sl[1]; sol[2] = sl[2];
+  } else {
   int row = 0;
   for (int i = 0; i < nwin; ++i) {
     const int flag = ldg(&vias[i].flag);
@@ -265,12 +309,12 @@ AFF_DEV void k_via_step(double* st, const KVia* vias, int n, double tnow, double
       for (int k = cI + 1; k < S; ++k) A[r * S + k] = fma(-f, A[cI * S + k], A[r * S + k]);
     }
   }
-  double* sol = A + maxUnk * (maxUnk + 1);   // maxUnk doubles after the matrix
   for (int r = K - 1; r >= 0; --r) {
     double sacc = A[r * S + K];
     for (int k = r + 1; k < K; ++k) sacc = fma(-A[r * S + k], sol[k], sacc);
     const double p = A[r * S + r];
     sol[r] = (p != 0.0) ? sacc / p : 0.0;
+  }
   }
   const double s = (dt < T) ? dt / T : 1.0;
   double p = 0.0, pd = 0.0, pdd = 0.0;
