@@ -15,7 +15,19 @@
 
 #include "affpredict.h"
 #include "kernel/plan_build.h"
+#include "aff_detmath.h"
+#include "kernel/plan.h"
+#include "kernel/warp.cuh"
+// The kernel source twice (see the head of rollout.cuh): offsets read from the plan, and the fixed layout
+// with compile-time offsets that the plan compiler picks for every batch within its caps.
+namespace kgeneric {
 #include "kernel/rollout.cuh"
+}
+#define AFFK_FIXED_LAYOUT 1
+namespace kfixed {
+#include "kernel/rollout.cuh"
+}
+#undef AFFK_FIXED_LAYOUT
 
 #ifndef AFF_WARPS_PER_BLOCK
 #define AFF_WARPS_PER_BLOCK 4
@@ -31,21 +43,24 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 // ------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(32) aff_prologue_kernel(const KPlan P)
 {
-  k_prologue(P);
+  kgeneric::k_prologue(P);
 }
 
 // Persistent rollout kernel: one warp per candidate, warps stride over the batch.
-__global__ void __launch_bounds__(32 * AFF_WARPS_PER_BLOCK, AFF_BLOCKS_PER_SM) aff_rollout_kernel(const KPlan P)
-{
-  extern __shared__ double smem[];
-  const int warp = threadIdx.x >> 5;
-  double* sm = smem + (size_t)warp * P.warp_doubles;
-  const int warpsTotal = gridDim.x * AFF_WARPS_PER_BLOCK;
-  for (int cand = blockIdx.x * AFF_WARPS_PER_BLOCK + warp; cand < P.nCands; cand += warpsTotal) {
-    k_rollout(P, cand, sm);
-    __syncwarp();
+#define AFF_ROLLOUT_KERNEL(NAME, NS)                                                                                       \
+  __global__ void __launch_bounds__(32 * AFF_WARPS_PER_BLOCK, AFF_BLOCKS_PER_SM) NAME(const KPlan P)                      \
+  {                                                                                                                      \
+    extern __shared__ double smem[];                                                                                     \
+    const int warp = threadIdx.x >> 5;                                                                                   \
+    double* sm = smem + (size_t)warp * P.warp_doubles;                                                                   \
+    const int warpsTotal = gridDim.x * AFF_WARPS_PER_BLOCK;                                                              \
+    for (int cand = blockIdx.x * AFF_WARPS_PER_BLOCK + warp; cand < P.nCands; cand += warpsTotal) {                      \
+      NS::k_rollout(P, cand, sm);                                                                                        \
+      __syncwarp();                                                                                                      \
+    }                                                                                                                    \
   }
-}
+AFF_ROLLOUT_KERNEL(aff_rollout_kernel, kfixed)            // batches in the fixed layout (KPlan::fixed_layout)
+AFF_ROLLOUT_KERNEL(aff_rollout_kernel_generic, kgeneric)  // anything larger
 
 // Register-resident DFMA chains: the FP64 roofline denominator.
 __global__ void aff_dfma_peak_kernel(double* out, int iters)
@@ -107,7 +122,7 @@ struct aff_batch
   DevBuf<aff_result> results;
   int grid = 0; size_t smemBytes = 0; int launches = 0;
   size_t h2dBytes = 0;
-  bool prologueDone = false;
+  bool prologueDone = false, useFixed = false;
   cudaStream_t lastStream = nullptr; bool launched = false;
   void release()
   {
@@ -230,10 +245,13 @@ int aff_batch_create(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, c
   // tuning experiments only (tools/try_variants.sh): extra dynamic shared memory per block, preferred carve-out in percent
   if (const char* pad = getenv("AFF_TUNE_SMEM_PAD")) b->smemBytes += (size_t)atoi(pad);
   if (b->smemBytes > (size_t)s->smemOptin) { b->release(); delete b; return fail(AFF_ERR_CAPACITY, "aff_batch_create: rollout state does not fit in shared memory"); }
-  CUDA_TRY(cudaFuncSetAttribute(aff_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smemBytes));
-  if (const char* co = getenv("AFF_TUNE_CARVEOUT")) CUDA_TRY(cudaFuncSetAttribute(aff_rollout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co)));
+  // AFF_TUNE_GENERIC_KERNEL: run the generic kernel on a fixed-layout plan too (A/B of the two builds)
+  b->useFixed = b->plan.fixed_layout != 0 && !getenv("AFF_TUNE_GENERIC_KERNEL");
+  const void* kfn = b->useFixed ? (const void*)aff_rollout_kernel : (const void*)aff_rollout_kernel_generic;
+  CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smemBytes));
+  if (const char* co = getenv("AFF_TUNE_CARVEOUT")) CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co)));
   int perSM = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, aff_rollout_kernel, 32 * AFF_WARPS_PER_BLOCK, b->smemBytes));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kfn, 32 * AFF_WARPS_PER_BLOCK, b->smemBytes));
   if (perSM < 1) perSM = 1;
   const int blocksNeeded = (int)((n_cands + AFF_WARPS_PER_BLOCK - 1) / AFF_WARPS_PER_BLOCK);
   b->grid = std::max(1, std::min(blocksNeeded, perSM * s->smCount));
@@ -264,7 +282,8 @@ int aff_batch_launch(aff_batch* b, void* stream)
     b->prologueDone = true;
     b->launches++;
   }
-  aff_rollout_kernel<<<b->grid, 32 * AFF_WARPS_PER_BLOCK, b->smemBytes, st>>>(b->plan);
+  if (b->useFixed) aff_rollout_kernel<<<b->grid, 32 * AFF_WARPS_PER_BLOCK, b->smemBytes, st>>>(b->plan);
+  else aff_rollout_kernel_generic<<<b->grid, 32 * AFF_WARPS_PER_BLOCK, b->smemBytes, st>>>(b->plan);
   CUDA_TRY(cudaGetLastError());
   b->launches++;
   return AFF_OK;

@@ -117,6 +117,31 @@ struct KCand
   double end_abs, start_abs;
 };
 
+// Fixed shared-memory layout (doubles) for batches within these caps: every region except the node
+// array starts at a compile-time offset and J / L have compile-time strides, so the kernel compiled
+// with AFFK_FIXED_LAYOUT needs no address arithmetic per access.  buildPlan() writes the same numbers
+// into KPlan, so the generic kernel (and the test emulator) run the identical layout.
+#define AFFK_FIX_NJ 24         // IK joints
+#define AFFK_FIX_XDIM 14       // task dimensions
+#define AFFK_FIX_TASKS 8
+#define AFFK_FIX_SLOTS 48      // node slots
+#define AFFK_FIX_DSHAPE 20
+#define AFFK_FIX_DBODY 16
+#define AFFK_FIX_TREES 4
+#define AFFK_FIX_JS 25
+#define AFFK_FIX_LS 15
+enum {
+  AFFK_FIX_o_q = 0, AFFK_FIX_o_qdot = 24, AFFK_FIX_o_dH = 48, AFFK_FIX_o_dq = 72, AFFK_FIX_o_sn = 96, AFFK_FIX_o_cs = 120,
+  AFFK_FIX_o_dx = 144, AFFK_FIX_o_st = 158, AFFK_FIX_o_xdes = 200, AFFK_FIX_o_xcur = 214,
+  AFFK_FIX_o_geo = 228, AFFK_FIX_o_objrel = 324, AFFK_FIX_o_objq6 = 348, AFFK_FIX_o_chain = 360,
+  AFFK_FIX_o_tdesc = 386, AFFK_FIX_o_rmask = 418,
+  AFFK_FIX_o_scratch = 426,                       // union: trajectory solver | J, L, rhs | collision scratch
+  AFFK_FIX_o_J = AFFK_FIX_o_scratch, AFFK_FIX_o_L = AFFK_FIX_o_J + AFFK_FIX_XDIM * AFFK_FIX_JS,
+  AFFK_FIX_o_rhs = AFFK_FIX_o_L + AFFK_FIX_XDIM * AFFK_FIX_LS, AFFK_FIX_IK_END = AFFK_FIX_o_rhs + AFFK_FIX_XDIM,
+  AFFK_FIX_o_shp = AFFK_FIX_o_scratch, AFFK_FIX_o_baabb = AFFK_FIX_o_shp + 12 * AFFK_FIX_DSHAPE,
+  AFFK_FIX_o_taabb = AFFK_FIX_o_baabb + 6 * AFFK_FIX_DBODY, AFFK_FIX_o_live = AFFK_FIX_o_taabb + 6 * AFFK_FIX_TREES
+};
+
 // Everything the kernels need, passed by value.
 struct KPlan
 {
@@ -165,6 +190,7 @@ struct KPlan
   int32_t o_node, o_q, o_qdot, o_dH, o_dq, o_sn, o_cs, o_J, o_L, o_rhs, o_dx, o_st, o_xdes, o_xcur, o_geo,
           o_objrel, o_objq6, o_shp, o_baabb, o_taabb, o_scratch, o_live, o_chain, o_tdesc, o_rmask, warp_doubles;
   int32_t JS, LS;
+  int32_t fixed_layout;            // 1: the offsets below are the AFFK_FIX_* constants (node array after the union)
   int32_t via_unk, via_stride;     // largest trajectory window of the batch (constrained values); solver scratch per lane (odd)                  // row strides of J and L (odd: conflict-free column access)
 
   aff_opts opts;

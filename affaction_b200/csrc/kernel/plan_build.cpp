@@ -558,9 +558,32 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   auto take = [&](int n) { const int at = o; o += n; return at; };
   P.nStatPar = (int)H.statpar_ref.size();
   if (P.nDyn + P.nStatPar > 250) { err = "too many FK node slots"; return AFF_ERR_CAPACITY; }
-  P.o_node = take(12 * std::max(P.nDyn + P.nStatPar, 1));
   int maxTasks = 1;
   for (const KCand& kc : H.cands) maxTasks = std::max(maxTasks, kc.n_tasks);
+  const int nSlots = std::max(P.nDyn + P.nStatPar, 1);
+  P.via_unk = std::max(maxViaUnk, 1);
+  P.via_stride = (P.via_unk * (P.via_unk + 1) + P.via_unk) | 1;   // matrix + solution, odd stride
+  const int uTraj = P.via_stride * std::min(std::max(H.maxXdim, 1), AFFK_VIA_LANES);
+  // live list (2*MAX_NEAR ints) + body trees (MAX_DBODY ints) + costly-pair scratch (32 ints + 32 doubles)
+  const int collTail = AFFK_MAX_NEAR + AFFK_MAX_DBODY / 2 + 16 + 32;
+  P.fixed_layout = (S.nJ <= AFFK_FIX_NJ && H.maxXdim <= AFFK_FIX_XDIM && maxTasks <= AFFK_FIX_TASKS && nSlots <= AFFK_FIX_SLOTS &&
+                    P.nDynShapes <= AFFK_FIX_DSHAPE && P.nDynBodies <= AFFK_FIX_DBODY && P.nTrees <= AFFK_FIX_TREES &&
+                    !getenv("AFF_TUNE_GENERIC_LAYOUT")) ? 1 : 0;
+  if (P.fixed_layout) {
+    // the compile-time layout of plan.h; only the node array (after the union) starts at a run-time offset
+    P.o_q = AFFK_FIX_o_q; P.o_qdot = AFFK_FIX_o_qdot; P.o_dH = AFFK_FIX_o_dH; P.o_dq = AFFK_FIX_o_dq; P.o_sn = AFFK_FIX_o_sn; P.o_cs = AFFK_FIX_o_cs;
+    P.o_dx = AFFK_FIX_o_dx; P.o_st = AFFK_FIX_o_st; P.o_xdes = AFFK_FIX_o_xdes; P.o_xcur = AFFK_FIX_o_xcur; P.o_geo = AFFK_FIX_o_geo;
+    P.o_objrel = AFFK_FIX_o_objrel; P.o_objq6 = AFFK_FIX_o_objq6; P.o_chain = AFFK_FIX_o_chain; P.o_tdesc = AFFK_FIX_o_tdesc; P.o_rmask = AFFK_FIX_o_rmask;
+    P.o_scratch = AFFK_FIX_o_scratch; P.o_J = AFFK_FIX_o_J; P.o_L = AFFK_FIX_o_L; P.o_rhs = AFFK_FIX_o_rhs;
+    P.o_shp = AFFK_FIX_o_shp; P.o_baabb = AFFK_FIX_o_baabb; P.o_taabb = AFFK_FIX_o_taabb; P.o_live = AFFK_FIX_o_live;
+    P.JS = AFFK_FIX_JS; P.LS = AFFK_FIX_LS;
+    const int uIk = AFFK_FIX_IK_END - AFFK_FIX_o_scratch, uColl = AFFK_FIX_o_live + collTail - AFFK_FIX_o_scratch;
+    P.o_node = AFFK_FIX_o_scratch + std::max(uTraj, std::max(uIk, uColl));
+    P.warp_doubles = (P.o_node + 12 * nSlots + 1) & ~1;
+    H.smemBytesPerWarp = sizeof(double) * (size_t)P.warp_doubles;
+    return AFF_OK;
+  }
+  P.o_node = take(12 * nSlots);
   const int nJe = (S.nJ + 1) & ~1, xde = (std::max(H.maxXdim, 1) + 1) & ~1;
   P.o_q = take(nJe); P.o_qdot = take(nJe); P.o_dH = take(nJe); P.o_dq = take(nJe); P.o_sn = take(nJe); P.o_cs = take(nJe);
   P.o_dx = take(xde);
@@ -574,13 +597,9 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   // union region: trajectory solver scratch | J, L, rhs | collision scratch
   const int uBase = o;
   P.JS = (S.nJ | 1); P.LS = (H.maxXdim | 1);
-  P.via_unk = std::max(maxViaUnk, 1);
-  P.via_stride = (P.via_unk * (P.via_unk + 1) + P.via_unk) | 1;   // matrix + solution, odd stride
-  const int uTraj = P.via_stride * std::min(std::max(H.maxXdim, 1), AFFK_VIA_LANES);
   const int mRows = std::max(H.maxXdim, 1);
   const int uIk = mRows * P.JS + mRows * P.LS + mRows;
-  // live list (2*MAX_NEAR ints) + body trees (MAX_DBODY ints) + costly-pair scratch (32 ints + 32 doubles)
-  const int uColl = 12 * std::max(P.nDynShapes, 1) + 6 * std::max(P.nDynBodies, 1) + 6 * std::max(P.nTrees, 1) + AFFK_MAX_NEAR + AFFK_MAX_DBODY / 2 + 16 + 32;
+  const int uColl = 12 * std::max(P.nDynShapes, 1) + 6 * std::max(P.nDynBodies, 1) + 6 * std::max(P.nTrees, 1) + collTail;
   P.o_scratch = uBase;
   P.o_J = uBase; P.o_L = uBase + mRows * P.JS; P.o_rhs = P.o_L + mRows * P.LS;
   P.o_shp = uBase; P.o_baabb = P.o_shp + 12 * std::max(P.nDynShapes, 1); P.o_taabb = P.o_baabb + 6 * std::max(P.nDynBodies, 1);

@@ -15,15 +15,31 @@
 // (explicit fma(), compiled with -fmad=false), and the few reductions over
 // lanes are order-independent (min / max / ballot) or use the fixed butterfly
 // order of w_tree_sum(), so results are reproducible bit for bit.
-#ifndef AFF_KERNEL_ROLLOUT_CUH
-#define AFF_KERNEL_ROLLOUT_CUH
-
+//
+// This file may be included twice, inside two namespaces: once as is (every shared-memory offset
+// and matrix stride is read from the plan) and once with AFFK_FIXED_LAYOUT defined (offsets and
+// strides of plan.h's fixed layout are compile-time constants: no address arithmetic per access).
+// The host compiler of plans uses the fixed layout whenever a batch fits its caps, so both kernels
+// see the same numbers in KPlan.
 #include <float.h>
 #include <math.h>
 
 #include "aff_detmath.h"
 #include "plan.h"
 #include "warp.cuh"
+
+#undef AFFK_O
+#undef AFFK_JS
+#undef AFFK_LS
+#if defined(AFFK_FIXED_LAYOUT)
+#define AFFK_O(P, name) ((int)AFFK_FIX_o_##name)
+#define AFFK_JS(P) ((int)AFFK_FIX_JS)
+#define AFFK_LS(P) ((int)AFFK_FIX_LS)
+#else
+#define AFFK_O(P, name) ((P).o_##name)
+#define AFFK_JS(P) ((P).JS)
+#define AFFK_LS(P) ((P).LS)
+#endif
 
 #define AFFK_TRACK_MAX 0.05      // MAX_TRACKING_ERROR, src/TrajectoryPredictor.cpp:50
 #define AFFK_TRAJ_EPS 1.0e-8
@@ -159,8 +175,8 @@ AFF_DEV void k_object_from_q6(const KCtx& c, int n, int slot)
 AFF_DEV void k_fk(const KCtx& c, bool init)
 {
   const KPlan& P = *c.P;
-  double* sn = c.sm + P.o_sn; double* cs = c.sm + P.o_cs;
-  const double* q = c.sm + P.o_q;
+  double* sn = c.sm + AFFK_O(P, sn); double* cs = c.sm + AFFK_O(P, cs);
+  const double* q = c.sm + AFFK_O(P, q);
   double* nodes = c.nodes;
   const int lane = c.lane;
   if (lane < P.nJ) { double s, co; aff_sincos(q[lane], &s, &co); sn[lane] = s; cs[lane] = co; }
@@ -188,7 +204,7 @@ AFF_DEV void k_fk(const KCtx& c, bool init)
       const int slot = (int)(en.w1 & 3u), n = (int)((en.w1 >> 8) & 255u);
       if ((c.objHasRel >> slot) & 1u) {
         const double* Pp = nodes + 12 * OBJ_GET(c, objParentSlot, slot);
-        const double* R = c.sm + P.o_objrel + 12 * slot;
+        const double* R = c.sm + AFFK_O(P, objrel) + 12 * slot;
         const int col = (e < 3) ? e : (e - 3) % 3, tb = (e < 3) ? 0 : 3 + 3 * ((e - 3) / 3);
         const double acc0 = (e < 3) ? Pp[e] : 0.0;
         val = fma(R[tb + 2], Pp[9 + col], fma(R[tb + 1], Pp[6 + col], fma(R[tb], Pp[3 + col], acc0)));
@@ -689,7 +705,7 @@ AFF_DEV double k_pair_distance(const KCtx& c, int ia, int ib)
   const KPlan& P = *c.P;
   const KShapeBody* ba = P.dbody + ia;
   const int fa = ldg(&ba->first_shape), na = ldg(&ba->n_shapes), sa = ldg(&ba->toggle_slot);
-  const double* shp = c.sm + P.o_shp;
+  const double* shp = c.sm + AFFK_O(P, shp);
   double dmin = DBL_MAX;
   for (int k1 = 0; k1 < na; ++k1) {
     const KShape* s1 = P.dshape + fa + k1;
@@ -792,10 +808,10 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
   const KPlan& P = *c.P;
   const int lane = c.lane;
   const double thr = P.bp_threshold;
-  double* shp = c.sm + P.o_shp;
-  double* baabb = c.sm + P.o_baabb;
-  double* taabb = c.sm + P.o_taabb;
-  int* live = (int*)(c.sm + P.o_live);             // AABB-found pairs: [2*i] = dyn body a, [2*i+1] = other
+  double* shp = c.sm + AFFK_O(P, shp);
+  double* baabb = c.sm + AFFK_O(P, baabb);
+  double* taabb = c.sm + AFFK_O(P, taabb);
+  int* live = (int*)(c.sm + AFFK_O(P, live));             // AABB-found pairs: [2*i] = dyn body a, [2*i+1] = other
   int* btree = live + 2 * AFFK_MAX_NEAR;           // tree of each dynamic body, -1 none, -2 inactive
   int* ckey = btree + AFFK_MAX_DBODY;              // scratch: pairs closer than the threshold
   double* cdist = (double*)(ckey + 32);
@@ -1013,19 +1029,19 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
   KCtx c;
   c.P = &P; c.C = P.cands + cand; c.sm = sm; c.lane = w_lane();
   c.nodes = sm + P.o_node;
-  c.chain = (unsigned*)(sm + P.o_chain);
-  c.tdesc = (int*)(sm + P.o_tdesc);
+  c.chain = (unsigned*)(sm + AFFK_O(P, chain));
+  c.tdesc = (int*)(sm + AFFK_O(P, tdesc));
   const KCand& C = *c.C;
   const int lane = c.lane, nJ = P.nJ;
   const double dt = P.opts.dt;
   const int nTasks = ldg(&C.n_tasks), xdim = ldg(&C.xdim);
   const int taskBase = ldg(&C.first_task);
 #define tasks (P.tasks + taskBase)
-  double* q = sm + P.o_q; double* qdot = sm + P.o_qdot; double* vbuf = sm + P.o_dH; double* wbuf = sm + P.o_dq;
-  double* J = sm + P.o_J; double* L = sm + P.o_L; double* rhs = sm + P.o_rhs; double* dxv = sm + P.o_dx;
-  double* st = sm + P.o_st; double* xdes = sm + P.o_xdes; double* xcur = sm + P.o_xcur; double* geo = sm + P.o_geo;
-  unsigned* rmask = (unsigned*)(sm + P.o_rmask);
-  const int JS = P.JS, LS = P.LS;
+  double* q = sm + AFFK_O(P, q); double* qdot = sm + AFFK_O(P, qdot); double* vbuf = sm + AFFK_O(P, dH); double* wbuf = sm + AFFK_O(P, dq);
+  double* J = sm + AFFK_O(P, J); double* L = sm + AFFK_O(P, L); double* rhs = sm + AFFK_O(P, rhs); double* dxv = sm + AFFK_O(P, dx);
+  double* st = sm + AFFK_O(P, st); double* xdes = sm + AFFK_O(P, xdes); double* xcur = sm + AFFK_O(P, xcur); double* geo = sm + AFFK_O(P, geo);
+  unsigned* rmask = (unsigned*)(sm + AFFK_O(P, rmask));
+  const int JS = AFFK_JS(P), LS = AFFK_LS(P);
   const int nSlots = P.nDyn + P.nStatPar;
 
   // ---- per-lane constants
@@ -1094,7 +1110,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
   for (int i = lane; i < P.nDyn; i += 32) { const int uo = ldg(&P.dyn_under[i]); if (uo) c.chain[i] = ldg(&P.dyn_chain[i]) | OBJ_GET(c, objChain, uo - 1); }
   if (lane < 6) {
     for (int s = 0; s < P.nObj; ++s)
-      sm[P.o_objq6 + 6 * s + lane] = (ldg(&C.pose_slot) == s) ? ldg(&C.pose_q6[lane]) : ldg(&P.obj_q6[6 * s + lane]);
+      sm[AFFK_O(P, objq6) + 6 * s + lane] = (ldg(&C.pose_slot) == s) ? ldg(&C.pose_q6[lane]) : ldg(&P.obj_q6[6 * s + lane]);
   }
   if (lane < xdim) { st[3 * lane] = 0.0; st[3 * lane + 1] = 0.0; st[3 * lane + 2] = 0.0; xdes[lane] = 0.0; }
   w_sync();
@@ -1166,7 +1182,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
           double s3[3];
           if (!active) { s3[0] = xcur[lane]; s3[1] = 0.0; s3[2] = 0.0; }
           else { s3[0] = st[3 * lane]; s3[1] = st[3 * lane + 1]; s3[2] = st[3 * lane + 2]; }
-          k_via_step(s3, vias + viaHead, viaEnd - viaHead, tnow, dt, sm + P.o_scratch + P.via_stride * (lane - batch), P.via_unk);
+          k_via_step(s3, vias + viaHead, viaEnd - viaHead, tnow, dt, sm + AFFK_O(P, scratch) + P.via_stride * (lane - batch), P.via_unk);
           st[3 * lane] = s3[0]; st[3 * lane + 1] = s3[1]; st[3 * lane + 2] = s3[2];
           xdes[lane] = s3[0];
         }
@@ -1197,7 +1213,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
               const int i = (lane - 3) / 3, j = (lane - 3) % 3;
               v = fma(Cc[3 + 3 * i + 2], Pp[3 + 3 * j + 2], fma(Cc[3 + 3 * i + 1], Pp[3 + 3 * j + 1], Cc[3 + 3 * i] * Pp[3 + 3 * j]));
             }
-            sm[P.o_objrel + 12 * slot + lane] = v;
+            sm[AFFK_O(P, objrel) + 12 * slot + lane] = v;
           }
           c.objHasRel |= 1u << slot;
           OBJ_SET(c, objParentSlot, slot, ps);
@@ -1573,5 +1589,3 @@ AFF_DEV void k_prologue(const KPlan& P)
     for (int q = 0; q < 3; ++q) { P.sbodyAABB[6 * b + q] = mn[q]; P.sbodyAABB[6 * b + 3 + q] = mx[q]; }
   }
 }
-
-#endif
