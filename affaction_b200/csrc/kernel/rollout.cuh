@@ -182,41 +182,49 @@ AFF_DEV void k_fk(const KCtx& c, bool init)
   if (lane < P.nJ) { double s, co; aff_sincos(q[lane], &s, &co); sn[lane] = s; cs[lane] = co; }
   w_sync();
   const int e = lane % 12;
+  const int col = (e < 3) ? e : (e - 3) % 3, eo = (e < 3) ? e : 0;
   const KFkEntry* tab = P.fktab + lane;
   for (int r = 0; r < P.nRounds; ++r, tab += 32) {
     const KFkEntry en = ldg_fk(tab);
     const int op = (int)((en.w0 >> 24) & 7u);
     const int pbase = (int)(en.w0 & 4095u), dst = (int)((en.w0 >> 12) & 4095u);
     const int partner = (int)(en.w0 >> 27);
-    double val = 0.0, s = 0.0, co = 1.0;
+    // The common operations are straight-line code with selects (lanes that do not need a value read
+    // element 0 of the node array instead); objects and constant joints under a moving parent take a
+    // warp-uniform branch, which most rounds skip.
+    const bool compose = (op >= FKOP_FIXED) && (op <= FKOP_TRANS);
+    const bool jointed = (op > FKOP_FIXED) && (op <= FKOP_TRANS);
+    const double* Pp = nodes + (compose ? pbase : 0);           // pbase points at the parent node
+    const double p0 = Pp[eo], p3 = Pp[3 + col], p6 = Pp[6 + col], p9 = Pp[9 + col];
+    const double cp = nodes[(op == FKOP_COPY) ? pbase : 0];     // pbase points at the parent element
+    const double acc0 = (e < 3) ? p0 : 0.0;
+    const double comp = fma(en.t2, p9, fma(en.t1, p6, fma(en.t0, p3, acc0)));
+    double val = (op == FKOP_COPY) ? cp : (compose ? comp : 0.0);
+    const bool constJoint = jointed && (en.w1 & 0x80u) != 0u;
+    const int qi = (jointed && !constJoint) ? (int)(en.w1 & 63u) : 0;
+    double s = (op == FKOP_TRANS) ? q[qi] : sn[qi], co = cs[qi];
     bool store = op != FKOP_IDLE;
-    if (op == FKOP_COPY) val = nodes[pbase];
-    else if (op >= FKOP_FIXED && op <= FKOP_TRANS) {
-      const int col = (e < 3) ? e : (e - 3) % 3;
-      const double* Pp = nodes + pbase;           // pbase already points at the parent node
-      const double acc0 = (e < 3) ? Pp[e] : 0.0;
-      val = fma(en.t2, Pp[9 + col], fma(en.t1, Pp[6 + col], fma(en.t0, Pp[3 + col], acc0)));
-      if (op != FKOP_FIXED) {
-        if (en.w1 & 0x80u) { const int n = (int)((en.w1 >> 8) & 255u); s = ldg(&P.dynSC[2 * n]); co = ldg(&P.dynSC[2 * n + 1]); if (op == FKOP_TRANS) s = ldg(&P.dynQ[n]); }
-        else { const int qi = (int)(en.w1 & 63u); s = (op == FKOP_TRANS) ? q[qi] : sn[qi]; co = cs[qi]; }
-      }
-    } else if (op == FKOP_OBJECT) {
-      const int slot = (int)(en.w1 & 3u), n = (int)((en.w1 >> 8) & 255u);
-      if ((c.objHasRel >> slot) & 1u) {
-        const double* Pp = nodes + 12 * OBJ_GET(c, objParentSlot, slot);
-        const double* R = c.sm + AFFK_O(P, objrel) + 12 * slot;
-        const int col = (e < 3) ? e : (e - 3) % 3, tb = (e < 3) ? 0 : 3 + 3 * ((e - 3) / 3);
-        const double acc0 = (e < 3) ? Pp[e] : 0.0;
-        val = fma(R[tb + 2], Pp[9 + col], fma(R[tb + 1], Pp[6 + col], fma(R[tb], Pp[3 + col], acc0)));
-      } else {
-        store = false;
-        if ((init || OBJ_GET(c, objParentDynamic, slot)) && e == 0) k_object_from_q6(c, n, slot);
+    if (w_ballot(constJoint)) {
+      if (constJoint) { const int n = (int)((en.w1 >> 8) & 255u); s = ldg(&P.dynSC[2 * n]); co = ldg(&P.dynSC[2 * n + 1]); if (op == FKOP_TRANS) s = ldg(&P.dynQ[n]); }
+    }
+    if (w_ballot(op == FKOP_OBJECT)) {
+      if (op == FKOP_OBJECT) {
+        const int slot = (int)(en.w1 & 3u), n = (int)((en.w1 >> 8) & 255u);
+        if ((c.objHasRel >> slot) & 1u) {
+          const double* Po = nodes + 12 * OBJ_GET(c, objParentSlot, slot);
+          const double* R = c.sm + AFFK_O(P, objrel) + 12 * slot;
+          const int tb = (e < 3) ? 0 : 3 + 3 * ((e - 3) / 3);
+          const double a0 = (e < 3) ? Po[e] : 0.0;
+          val = fma(R[tb + 2], Po[9 + col], fma(R[tb + 1], Po[6 + col], fma(R[tb], Po[3 + col], a0)));
+        } else {
+          store = false;
+          if ((init || OBJ_GET(c, objParentDynamic, slot)) && e == 0) k_object_from_q6(c, n, slot);
+        }
       }
     }
     const double other = w_shfl(val, partner);
-    if (op == FKOP_ROT_A) val = fma(s, other, co * val);
-    else if (op == FKOP_ROT_B) val = fma(co, val, -(s * other));
-    else if (op == FKOP_TRANS) val = fma(s, other, val);
+    const double rotA = fma(s, other, co * val), rotB = fma(co, val, -(s * other)), trn = fma(s, other, val);
+    val = (op == FKOP_ROT_A) ? rotA : ((op == FKOP_ROT_B) ? rotB : ((op == FKOP_TRANS) ? trn : val));
     if (store) nodes[dst] = val;
     w_sync();
   }
