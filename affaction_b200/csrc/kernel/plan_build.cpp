@@ -249,6 +249,7 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     const int nR = (int)H.rounds.size() / 2;
     KFkEntry idle; std::memset(&idle, 0, sizeof(idle));
     H.fktab.assign((size_t)nR * 32, idle);
+    P.fk_obj_rounds[0] = P.fk_obj_rounds[1] = P.fk_const_rounds[0] = P.fk_const_rounds[1] = 0u;
     for (int r = 0; r < nR; ++r)
       for (int grp = 0; grp < 2; ++grp) {
         const int n = H.rounds[2 * r + grp];
@@ -262,7 +263,7 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
           const int tb = e < 3 ? 0 : 3 + 3 * row;
           en.t0 = nd.T[tb]; en.t1 = nd.T[tb + 1]; en.t2 = nd.T[tb + 2];
           uint32_t op = 2, partner = (uint32_t)lane, pbase = (uint32_t)(12 * pslot), dst = (uint32_t)(12 * n + e), w1 = 0;
-          if (nd.kind == AFFK_NODE_OBJECT) { op = 6; w1 = (uint32_t)(nd.qidx & 3) | ((uint32_t)n << 8); }
+          if (nd.kind == AFFK_NODE_OBJECT) { op = 6; w1 = (uint32_t)(nd.qidx & 3) | ((uint32_t)n << 8); P.fk_obj_rounds[(r >> 5) & 1] |= 1u << (r & 31); }
           else if (nd.kind == AFFK_NODE_FIXED) { if (nd.identityT) { op = 1; pbase = (uint32_t)(12 * pslot + e); } }
           else {
             const bool isRot = nd.jtype >= AFF_JNT_ROT_X;
@@ -273,6 +274,7 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
               else if (row == b) { op = 4; partner = (uint32_t)(grp * 12 + 3 + 3 * a + col); }
             } else if (!isRot && e < 3) { op = 5; partner = (uint32_t)(grp * 12 + 3 + 3 * d + e); }
             w1 = (nd.kind == AFFK_NODE_JOINT_IK) ? (uint32_t)(nd.qidx & 63) : (0x80u | ((uint32_t)n << 8));
+            if (nd.kind != AFFK_NODE_JOINT_IK) P.fk_const_rounds[(r >> 5) & 1] |= 1u << (r & 31);
           }
           if (pbase > 4095u || dst > 4095u) { err = "FK table: node array too large"; return AFF_ERR_CAPACITY; }
           en.w0 = pbase | (dst << 12) | (op << 24) | (partner << 27);

@@ -204,10 +204,10 @@ AFF_DEV void k_fk(const KCtx& c, bool init)
     const int qi = (jointed && !constJoint) ? (int)(en.w1 & 63u) : 0;
     double s = (op == FKOP_TRANS) ? q[qi] : sn[qi], co = cs[qi];
     bool store = op != FKOP_IDLE;
-    if (w_ballot(constJoint)) {
+    if ((P.fk_const_rounds[(r >> 5) & 1] >> (r & 31)) & 1u) {          // warp-uniform: known to the plan
       if (constJoint) { const int n = (int)((en.w1 >> 8) & 255u); s = ldg(&P.dynSC[2 * n]); co = ldg(&P.dynSC[2 * n + 1]); if (op == FKOP_TRANS) s = ldg(&P.dynQ[n]); }
     }
-    if (w_ballot(op == FKOP_OBJECT)) {
+    if ((P.fk_obj_rounds[(r >> 5) & 1] >> (r & 31)) & 1u) {
       if (op == FKOP_OBJECT) {
         const int slot = (int)(en.w1 & 3u), n = (int)((en.w1 >> 8) & 255u);
         if ((c.objHasRel >> slot) & 1u) {
