@@ -873,18 +873,17 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
     btree[lane] = act ? (os ? OBJ_GET(c, objTree, os - 1) : ldg(&b->tree)) : -2;
   }
   w_sync();
-  // 3. tree AABBs
-  if (lane < P.nTrees) {
-    double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  // 3. tree AABBs: one lane per (tree, bound); min / max over the tree's bodies
+  for (int i = lane; i < 6 * P.nTrees; i += 32) {
+    const int t = i / 6, k = i % 6;
+    const bool isMin = k < 3;
+    double v = isMin ? DBL_MAX : -DBL_MAX;
     for (int b = 0; b < P.nDynBodies; ++b) {
-      if (btree[b] != lane) continue;
-      for (int q = 0; q < 3; ++q) {
-        const double lo = baabb[6 * b + q], hi = baabb[6 * b + 3 + q];
-        if (lo < mn[q]) mn[q] = lo;
-        if (hi > mx[q]) mx[q] = hi;
-      }
+      const double x = baabb[6 * b + k];
+      const bool take = (btree[b] == t) && (isMin ? x < v : x > v);
+      v = take ? x : v;
     }
-    for (int q = 0; q < 3; ++q) { taabb[6 * lane + q] = mn[q]; taabb[6 * lane + 3 + q] = mx[q]; }
+    taabb[i] = v;
   }
   w_sync();
   // 4. static bodies that are not explicit: two-level AABB test (tree box, then tree bodies)

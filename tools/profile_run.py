@@ -15,11 +15,14 @@ dev = ab.DeviceBatch(s, b, ab.default_opts())
 st = torch.cuda.current_stream().cuda_stream
 e0 = torch.cuda.Event(enable_timing=True)
 e1 = torch.cuda.Event(enable_timing=True)
+times = []
 for i in range(launches):
     e0.record()
     dev.launch(st)
     e1.record()
     torch.cuda.synchronize()
-    print("launch %d: %.2f ms, %.0f rollouts/s" % (i, e0.elapsed_time(e1), n / e0.elapsed_time(e1) * 1e3))
+    times.append(e0.elapsed_time(e1))
+    print("launch %d: %.2f ms, %.0f rollouts/s" % (i, times[-1], n / times[-1] * 1e3))
 res = dev.results()
 print("success", sum(r.success for r in res), "of", n)
+print("best %.2f ms = %.0f rollouts/s" % (min(times), n / min(times) * 1e3))
