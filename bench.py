@@ -100,7 +100,8 @@ def make_batches(ab, scene, rank, per_variant):
     batches = []
     for v, cmd in enumerate(VARIANTS):
         hb = ab.HostBatch(scene)
-        hb.add_perturbed(cmd, per_variant, seed0=0xAFFAC7 + (rank * len(VARIANTS) + v) * per_variant)
+        # seeds do not depend on the batch size: a smaller batch is a prefix of the full one
+        hb.add_perturbed(cmd, per_variant, seed0=0xAFFAC7 + (rank * len(VARIANTS) + v) * PER_VARIANT)
         batches.append(hb)
     return batches
 
@@ -113,9 +114,11 @@ def cpu_arm(ab, scene, n_rollouts, threads):
     batches = make_batches(ab, scene, 0, per)
     opts = ab.default_opts()
     t0 = time.perf_counter()
+    results = []
     for hb in batches:
-        ob.predict_batch(scene, hb, opts, n_threads=threads)
+        results.append(ob.predict_batch(scene, hb, opts, n_threads=threads))
     dt = time.perf_counter() - t0
+    cpu_arm.last_results = results          # per variant, for the agreement report
     return per * len(VARIANTS) / dt, dt, per * len(VARIANTS)
 
 
@@ -256,12 +259,25 @@ def run_cuda(args, rank, local_rank, world):
             pass
         hbm_achieved = ALGORITHMIC_BYTES_PER_ROLLOUT * n_local / avg_kernel_s * 1e-9
         # bounded CPU sample on the box's host cores (N=1 only)
-        cpu = None
+        cpu, agreement = None, None
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             v, secs, n = cpu_arm(ab, scene, max(len(VARIANTS), 120 * threads), threads)   # ~10-30 s of CPU work
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "%d rollouts of the same workload in %.1f s (CPU oracle, %d threads)" % (n, secs, threads)}
+            # the CPU sample = the first candidates of each variant of this rank's GPU batch: compare the records
+            agreement = {"sample": 0, "records_equal": 0, "verdicts_equal": 0, "ranked_first_equal": True,
+                         "max_abs_diff": {"min_dist": 0.0, "jl_cost": 0.0, "coll_cost": 0.0}}
+            for vi, cpu_res in enumerate(cpu_arm.last_results):
+                gpu_res = res[vi * per_variant: vi * per_variant + len(cpu_res)]
+                for a, b in zip(cpu_res, gpu_res):
+                    agreement["sample"] += 1
+                    agreement["records_equal"] += int(a.as_tuple() == b.as_tuple())
+                    agreement["verdicts_equal"] += int((a.success, a.code, a.first_fail_step) == (b.success, b.code, b.first_fail_step))
+                    for f in agreement["max_abs_diff"]:
+                        agreement["max_abs_diff"][f] = max(agreement["max_abs_diff"][f], abs(getattr(a, f) - getattr(b, f)))
+                if ab.rank(cpu_res)[0] != ab.rank(list(gpu_res))[0]:
+                    agreement["ranked_first_equal"] = False
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -285,6 +301,7 @@ def run_cuda(args, rank, local_rank, world):
                              "frac": hbm_achieved / hbm_peak, "algorithmic_bytes_per_rollout": ALGORITHMIC_BYTES_PER_ROLLOUT,
                              "peak_source": hbm_src},
             "cpu_baseline": cpu,
+            "agreement": agreement,
             "clocks": sampler.summary(),
         }
         print(json.dumps(line))
