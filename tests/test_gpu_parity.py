@@ -289,3 +289,27 @@ def test_full_size_sweep_properties(scene):
             ref, _ = ob.predict(scene, batch, i, opts)
             assert res[i].as_tuple() == ref.as_tuple()
     assert mix == {"tracking": 13934, "ok": 9720, "collision": 4110, "joint_limit": 652}
+
+
+def test_every_get_in_the_scene_matches_oracle(scene):
+    """All 56 graspable entities of the pizza scene (bowls, bottles, plates, ingredients, tray ...),
+    two candidates each: every record equal to the oracle's."""
+    names = []
+    for line in open(os.path.join(os.path.dirname(ab.__file__), "data", "pizza.affscene")):
+        if line.startswith("entity ") and line.split()[1] not in names:
+            names.append(line.split()[1])
+    opts = ab.default_opts()
+    checked, verdicts = 0, set()
+    for name in names:
+        batch = ab.HostBatch(scene)
+        try:
+            n = batch.add_action("get " + name)
+        except ab.AffError:
+            continue                      # furniture: "cannot be grasped"
+        gpu = ab.predict_batch(scene, batch, opts)
+        ref = ob.predict_batch(scene, batch, opts, n_threads=min(n, os.cpu_count() or 1))
+        for i in range(n):
+            assert gpu[i].as_tuple() == ref[i].as_tuple(), "get %s candidate %d" % (name, i)
+            verdicts.add(gpu[i].code)
+        checked += n
+    assert checked == 112 and len(verdicts) >= 3
