@@ -313,3 +313,22 @@ def test_every_get_in_the_scene_matches_oracle(scene):
             verdicts.add(gpu[i].code)
         checked += n
     assert checked == 112 and len(verdicts) >= 3
+
+
+def test_ragged_batch_and_edge_sizes(scene):
+    """One batch mixing actions of different shapes (2 get candidates with 7 tasks / 1555 steps, a pose
+    with 20 one-joint tasks, a 16 s finger_push with 2155 steps): ragged task counts, task dimensions
+    and step counts in one launch.  Then the edge sizes: an empty batch and a batch of one."""
+    batch = ab.HostBatch(scene)
+    n = batch.add_action("get fresh_tomatoes") + batch.add_action("pose TableCalibration") + batch.add_action("finger_push oven")
+    assert n == 4
+    opts = ab.default_opts(log_q=True)
+    dev = ab.DeviceBatch(scene, batch, opts)
+    dev.launch()
+    assert [dev.num_steps(i) for i in range(n)] == [1555, 1555, 1555, 2155]
+    assert _compare(scene, batch, opts, dev, range(n)) == 0.0
+    assert ab.predict_batch(scene, ab.HostBatch(scene)) == []          # nothing to predict is not an error
+    one = ab.HostBatch(scene)
+    one.add_perturbed("get fresh_tomatoes", 1)
+    ref, _ = ob.predict(scene, one, 0, ab.default_opts())
+    assert ab.predict_batch(scene, one)[0].as_tuple() == ref.as_tuple()
