@@ -10,6 +10,7 @@
 #include <cfloat>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -248,7 +249,18 @@ int aff_batch_create(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, c
   // AFF_TUNE_GENERIC_KERNEL: run the generic kernel on a fixed-layout plan too (A/B of the two builds)
   b->useFixed = b->plan.fixed_layout != 0 && !getenv("AFF_TUNE_GENERIC_KERNEL");
   const void* kfn = b->useFixed ? (const void*)aff_rollout_kernel : (const void*)aff_rollout_kernel_generic;
-  CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smemBytes));
+  {
+    // The limit is a property of the kernel, not of the batch: only ever raise it, or a batch created
+    // earlier with a larger footprint could no longer be launched.
+    static std::mutex mtx;
+    static size_t raised[64][2] = {};
+    std::lock_guard<std::mutex> lock(mtx);
+    size_t& cur = raised[s->device & 63][b->useFixed ? 0 : 1];
+    if (b->smemBytes > cur) {
+      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smemBytes));
+      cur = b->smemBytes;
+    }
+  }
   if (const char* co = getenv("AFF_TUNE_CARVEOUT")) CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co)));
   int perSM = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kfn, 32 * AFF_WARPS_PER_BLOCK, b->smemBytes));

@@ -332,3 +332,19 @@ def test_ragged_batch_and_edge_sizes(scene):
     one.add_perturbed("get fresh_tomatoes", 1)
     ref, _ = ob.predict(scene, one, 0, ab.default_opts())
     assert ab.predict_batch(scene, one)[0].as_tuple() == ref.as_tuple()
+
+
+def test_batches_with_different_footprints_coexist(scene):
+    """A batch created earlier with the larger shared-memory footprint must still launch after a
+    smaller one has been created (the dynamic shared-memory limit belongs to the kernel)."""
+    big = ab.HostBatch(scene)
+    big.add_perturbed("get italian_seasoning_bowl", 8)
+    small = ab.HostBatch(scene)
+    small.add_perturbed("get fresh_tomatoes", 8)
+    dev_big = ab.DeviceBatch(scene, big, ab.default_opts())
+    dev_small = ab.DeviceBatch(scene, small, ab.default_opts())
+    assert dev_big.smem_bytes_per_warp > dev_small.smem_bytes_per_warp
+    dev_small.launch()
+    dev_big.launch()
+    ref = ob.predict_batch(scene, big, ab.default_opts(), n_threads=8)
+    assert [r.as_tuple() for r in dev_big.results()] == [r.as_tuple() for r in ref]
