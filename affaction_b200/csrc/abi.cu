@@ -10,6 +10,7 @@
 #include <cfloat>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -226,12 +227,15 @@ int aff_batch_create(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, c
   if (opts) o = *opts; else aff_default_opts(&o);
   if (!(o.dt > 0.0)) return fail(AFF_ERR_INVALID, "aff_batch_create: dt must be positive");
   CUDA_TRY(cudaSetDevice(s->device));
-  aff_batch* b = new aff_batch;
+  // owned until the end: every early return below frees the device buffers and the handle
+  struct Drop { void operator()(aff_batch* p) const { p->release(); delete p; } };
+  std::unique_ptr<aff_batch, Drop> owner(new aff_batch);
+  aff_batch* b = owner.get();
   b->scene = s;
   std::string e;
   const auto tb0 = std::chrono::steady_clock::now();
   int rc = affk::buildPlan(s->model, tasks, n_tasks, cons, n_cons, cands, n_cands, o, b->host, e);
-  if (rc != AFF_OK) { delete b; return fail(rc, "aff_batch_create: " + e); }
+  if (rc != AFF_OK) return fail(rc, "aff_batch_create: " + e);
   const auto tb1 = std::chrono::steady_clock::now();
   rc = uploadBatch(b, 0);
   if (getenv("AFF_TIMING")) {
@@ -240,12 +244,12 @@ int aff_batch_create(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, c
     std::fprintf(stderr, "aff_batch_create: plan %.1f ms, alloc + H2D %.1f ms (%.1f MB)\n", std::chrono::duration<double, std::milli>(tb1 - tb0).count(),
                  std::chrono::duration<double, std::milli>(tb2 - tb1).count(), b->h2dBytes / 1e6);
   }
-  if (rc != AFF_OK) { b->release(); delete b; return rc; }
+  if (rc != AFF_OK) return rc;
   // launch geometry: persistent blocks, as many as fit per SM
   b->smemBytes = b->host.smemBytesPerWarp * AFF_WARPS_PER_BLOCK;
   // tuning experiments only (tools/try_variants.sh): extra dynamic shared memory per block, preferred carve-out in percent
   if (const char* pad = getenv("AFF_TUNE_SMEM_PAD")) b->smemBytes += (size_t)atoi(pad);
-  if (b->smemBytes > (size_t)s->smemOptin) { b->release(); delete b; return fail(AFF_ERR_CAPACITY, "aff_batch_create: rollout state does not fit in shared memory"); }
+  if (b->smemBytes > (size_t)s->smemOptin) return fail(AFF_ERR_CAPACITY, "aff_batch_create: rollout state does not fit in shared memory");
   // AFF_TUNE_GENERIC_KERNEL: run the generic kernel on a fixed-layout plan too (A/B of the two builds)
   b->useFixed = b->plan.fixed_layout != 0 && !getenv("AFF_TUNE_GENERIC_KERNEL");
   const void* kfn = b->useFixed ? (const void*)aff_rollout_kernel : (const void*)aff_rollout_kernel_generic;
@@ -268,7 +272,7 @@ int aff_batch_create(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, c
   const int blocksNeeded = (int)((n_cands + AFF_WARPS_PER_BLOCK - 1) / AFF_WARPS_PER_BLOCK);
   b->grid = std::max(1, std::min(blocksNeeded, perSM * s->smCount));
   CUDA_TRY(cudaStreamSynchronize(0));
-  *out = b;
+  *out = owner.release();
   return AFF_OK;
 }
 
