@@ -352,14 +352,34 @@ int aff_predict_batch(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, 
   // uploads chunk k+1 (default stream) while the kernels of chunk k run on their own stream.
   CUDA_TRY(cudaSetDevice(s->device));
   size_t wave = (size_t)s->smCount * AFF_BLOCKS_PER_SM * AFF_WARPS_PER_BLOCK;
-  std::vector<aff_batch*> parts;
-  std::vector<size_t> first;
-  cudaStream_t ks = nullptr;
+  // chunks in flight: at most three (running, queued, being compiled); the oldest is collected and freed
+  struct Part { aff_batch* b; size_t first; cudaEvent_t done; };
+  std::vector<Part> parts;
+  cudaStream_t ks = nullptr, cs = nullptr;
   int rc = AFF_OK;
   double planMs = 0.0;
-  auto cleanup = [&]() { for (aff_batch* p : parts) aff_batch_destroy(p); if (ks) cudaStreamDestroy(ks); };
-  if (n_cands > 2 * wave) { if (cudaStreamCreateWithFlags(&ks, cudaStreamNonBlocking) != cudaSuccess) { ks = nullptr; wave = n_cands; } }
-  else wave = n_cands;
+  size_t nParts = 0;
+  // results of the oldest chunk -> host, then its buffers back to the pool (its kernels have finished:
+  // nothing else uses them, so no further synchronisation is needed before the stream-ordered free)
+  auto retire = [&](Part& p) -> int {
+    int r = AFF_OK;
+    const size_t cnt = (size_t)p.b->plan.nCands;
+    if (p.done) {
+      if (cudaEventSynchronize(p.done) != cudaSuccess) r = fail(AFF_ERR_CUDA, "aff_predict_batch: kernel failed");
+      cudaEventDestroy(p.done);
+      p.b->launched = false;
+    }
+    if (r == AFF_OK) r = aff_batch_results(p.b, cs, out + p.first, cnt);
+    if (r == AFF_OK) for (size_t i = 0; i < cnt; ++i) out[p.first + i].idx += (int32_t)p.first;
+    aff_batch_destroy(p.b);
+    return r;
+  };
+  if (n_cands > 2 * wave) {
+    if (cudaStreamCreateWithFlags(&ks, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) {
+      if (ks) cudaStreamDestroy(ks);
+      ks = cs = nullptr; wave = n_cands;
+    }
+  } else wave = n_cands;
   for (size_t off = 0; off < n_cands && rc == AFF_OK;) {
     size_t cnt = std::min(wave, n_cands - off);
     if (n_cands - off - cnt < wave / 2) cnt = n_cands - off;        // no short last chunk
@@ -381,28 +401,29 @@ int aff_predict_batch(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, 
     }
     planMs += ms(tp, now());
     if (rc != AFF_OK) break;
-    parts.push_back(b);
-    first.push_back(off);
-    if (parts.size() == 1 && ks) {
+    Part part{b, off, nullptr};
+    if (nParts == 0 && ks) {
       // the first chunk tells how many rollouts are resident at once with this batch's shared-memory footprint
       const size_t resident = (size_t)b->grid * AFF_WARPS_PER_BLOCK;
       if (resident > 0 && resident < wave) wave = resident;
     }
     rc = aff_batch_launch(b, ks);
+    if (rc == AFF_OK && ks && (cudaEventCreateWithFlags(&part.done, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(part.done, ks) != cudaSuccess))
+      rc = fail(AFF_ERR_CUDA, "aff_predict_batch: cannot record an event");
+    parts.push_back(part);
+    ++nParts;
     off += cnt;
+    if (rc == AFF_OK && parts.size() > 2) { rc = retire(parts.front()); parts.erase(parts.begin()); }
   }
   const auto t1 = now();
-  for (size_t k = 0; k < parts.size() && rc == AFF_OK; ++k) {
-    const size_t cnt = (size_t)parts[k]->plan.nCands;
-    rc = aff_batch_results(parts[k], ks, out + first[k], cnt);
-    for (size_t i = 0; i < cnt; ++i) out[first[k] + i].idx += (int32_t)first[k];
-  }
+  for (Part& p : parts) { const int r = retire(p); if (rc == AFF_OK) rc = r; }
+  parts.clear();
   const auto t2 = now();
-  const size_t nParts = parts.size();
-  cleanup();
+  if (ks) cudaStreamDestroy(ks);
+  if (cs) cudaStreamDestroy(cs);
   const auto t3 = now();
   if (timing) std::fprintf(stderr, "aff_predict_batch: %zu candidates in %zu chunk(s): plan + H2D %.1f ms (overlapped after the first chunk), "
-                           "submit %.1f ms, wait + D2H %.1f ms, destroy %.1f ms\n", n_cands, nParts, planMs, ms(t0, t1), ms(t1, t2), ms(t2, t3));
+                           "submit + collect %.1f ms, drain %.1f ms, streams %.1f ms\n", n_cands, nParts, planMs, ms(t0, t1), ms(t1, t2), ms(t2, t3));
   return rc;
 }
 
