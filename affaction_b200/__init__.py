@@ -84,7 +84,7 @@ HOST_SYMBOLS = [
     "aff_host_scene_device", "aff_host_batch_create", "aff_host_batch_destroy", "aff_host_batch_clear",
     "aff_host_batch_add_action", "aff_host_batch_add_perturbed", "aff_host_batch_num_tasks", "aff_host_batch_num_constraints",
     "aff_host_batch_num_candidates", "aff_host_batch_tasks", "aff_host_batch_constraints", "aff_host_batch_candidates",
-    "aff_host_batch_task_name", "aff_host_predict", "aff_host_format_message", "aff_host_check_trajectory",
+    "aff_host_batch_task_name", "aff_host_predict", "aff_host_format_message", "aff_host_check_trajectory", "aff_host_scene_apply_rollout", "aff_host_predict_sequence",
 ]
 
 
@@ -122,6 +122,8 @@ def lib():
         "aff_host_batch_task_name": (cstr, [vp, sz, i32]),
         "aff_host_predict": (i32, [vp, vp, dbl, i32, i32, vp, vp, sz]),
         "aff_host_format_message": (i32, [vp, vp, vp, dbl, vp, sz]),
+        "aff_host_scene_apply_rollout": (i32, [vp, vp, sz, vp, i32, dbl]),
+        "aff_host_predict_sequence": (i32, [vp, cstr, dbl, i32, vp, vp, vp, sz, i32]),
         "aff_host_check_trajectory": (i32, [vp, vp, sz, i32, i32, i32, dbl, i32, vp, vp, vp, vp, vp, vp, sz, vp, sz]),
     }
     for name, (res, args) in sig.items():
@@ -193,6 +195,24 @@ class HostScene:
         rc = lib().aff_host_scene_set_ik_state(self.h, q.ctypes.data_as(C.c_void_p), len(q))
         if rc != AFF_OK:
             raise AffError("set_ik_state failed: %s" % lib().aff_host_last_error().decode())
+
+    def apply_rollout(self, batch, cand, q, dt=0.01):
+        """Scene state after candidate `cand` of `batch` has run (q = its joint log, rows x nJ)."""
+        import numpy as np
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        rc = lib().aff_host_scene_apply_rollout(self.h, batch.h, cand, q.ctypes.data_as(C.c_void_p), q.shape[0], dt)
+        if rc != AFF_OK:
+            raise AffError("apply_rollout failed: %s" % lib().aff_host_last_error().decode())
+
+    def predict_sequence(self, text, dt=0.01, device=0, max_actions=16, msg_len=768):
+        """aff_host_predict_sequence: [(winner record, number of candidates, message)] per action."""
+        res = (Result * max_actions)()
+        ncand = (C.c_int * max_actions)()
+        msgs = C.create_string_buffer(max_actions * msg_len)
+        n = lib().aff_host_predict_sequence(self.h, text.encode(), dt, device, res, ncand, msgs, msg_len, max_actions)
+        if n < 0:
+            raise AffError("predict_sequence: %s / %s" % (lib().aff_host_last_error().decode(), lib().aff_last_error().decode()))
+        return [(res[i], ncand[i], msgs.raw[i * msg_len:(i + 1) * msg_len].split(b"\0", 1)[0].decode()) for i in range(n)]
 
     def device_scene(self, device=0):
         p = lib().aff_host_scene_device(self.h, device)

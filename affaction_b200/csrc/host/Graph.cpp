@@ -191,10 +191,16 @@ void Graph::computeForwardKinematics()
   }
 }
 
-void Graph::connectBody(int child, int parent)
+void Graph::connectBody(int child, int parent, bool identityTransform)
 {
   Body& c = bodies.at(child);
   if (!c.rigid_body_joints || c.nJoints < 6) throw std::runtime_error("connectBody: " + c.name + " has no rigid body joints");
+  if (identityTransform) {      // setConnectTransform(HTr_identity()): the child sits on the parent frame
+    for (int k = 0; k < 6; ++k) joints[c.firstJoint + k].q_init = 0.0;
+    c.parent = parent;
+    computeForwardKinematics();
+    return;
+  }
   const HTr& C = c.A_BI; const HTr& P = bodies.at(parent).A_BI;
   // relative pose -> six rigid-body dof values (x y z + x-y-z Euler angles)
   double rel[3], R[3][3];
@@ -210,6 +216,42 @@ void Graph::connectBody(int child, int parent)
   for (int k = 0; k < 3; ++k) { joints[c.firstJoint + k].q_init = rel[k]; joints[c.firstJoint + 3 + k].q_init = ea[k]; }
   c.parent = parent;
   computeForwardKinematics();
+}
+
+void Graph::applyRollout(const aff_constraint* cons, int nCons, const double* qlog, int rows, double dt)
+{
+  if (!qlog || rows < 1) throw std::runtime_error("applyRollout: no joint log");
+  auto setRow = [&](int row) {
+    for (Joint& j : joints) if (j.jacobiIndex >= 0) j.q_init = qlog[(size_t)row * nJ + j.jacobiIndex];
+    computeForwardKinematics();
+  };
+  // the time the trajectory controller has reached in iteration `iter` is dt added up iter + 1 times;
+  // an event of iteration `iter` sees the poses of qlog row `iter` (TrajectoryPredictor.cpp:182-188)
+  std::vector<char> fired((size_t)std::max(nCons, 0), 0);
+  double tnow = 0.0;
+  for (int iter = 0; iter + 1 < rows; ++iter) {
+    tnow = tnow + dt;
+    bool any = false;
+    for (int k = 0; k < nCons; ++k) {
+      if (fired[k]) continue;
+      const aff_constraint& c = cons[k];
+      if (c.kind == AFF_CON_CONNECT && c.t - tnow < 1.0e-8) any = true;
+      if (c.kind == AFF_CON_COLLISION && c.t - tnow < 0.0) any = true;
+    }
+    if (!any) continue;
+    setRow(iter);
+    for (int k = 0; k < nCons; ++k) {
+      if (fired[k]) continue;
+      const aff_constraint& c = cons[k];
+      if (c.kind == AFF_CON_CONNECT && c.t - tnow < 1.0e-8) { connectBody(c.body_a, c.body_b, c.dim == 1); fired[k] = 1; }
+      else if (c.kind == AFF_CON_COLLISION && c.t - tnow < 0.0) {
+        Body& b = bodies.at(c.body_a);
+        for (int sI = 0; sI < b.nShapes; ++sI) shapes[b.firstShape + sI].distance = c.flag != 0;   // CollisionModelConstraint.h:101-147
+        fired[k] = 1;
+      }
+    }
+  }
+  setRow(rows - 1);
 }
 
 static void shapeAABB(const Shape& s, const HTr& A, double mn[3], double mx[3])

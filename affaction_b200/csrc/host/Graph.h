@@ -76,7 +76,11 @@ public:
   void computeForwardKinematics();
   // Re-parent `child` under `parent` keeping its world pose: what a fired
   // ConnectBodyConstraint leaves behind (used to chain get -> put on the host).
-  void connectBody(int child, int parent);
+  void connectBody(int child, int parent, bool identityTransform = false);
+  // State a finished rollout leaves behind (what the live graph looks like after the action ran):
+  // every ConnectBody / CollisionModel constraint is applied at the step it fired, with the joint
+  // state of that step (qlog row), then the joints take the final row.  qlog: rows x nJ, jacobi order.
+  void applyRollout(const struct aff_constraint* cons, int nCons, const double* qlog, int rows, double dt);
 
   // RcsGraph_computeBodyAABB over shapes with the distance flag. false if none.
   bool computeBodyAABB(int body, double xyzMin[3], double xyzMax[3]) const;

@@ -101,6 +101,18 @@ int aff_host_scene_set_ik_state(aff_host_scene* s, const double* q, int n)
   return AFF_OK;
 }
 
+int aff_host_scene_apply_rollout(aff_host_scene* s, const aff_host_batch* b, size_t cand, const double* qlog, int rows, double dt)
+{
+  try {
+    if (!s || !b || cand >= b->batch.candidates.size()) { g_hostError = "apply_rollout: candidate out of range"; return AFF_ERR_INVALID; }
+    const aff_candidate& c = b->batch.candidates[cand];
+    s->graph.applyRollout(b->batch.constraints.data() + c.first_constraint, c.n_constraints, qlog, rows, dt);
+    s->graph.toDesc();
+    if (s->device) { aff_scene_destroy(s->device); s->device = nullptr; }
+    return AFF_OK;
+  } catch (const std::exception& e) { g_hostError = e.what(); return AFF_ERR_INVALID; }
+}
+
 aff_scene* aff_host_scene_device(aff_host_scene* s, int device)
 {
   if (!s->device) {
@@ -238,6 +250,77 @@ int aff_host_format_message(aff_host_scene* s, aff_host_batch* b, const aff_resu
   std::strncpy(out, p.message.c_str(), n - 1);
   out[n - 1] = '\0';
   return (int)p.message.size();
+}
+
+// "a; b; c": predict, take the ranked-first candidate, apply its end state, go on.
+int aff_host_predict_sequence(aff_host_scene* s, const char* text, double dt, int device,
+                              aff_result* winners, int* nCandidates, char* messages, size_t msgStride, int maxActions)
+{
+  try {
+    std::vector<std::string> actions;
+    {
+      std::istringstream is(text ? text : "");
+      for (std::string a; std::getline(is, a, ';');) {
+        const size_t b0 = a.find_first_not_of(" \t\n"), b1 = a.find_last_not_of(" \t\n");
+        if (b0 != std::string::npos) actions.push_back(a.substr(b0, b1 - b0 + 1));
+      }
+    }
+    int done = 0;
+    for (const std::string& text_i : actions) {
+      if (done >= maxActions) break;
+      CandidateBatch batch;
+      std::vector<std::string> commands;
+      auto action = ActionFactory::create(s->domain, s->graph, text_i);
+      const size_t n = action->getNumSolutions();
+      for (size_t i = 0; i < n; ++i) {
+        auto local = action->clone();
+        if (!local->initialize(s->domain, s->graph, i)) { g_hostError = "initialize failed"; return AFF_ERR_INVALID; }
+        local->appendTo(batch, s->graph, local->getDurationHint(), dt);
+      }
+      aff_scene* dev = aff_host_scene_device(s, device);
+      if (!dev) return AFF_ERR_CUDA;
+      aff_opts opts;
+      aff_default_opts(&opts);
+      opts.dt = dt;
+      opts.log_q = 1;                 // the winner's joint trajectory is the next action's start
+      aff_batch* db = nullptr;
+      if (aff_batch_create(dev, batch.tasks.data(), batch.tasks.size(), batch.constraints.data(), batch.constraints.size(),
+                           batch.candidates.data(), batch.candidates.size(), &opts, &db) != AFF_OK) { g_hostError = aff_last_error(); return AFF_ERR_CUDA; }
+      std::vector<aff_result> raw(batch.candidates.size());
+      int rc = aff_batch_launch(db, nullptr);
+      if (rc == AFF_OK) rc = aff_batch_results(db, nullptr, raw.data(), raw.size());
+      std::vector<int32_t> order(raw.size());
+      aff_rank_results(raw.data(), raw.size(), order.data());
+      const aff_result best = raw[order[0]];
+      std::vector<double> q;
+      int rows = 0;
+      if (rc == AFF_OK && best.success) {
+        rows = aff_batch_num_steps(db, (size_t)best.idx) + 1;
+        q.resize((size_t)rows * s->graph.nJ);
+        rows = aff_batch_fetch_q(db, (size_t)best.idx, q.data(), (size_t)rows);
+        if (rows < 0) rc = rows;
+      }
+      aff_batch_destroy(db);
+      if (rc != AFF_OK) { g_hostError = aff_last_error(); return AFF_ERR_CUDA; }
+      if (winners) winners[done] = best;
+      if (nCandidates) nCandidates[done] = (int)raw.size();
+      if (messages && msgStride > 0) {
+        const std::string m = TrajectoryPredictor::convert(best, s->graph, batch.taskNames[best.idx], dt).message + " command: " + text_i;
+        std::strncpy(messages + (size_t)done * msgStride, m.c_str(), msgStride - 1);
+        messages[(size_t)done * msgStride + msgStride - 1] = '\0';
+      }
+      ++done;
+      if (!best.success) break;         // the reference clears the rest of the queue when an action fails
+      const aff_candidate& c = batch.candidates[best.idx];
+      s->graph.applyRollout(batch.constraints.data() + c.first_constraint, c.n_constraints, q.data(), rows, dt);
+      s->graph.toDesc();
+      if (s->device) { aff_scene_destroy(s->device); s->device = nullptr; }
+    }
+    return done;
+  } catch (const std::exception& e) {
+    g_hostError = e.what();
+    return AFF_ERR_INVALID;
+  }
 }
 
 // TrajectoryComponent on one candidate of a batch: its task list plays the runtime controller's,

@@ -37,6 +37,10 @@ int aff_host_scene_connect(aff_host_scene* s, const char* child, const char* par
 /* Set the unconstrained joints (jacobi order, n = aff_host_num_ik_joints) to the state a
  * finished rollout ended in: start state of the next action of a sequence. */
 int aff_host_scene_set_ik_state(aff_host_scene* s, const double* q, int n);
+/* Bring the scene into the state candidate `cand` of the batch leaves behind when it has run: its
+ * ConnectBody / CollisionModel constraints applied at the steps they fired (with the joint state of
+ * those steps), then the final joint state.  qlog = rows x nJ from aff_batch_fetch_q. */
+int aff_host_scene_apply_rollout(aff_host_scene* s, const aff_host_batch* b, size_t cand, const double* qlog, int rows, double dt);
 /* Device-side scene handle (created on first use). NULL on CUDA failure. */
 aff_scene* aff_host_scene_device(aff_host_scene* s, int device);
 
@@ -62,6 +66,15 @@ const char* aff_host_batch_task_name(const aff_host_batch* b, size_t cand, int t
 int aff_host_predict(aff_host_scene* s, aff_host_batch* b, double dt, int sort_results, int device,
                      aff_result* raw_out, char* messages, size_t msg_stride);
 int aff_host_format_message(aff_host_scene* s, aff_host_batch* b, const aff_result* r, double dt, char* out, size_t n);
+
+/* An action sequence "a; b; c" predicted the way the reference runs one (each action is predicted
+ * from the state the previous one left, examples/ExampleActionsECS.cpp:924-979): per action all
+ * candidates on the GPU, the ranked-first one is taken, its end state applied to the scene.  Stops
+ * after the first action without a feasible candidate.  winners[i] / messages (msg_stride bytes each)
+ * describe the ranked-first candidate of action i.  Returns the number of actions predicted, or <0.
+ * The scene is left in the state after the last feasible action. */
+int aff_host_predict_sequence(aff_host_scene* s, const char* text, double dt, int device,
+                              aff_result* winners, int* n_candidates, char* messages, size_t msg_stride, int max_actions);
 
 /* Second call site: TrajectoryComponent::checkerThread (reference src/TrajectoryComponent.cpp:346-399)
  * on candidate `cand` of the batch = "the runtime controller's tasks + one trajectory".

@@ -1,6 +1,6 @@
-"""get -> put chaining used by several tests: predict the get with the oracle, take the
-ranked-first candidate's final joint state, re-parent the object to the winning hand frame
-(what ConnectBodyConstraint leaves behind) and return a scene ready for `put`."""
+"""get -> put chaining used by several tests: predict the get with the oracle, and bring the
+scene into the state the rollout of candidate 0 leaves behind (object re-parented to the hand
+frame at the grasp step, joints at their final values): a scene ready for `put` / `pour` / `drop`."""
 import affaction_b200 as ab
 import oracle_binding as ob
 
@@ -14,9 +14,7 @@ def scene_after_get(obj, require_success=True):
     opts = ab.default_opts(log_q=True)
     r, q = ob.predict(scene, b, 0, opts, log_q=True)
     assert r.success == 1 or not require_success
-    cons = list((ab.Constraint * b.n_constraints).from_address(b.constraints_ptr))
-    c0 = list((ab.Candidate * b.n_candidates).from_address(b.candidates_ptr))[0]
-    conn = [c for c in cons[c0.first_constraint:c0.first_constraint + c0.n_constraints] if c.kind == 2][0]
-    scene.set_ik_state(q[-1])
-    scene.connect(scene.body_name(conn.body_a), scene.body_name(conn.body_b))
+    # the object is attached with the relative pose of the step the ConnectBodyConstraint fired in
+    # and then travels with the hand to the final joint state (Graph::applyRollout)
+    scene.apply_rollout(b, 0, q)
     return scene

@@ -44,8 +44,8 @@ def test_emulated_kernel_put_candidate(built):
     b = ab.HostBatch(scene)
     assert b.add_action("put italian_seasoning_bowl table") == 6
     opts = ab.default_opts(log_q=True)
-    ref, q_ref = ob.predict(scene, b, 2, opts, log_q=True)
-    (emu,), q_emu = eb.predict(scene, b, opts, first=2, count=1, log_q=True, n_steps=ref.n_steps - 1)
+    ref, q_ref = ob.predict(scene, b, 4, opts, log_q=True)        # the one candidate that collides
+    (emu,), q_emu = eb.predict(scene, b, opts, first=4, count=1, log_q=True, n_steps=ref.n_steps - 1)
     assert ref.code == -4
     assert emu.as_tuple() == ref.as_tuple()
     assert np.array_equal(q_emu[0], q_ref)

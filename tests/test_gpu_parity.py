@@ -348,3 +348,27 @@ def test_batches_with_different_footprints_coexist(scene):
     dev_big.launch()
     ref = ob.predict_batch(scene, big, ab.default_opts(), n_threads=8)
     assert [r.as_tuple() for r in dev_big.results()] == [r.as_tuple() for r in ref]
+
+
+def test_predict_sequence_chains_actions(built):
+    """BASELINE.json configs[3]: an action sequence predicted action by action, each from the state
+    the ranked-first candidate of the previous one leaves (examples/ExampleActionsECS.cpp:924-979)."""
+    from chain_util import scene_after_get
+    scene = ab.HostScene()
+    steps = scene.predict_sequence("get italian_seasoning_bowl; put italian_seasoning_bowl table; pose Default")
+    assert [n for _, n, _ in steps] == [2, 6, 1]
+    assert all(r.success == 1 for r, _, _ in steps) and all(m.startswith("SUCCESS") for _, _, m in steps)
+    # the same chain by hand, with the oracle: same winner records
+    manual = ab.HostScene()
+    for (rec, n, _), cmd in zip(steps, ("get italian_seasoning_bowl", "put italian_seasoning_bowl table", "pose Default")):
+        b = ab.HostBatch(manual)
+        assert b.add_action(cmd) == n
+        opts = ab.default_opts(log_q=True)
+        cands = [ob.predict(manual, b, i, opts, log_q=True) for i in range(n)]
+        best = ab.rank([c[0] for c in cands])[0]
+        assert rec.idx == best and rec.as_tuple() == cands[best][0].as_tuple()
+        manual.apply_rollout(b, best, cands[best][1])
+    # the sequence the scene file ships: the restated get of the bottle misses the tracking limit, so
+    # the rest of the queue is dropped, as the reference does after a failed action
+    shipped = ab.HostScene().predict_sequence("get tomato_sauce_bottle; pour tomato_sauce_bottle pizza_dough; put tomato_sauce_bottle shelf")
+    assert len(shipped) == 1 and shipped[0][0].success == 0 and "Reachability problem" in shipped[0][2]

@@ -275,3 +275,20 @@ def test_finger_push_tasks(scene):
                      ("finger_push oven table", "cannot be used to switch something on")):
         with pytest.raises(ab.AffError, match=msg):
             ab.HostBatch(scene).add_action(cmd)
+
+
+def test_apply_rollout_attaches_at_the_grasp_step(built):
+    """Graph::applyRollout: the object is re-parented with the relative pose of the step the
+    ConnectBodyConstraint fired in and then follows the hand: after `get` it sits in the hand,
+    liftHeight (0.12 m) above where it stood."""
+    import oracle_binding as ob
+    from chain_util import scene_after_get
+    before = ob.fk(ab.HostScene())
+    scene = scene_after_get("italian_seasoning_bowl")
+    after = ob.fk(scene)
+    bowl, hand = scene.body_id("italian_seasoning_bowl"), scene.body_id("hand_right_pincergrasp")
+    assert after[bowl, 2] - before[bowl, 2] == pytest.approx(0.12, abs=2e-3)
+    assert np.linalg.norm(after[bowl, :3] - after[hand, :3]) < 0.15 < np.linalg.norm(before[bowl, :3] - before[hand, :3])
+    # held: a second get of the same object is refused the way the reference words it
+    with pytest.raises(ab.AffError, match="already held|SUCCESS"):
+        ab.HostBatch(scene).add_action("get italian_seasoning_bowl")
