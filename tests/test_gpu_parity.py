@@ -372,3 +372,18 @@ def test_predict_sequence_chains_actions(built):
     # the rest of the queue is dropped, as the reference does after a failed action
     shipped = ab.HostScene().predict_sequence("get tomato_sauce_bottle; pour tomato_sauce_bottle pizza_dough; put tomato_sauce_bottle shelf")
     assert len(shipped) == 1 and shipped[0][0].success == 0 and "Reachability problem" in shipped[0][2]
+
+
+@pytest.mark.parametrize("dt,after,alpha,lam", [(0.02, 100, 0.05, 1.0e-6), (0.005, 0, 0.1, 1.0e-4)])
+def test_other_predictor_options_match_oracle(scene, dt, after, alpha, lam):
+    """Nothing in the kernel is tied to the default dt / after-steps / alpha / lambda."""
+    batch = ab.HostBatch(scene)
+    lib = ab.lib()
+    assert lib.aff_host_batch_add_action(batch.h, scene.h, b"get fresh_tomatoes", 1.0, dt) == 2
+    assert lib.aff_host_batch_add_action(batch.h, scene.h, b"get italian_seasoning_bowl", 1.0, dt) == 2
+    opts = ab.default_opts(log_q=True)
+    opts.dt, opts.n_after_steps, opts.alpha, opts.lam = dt, after, alpha, lam
+    dev = ab.DeviceBatch(scene, batch, opts)
+    dev.launch()
+    assert dev.num_steps(0) == int(round((10.0 + 5 * dt + 0.5) / dt)) + after      # tasks switch off 0.5 s after t_end
+    assert _compare(scene, batch, opts, dev, range(4)) == 0.0
