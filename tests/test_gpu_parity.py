@@ -387,3 +387,28 @@ def test_other_predictor_options_match_oracle(scene, dt, after, alpha, lam):
     dev.launch()
     assert dev.num_steps(0) == int(round((10.0 + 5 * dt + 0.5) / dt)) + after      # tasks switch off 0.5 s after t_end
     assert _compare(scene, batch, opts, dev, range(4)) == 0.0
+
+
+def test_invalid_initial_state_is_reported_like_the_oracle(built):
+    """check() before the first step (src/TrajectoryPredictor.cpp:135-140, 426-441): a start state
+    with a joint beyond its limit ends the rollout with zero steps, on the GPU as in the oracle."""
+    scene = ab.HostScene()
+    b = ab.HostBatch(scene)
+    b.add_action("pose Default")
+    opts = ab.default_opts(log_q=True)
+    _, q = ob.predict(scene, b, 0, opts, log_q=True)
+    start = q[0].copy()
+    finger = [j for j in range(scene.nJ) if "finger_1_right" in scene.joint_name(j)][0]
+    start[finger] = 5.0                                         # far beyond the finger's range
+    scene.set_ik_state(start)
+    batch = ab.HostBatch(scene)
+    n = batch.add_action("get fresh_tomatoes")
+    dev = ab.DeviceBatch(scene, batch, opts)
+    dev.launch()
+    gpu = dev.results()
+    for i in range(n):
+        ref, _ = ob.predict(scene, batch, i, opts)
+        assert ref.code == -6 and ref.n_steps == 0             # AFF_CODE_INITIAL_STATE
+        assert gpu[i].as_tuple() == ref.as_tuple()
+    _, msgs = batch.predict()
+    assert all(m.startswith("FATAL_ERROR: Initial state is invalid") for m in msgs)
