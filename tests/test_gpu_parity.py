@@ -412,3 +412,16 @@ def test_invalid_initial_state_is_reported_like_the_oracle(built):
         assert gpu[i].as_tuple() == ref.as_tuple()
     _, msgs = batch.predict()
     assert all(m.startswith("FATAL_ERROR: Initial state is invalid") for m in msgs)
+
+
+@pytest.mark.parametrize("cmd", ["get fresh_tomatoes duration 0.5", "get fresh_tomatoes duration 2", "get italian_seasoning_bowl duration 1.5",
+                                 "get tomato_sauce_bottle duration 30", "get fresh_tomatoes liftHeight 0.3"])
+def test_get_options_match_oracle(scene, cmd):
+    """Command options change the step count and the trajectory (too short a duration fails the
+    tracking limit within a few steps and the rollout still runs to its end; 30 s = 3555 steps)."""
+    batch = ab.HostBatch(scene)
+    n = batch.add_action(cmd)
+    opts = ab.default_opts(log_q=True)
+    dev = ab.DeviceBatch(scene, batch, opts)
+    dev.launch()
+    assert _compare(scene, batch, opts, dev, range(n)) == 0.0
