@@ -383,6 +383,13 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
       if (aTree) for (size_t j = 0; j < H.sbody.size(); ++j) if (H.sbody[j].explicit_bp && H.sbody[j].any_active0) addBodyPair((int)i, -1 - (int)j);
     }
     if (H.pairsSS.size() > AFFK_MAX_PAIRS || H.pairsSB.size() > AFFK_MAX_PAIRS) { err = "too many precompiled collision pairs"; return AFF_ERR_CAPACITY; }
+    // Pairs of the same storage kind (partner in shared memory / in the static tables) and the same need
+    // for a per-step liveness decision sit next to each other, so that most rounds of 32 take one side of
+    // those branches as a whole warp.  The order of the lists has no effect on the results (keyed minimum,
+    // costs summed in key order).
+    auto kindOf = [](const KPair& p) { return ((p.a >= 0) ? 0 : 1) | ((p.b >= 0) ? 0 : 2) | (((uint32_t)p.meta >> 31) ? 4 : 0); };
+    std::stable_sort(H.pairsSS.begin(), H.pairsSS.end(), [&](const KPair& x, const KPair& y) { return kindOf(x) < kindOf(y); });
+    std::stable_sort(H.pairsSB.begin(), H.pairsSB.end(), [&](const KPair& x, const KPair& y) { return kindOf(x) < kindOf(y); });
     if (H.dbody.size() > 31) { err = "too many dynamic shape bodies"; return AFF_ERR_CAPACITY; }
   }
 
