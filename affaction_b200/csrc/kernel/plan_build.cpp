@@ -312,7 +312,17 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     sb.n_shapes = (int)dst.size() - sb.first_shape;
     if (sb.n_shapes > 0) (dynamicSide ? H.dbody : H.sbody).push_back(sb);
   };
-  for (int b = 0; b < nB; ++b) if (shapeBody[b]) addShapes(b, dynamicB[b] != 0);
+  // dynamic bodies in body order; static bodies with the ones the per-step AABB test looks at first
+  // (not explicit, some shape active from the start), so that the test loops over a prefix only
+  auto nearCandidate = [&](int b) {
+    if (S.explicitBp[b]) return false;
+    for (int k = 0; k < S.nShapes[b]; ++k) if (S.sdist[S.firstShape[b] + k]) return true;
+    return false;
+  };
+  for (int b = 0; b < nB; ++b) if (shapeBody[b] && dynamicB[b]) addShapes(b, true);
+  for (int b = 0; b < nB; ++b) if (shapeBody[b] && !dynamicB[b] && nearCandidate(b)) addShapes(b, false);
+  P.nStatNear = (int)H.sbody.size();
+  for (int b = 0; b < nB; ++b) if (shapeBody[b] && !dynamicB[b] && !nearCandidate(b)) addShapes(b, false);
   if ((int)H.dshape.size() > AFFK_MAX_DSHAPE || (int)H.dbody.size() > AFFK_MAX_DBODY) { err = "too many dynamic shapes"; return AFF_ERR_CAPACITY; }
   // ---- precompiled shape pairs of the collision model, by type.  A body pair is listed when it can
   // ever be live without the AABB test: two dynamic bodies that are (or may come to be) in different
@@ -389,7 +399,9 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     // costs summed in key order).
     auto kindOf = [](const KPair& p) { return ((p.a >= 0) ? 0 : 1) | ((p.b >= 0) ? 0 : 2) | (((uint32_t)p.meta >> 31) ? 4 : 0); };
     std::stable_sort(H.pairsSS.begin(), H.pairsSS.end(), [&](const KPair& x, const KPair& y) { return kindOf(x) < kindOf(y); });
-    std::stable_sort(H.pairsSB.begin(), H.pairsSB.end(), [&](const KPair& x, const KPair& y) { return kindOf(x) < kindOf(y); });
+    // segment-box before segment-cylinder (the cylinder distance is an iteration: keep it out of box rounds)
+    auto kindSB = [&](const KPair& p) { const int t = (p.b >= 0) ? H.dshape[p.b].type : H.sshape[-1 - p.b].type; return kindOf(p) | (t == AFF_SHAPE_CYLINDER ? 8 : 0); };
+    std::stable_sort(H.pairsSB.begin(), H.pairsSB.end(), [&](const KPair& x, const KPair& y) { return kindSB(x) < kindSB(y); });
     if (H.dbody.size() > 31) { err = "too many dynamic shape bodies"; return AFF_ERR_CAPACITY; }
   }
 

@@ -888,10 +888,10 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
   w_sync();
   // 4. static bodies that are not explicit: two-level AABB test (tree box, then tree bodies)
   int nLive = 0;
-  for (int base = 0; base < P.nStatBodies; base += 32) {
+  for (int base = 0; base < P.nStatNear; base += 32) {
     const int i = base + lane;
     int near = 0;
-    if (i < P.nStatBodies && ldg(&P.sbody[i].explicit_bp) == 0 && ldg(&P.sbody[i].any_active0)) {
+    if (i < P.nStatNear) {          // the plan lists the bodies this test applies to first
       double bb[6];
       for (int q = 0; q < 6; ++q) bb[q] = ldg(&P.sbodyAABB[6 * i + q]);
       for (int t = 0; t < P.nTrees; ++t) if (k_aabb_overlap(taabb + 6 * t, bb, thr)) near = 1;
