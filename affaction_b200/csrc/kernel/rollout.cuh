@@ -1394,6 +1394,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
       double t = 0.0;
       if (lane >= j && lane < m) {
         t = L[lane * LS + j];
+#pragma unroll 4
         for (int k = 0; k < j; ++k) t = fma(-L[lane * LS + k], L[j * LS + k], t);
       }
       const double sdiag = w_shfl(t, j);
