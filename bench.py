@@ -45,7 +45,7 @@ L2_FLUSH_BYTES = 256 << 20
 # candidate tables read once (tasks, via points, activations, graph constraints, candidate record) + 88-byte verdict
 ALGORITHMIC_BYTES_PER_ROLLOUT = 2300 + 88
 # dram__bytes_read.sum + dram__bytes_write.sum of one aff_rollout_kernel launch / rollouts in it (profiles/r1_summary.md)
-NCU_DRAM_BYTES_PER_ROLLOUT = 5320
+NCU_DRAM_BYTES_PER_ROLLOUT = 2758
 
 
 def algorithmic_flops_per_rollout():
@@ -292,7 +292,7 @@ def run_cuda(args, rank, local_rank, world):
             "gpu_launches": launches * world,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None,
                          "traffic": NCU_DRAM_BYTES_PER_ROLLOUT * per_launch, "traffic_unit": "bytes per launch (dram read + write, "
-                         "ncu --set full capture profiles/r1_summary.md: 5.3 KB per rollout) - FP64 work does not scale with it",
+                         "ncu --set full capture profiles/r1_summary.md: 2.76 KB per rollout) - FP64 work does not scale with it",
                          "kernel": "aff_rollout_kernel",
                          "flops_per_rollout": algorithmic_flops_per_rollout(), "peak_source": "DFMA microbenchmark measured in this run "
                          "(MEASURED_PEAKS.json holds no FP64 figure)", "kernel_ms_per_step": sum(kernel_ms) / len(kernel_ms)},
