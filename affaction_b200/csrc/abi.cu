@@ -49,8 +49,11 @@ __global__ void __launch_bounds__(32) aff_prologue_kernel(const KPlan P)
 }
 
 // Persistent rollout kernel: one warp per candidate, warps stride over the batch.
+#ifndef AFF_LAUNCH_BOUNDS
+#define AFF_LAUNCH_BOUNDS __launch_bounds__(32 * AFF_WARPS_PER_BLOCK, AFF_BLOCKS_PER_SM)
+#endif
 #define AFF_ROLLOUT_KERNEL(NAME, NS)                                                                                       \
-  __global__ void __launch_bounds__(32 * AFF_WARPS_PER_BLOCK, AFF_BLOCKS_PER_SM) NAME(const KPlan P)                      \
+  __global__ void AFF_LAUNCH_BOUNDS NAME(const KPlan P)                      \
   {                                                                                                                      \
     extern __shared__ double smem[];                                                                                     \
     const int warp = threadIdx.x >> 5;                                                                                   \
