@@ -754,8 +754,6 @@ AFF_DEV double k_pair_distance(const KCtx& c, int ia, int ib)
 #define KP_SLOT_A(m) ((m) & 3)
 #define KP_SLOT_B(m) (((m) >> 2) & 3)
 #define KP_SWAP(m) (((m) >> 4) & 1)
-#define KP_GROUP(m) (((m) >> 5) & 7)       /* followers that belong to this leader */
-#define KP_FOLLOWER(m) (((m) >> 8) & 1)
 #define KP_TREE_A(m) ((int)(((m) >> 9) & 15) - 1)
 #define KP_TREE_B(m) ((int)(((m) >> 13) & 15) - 1)
 #define KP_EXPL_A(m) (((m) >> 17) & 1)
