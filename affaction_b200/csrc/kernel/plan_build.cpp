@@ -248,7 +248,7 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     // per-lane FK table
     const int nR = (int)H.rounds.size() / 2;
     KFkEntry idle; std::memset(&idle, 0, sizeof(idle));
-    H.fktab.assign((size_t)nR * 32, idle);
+    H.fktab.assign((size_t)nR * 32, idle);   // idle lanes get their destination (the spare element) in patchFkAux
     P.fk_obj_rounds[0] = P.fk_obj_rounds[1] = P.fk_const_rounds[0] = P.fk_const_rounds[1] = 0u;
     for (int r = 0; r < nR; ++r)
       for (int grp = 0; grp < 2; ++grp) {
@@ -262,9 +262,11 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
           const int row = e < 3 ? -1 : (e - 3) / 3, col = e < 3 ? e : (e - 3) % 3;
           const int tb = e < 3 ? 0 : 3 + 3 * row;
           en.t0 = nd.T[tb]; en.t1 = nd.T[tb + 1]; en.t2 = nd.T[tb + 2];
-          uint32_t op = 2, partner = (uint32_t)lane, pbase = (uint32_t)(12 * pslot), dst = (uint32_t)(12 * n + e), w1 = 0;
-          if (nd.kind == AFFK_NODE_OBJECT) { op = 6; w1 = (uint32_t)(nd.qidx & 3) | ((uint32_t)n << 8); P.fk_obj_rounds[(r >> 5) & 1] |= 1u << (r & 31); }
-          else if (nd.kind == AFFK_NODE_FIXED) { if (nd.identityT) { op = 1; pbase = (uint32_t)(12 * pslot + e); } }
+          // aux (w1 bits 16-27): index of the lane's extra operand, filled in once the layout is known
+          // (patchFkAux below); until then it holds the element relative to the node array for COPY
+          uint32_t op = 2, partner = (uint32_t)lane, pbase = (uint32_t)(12 * pslot), dst = (uint32_t)(12 * n + e), w1 = 0, aux = 0;
+          if (nd.kind == AFFK_NODE_OBJECT) { op = 6; pbase = 0; w1 = (uint32_t)(nd.qidx & 3) | ((uint32_t)n << 8); P.fk_obj_rounds[(r >> 5) & 1] |= 1u << (r & 31); }
+          else if (nd.kind == AFFK_NODE_FIXED) { if (nd.identityT) { op = 1; pbase = 0; aux = (uint32_t)(12 * pslot + e); } }
           else {
             const bool isRot = nd.jtype >= AFF_JNT_ROT_X;
             const int d = isRot ? nd.jtype - AFF_JNT_ROT_X : nd.jtype;
@@ -273,9 +275,14 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
               if (row == a) { op = 3; partner = (uint32_t)(grp * 12 + 3 + 3 * b + col); }
               else if (row == b) { op = 4; partner = (uint32_t)(grp * 12 + 3 + 3 * a + col); }
             } else if (!isRot && e < 3) { op = 5; partner = (uint32_t)(grp * 12 + 3 + 3 * d + e); }
-            w1 = (nd.kind == AFFK_NODE_JOINT_IK) ? (uint32_t)(nd.qidx & 63) : (0x80u | ((uint32_t)n << 8));
-            if (nd.kind != AFFK_NODE_JOINT_IK) P.fk_const_rounds[(r >> 5) & 1] |= 1u << (r & 31);
+            // only the lanes that apply the joint carry its index; the others stay plain compositions
+            if (op != 2) {
+              w1 = (nd.kind == AFFK_NODE_JOINT_IK) ? (uint32_t)(nd.qidx & 63) : (0x80u | ((uint32_t)n << 8));
+              if (nd.kind != AFFK_NODE_JOINT_IK) P.fk_const_rounds[(r >> 5) & 1] |= 1u << (r & 31);
+            }
           }
+          if (aux > 4095u) { err = "FK table: node array too large"; return AFF_ERR_CAPACITY; }
+          w1 |= aux << 16;
           if (pbase > 4095u || dst > 4095u) { err = "FK table: node array too large"; return AFF_ERR_CAPACITY; }
           en.w0 = pbase | (dst << 12) | (op << 24) | (partner << 27);
           en.w1 = w1;
@@ -574,6 +581,21 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   P.nCands = (int)nCands;
   P.opts = opts;
 
+  // FK table, second pass: operands that depend on the layout (see KFkEntry in rollout.cuh)
+  auto patchFkAux = [&]() -> bool {
+    const uint32_t spare = (uint32_t)(12 * (P.nDyn + P.nStatPar));
+    for (KFkEntry& en : H.fktab) {
+      const uint32_t op = (en.w0 >> 24) & 7u;
+      uint32_t aux = (en.w1 >> 16) & 4095u;
+      if (op == 0) en.w0 = (en.w0 & ~(4095u << 12)) | (spare << 12);                 // idle: store to the spare element
+      else if (op == 1) aux += (uint32_t)P.o_node;                                    // COPY: parent element
+      else if (op >= 3 && op <= 5 && !(en.w1 & 0x80u)) aux = (uint32_t)((op == 5) ? P.o_q : P.o_sn) + (en.w1 & 63u);
+      if (aux > 4095u || spare > 4095u) return false;
+      en.w1 = (en.w1 & 0xF000FFFFu) | (aux << 16);
+    }
+    return true;
+  };
+
   // ---- shared-memory layout (doubles)
   int o = 0;
   auto take = [&](int n) { const int at = o; o += n; return at; };
@@ -600,11 +622,12 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     P.JS = AFFK_FIX_JS; P.LS = AFFK_FIX_LS;
     const int uIk = AFFK_FIX_IK_END - AFFK_FIX_o_scratch, uColl = AFFK_FIX_o_live + collTail - AFFK_FIX_o_scratch;
     P.o_node = AFFK_FIX_o_scratch + std::max(uTraj, std::max(uIk, uColl));
-    P.warp_doubles = (P.o_node + 12 * nSlots + 1) & ~1;
+    P.warp_doubles = (P.o_node + 12 * nSlots + 1 + 1) & ~1;         // + the spare element idle FK lanes store to
     H.smemBytesPerWarp = sizeof(double) * (size_t)P.warp_doubles;
+    if (!patchFkAux()) { err = "FK table: shared-memory index out of range"; return AFF_ERR_CAPACITY; }
     return AFF_OK;
   }
-  P.o_node = take(12 * nSlots);
+  P.o_node = take(12 * nSlots + 2);          // + the spare element idle FK lanes store to
   const int nJe = (S.nJ + 1) & ~1, xde = (std::max(H.maxXdim, 1) + 1) & ~1;
   P.o_q = take(nJe); P.o_qdot = take(nJe); P.o_dH = take(nJe); P.o_dq = take(nJe); P.o_sn = take(nJe); P.o_cs = take(nJe);
   P.o_dx = take(xde);
@@ -628,6 +651,7 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   o = uBase + std::max(uTraj, std::max(uIk, uColl));
   P.warp_doubles = (o + 1) & ~1;
   H.smemBytesPerWarp = sizeof(double) * (size_t)P.warp_doubles;
+  if (!patchFkAux()) { err = "FK table: shared-memory index out of range"; return AFF_ERR_CAPACITY; }
   return AFF_OK;
 }
 

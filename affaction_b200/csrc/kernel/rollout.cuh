@@ -157,9 +157,11 @@ AFF_DEV void k_object_from_q6(const KCtx& c, int n, int slot)
 
 // FK table entry, one per (round, lane): everything lane `l` needs to produce its HTr element of
 // the node scheduled in its group this round (plan_build.cpp: buildFkTable).
-//   w0: bits 0-11 parent element base (doubles from the node array), 12-23 destination element,
-//       24-26 op, 27-31 partner lane
-//   w1: bits 0-5 jacobi index (IK joints) | bits 8-15 dynamic node (constant joints, objects)
+//   w0: bits 0-11 parent node base (doubles from the node array; 0 unless the lane composes), 12-23
+//       destination element (idle lanes: the spare element behind the array), 24-26 op, 27-31 partner lane
+//   w1: bits 0-5 jacobi index (IK joints; object slot for objects) | bit 7 constant joint | bits 8-15
+//       dynamic node (constant joints, objects) | bits 16-27 shared-memory index of the lane's extra
+//       operand: the parent's element (COPY), q or sin(q) of the joint (IK joints), else 0
 //   t0..t2: the three entries of the node's fixed transform this lane multiplies with
 // Element e of T o P:  org: P[e] + T0 P[3+e] + T1 P[6+e] + T2 P[9+e];  rot(i,j): T[i][0] P[3+j] + T[i][1] P[6+j] + T[i][2] P[9+j]
 #define FKOP_IDLE 0
@@ -184,30 +186,36 @@ AFF_DEV void k_fk(const KCtx& c, bool init)
   const int e = lane % 12;
   const int col = (e < 3) ? e : (e - 3) % 3, eo = (e < 3) ? e : 0;
   const KFkEntry* tab = P.fktab + lane;
+  const unsigned long long constRounds = ((unsigned long long)P.fk_const_rounds[1] << 32) | P.fk_const_rounds[0];
+  const unsigned long long objRounds = ((unsigned long long)P.fk_obj_rounds[1] << 32) | P.fk_obj_rounds[0];
+  const int scratchDst = 12 * (P.nDyn + P.nStatPar);      // one spare element behind the node array
   for (int r = 0; r < P.nRounds; ++r, tab += 32) {
     const KFkEntry en = ldg_fk(tab);
     const int op = (int)((en.w0 >> 24) & 7u);
-    const int pbase = (int)(en.w0 & 4095u), dst = (int)((en.w0 >> 12) & 4095u);
+    const int pbase = (int)(en.w0 & 4095u);               // parent node (0 for lanes that do not compose)
+    int dst = (int)((en.w0 >> 12) & 4095u);                // idle lanes: the spare element
     const int partner = (int)(en.w0 >> 27);
-    // The common operations are straight-line code with selects (lanes that do not need a value read
-    // element 0 of the node array instead); objects and constant joints under a moving parent take a
-    // warp-uniform branch, which most rounds skip.
-    const bool compose = (op >= FKOP_FIXED) && (op <= FKOP_TRANS);
-    const bool jointed = (op > FKOP_FIXED) && (op <= FKOP_TRANS);
-    const double* Pp = nodes + (compose ? pbase : 0);           // pbase points at the parent node
+    const int aux = (int)((en.w1 >> 16) & 4095u);          // COPY: the parent's element; joints: q / sin entry; else 0
+    const int qi = (int)(en.w1 & 63u);
+    // The common operations are straight-line code: every lane reads its operands from addresses the
+    // table made valid for it, computes all variants and selects; objects and constant joints under a
+    // moving parent sit in rounds the plan has flagged.
+    const double* Pp = nodes + pbase;
     const double p0 = Pp[eo], p3 = Pp[3 + col], p6 = Pp[6 + col], p9 = Pp[9 + col];
-    const double cp = nodes[(op == FKOP_COPY) ? pbase : 0];     // pbase points at the parent element
+    const double x = c.sm[aux];
     const double acc0 = (e < 3) ? p0 : 0.0;
     const double comp = fma(en.t2, p9, fma(en.t1, p6, fma(en.t0, p3, acc0)));
-    double val = (op == FKOP_COPY) ? cp : (compose ? comp : 0.0);
-    const bool constJoint = jointed && (en.w1 & 0x80u) != 0u;
-    const int qi = (jointed && !constJoint) ? (int)(en.w1 & 63u) : 0;
-    double s = (op == FKOP_TRANS) ? q[qi] : sn[qi], co = cs[qi];
-    bool store = op != FKOP_IDLE;
-    if ((P.fk_const_rounds[(r >> 5) & 1] >> (r & 31)) & 1u) {          // warp-uniform: known to the plan
-      if (constJoint) { const int n = (int)((en.w1 >> 8) & 255u); s = ldg(&P.dynSC[2 * n]); co = ldg(&P.dynSC[2 * n + 1]); if (op == FKOP_TRANS) s = ldg(&P.dynQ[n]); }
+    const bool compose = (op >= FKOP_FIXED) && (op <= FKOP_TRANS);
+    double val = (op == FKOP_COPY) ? x : (compose ? comp : 0.0);
+    double s = x, co = cs[qi];
+    if ((constRounds >> r) & 1ull) {
+      if (op > FKOP_FIXED && op <= FKOP_TRANS && (en.w1 & 0x80u)) {
+        const int n = (int)((en.w1 >> 8) & 255u);
+        s = (op == FKOP_TRANS) ? ldg(&P.dynQ[n]) : ldg(&P.dynSC[2 * n]);
+        co = ldg(&P.dynSC[2 * n + 1]);
+      }
     }
-    if ((P.fk_obj_rounds[(r >> 5) & 1] >> (r & 31)) & 1u) {
+    if ((objRounds >> r) & 1ull) {
       if (op == FKOP_OBJECT) {
         const int slot = (int)(en.w1 & 3u), n = (int)((en.w1 >> 8) & 255u);
         if ((c.objHasRel >> slot) & 1u) {
@@ -217,7 +225,7 @@ AFF_DEV void k_fk(const KCtx& c, bool init)
           const double a0 = (e < 3) ? Po[e] : 0.0;
           val = fma(R[tb + 2], Po[9 + col], fma(R[tb + 1], Po[6 + col], fma(R[tb], Po[3 + col], a0)));
         } else {
-          store = false;
+          dst = scratchDst;
           if ((init || OBJ_GET(c, objParentDynamic, slot)) && e == 0) k_object_from_q6(c, n, slot);
         }
       }
@@ -225,7 +233,7 @@ AFF_DEV void k_fk(const KCtx& c, bool init)
     const double other = w_shfl(val, partner);
     const double rotA = fma(s, other, co * val), rotB = fma(co, val, -(s * other)), trn = fma(s, other, val);
     val = (op == FKOP_ROT_A) ? rotA : ((op == FKOP_ROT_B) ? rotB : ((op == FKOP_TRANS) ? trn : val));
-    if (store) nodes[dst] = val;
+    nodes[dst] = val;
     w_sync();
   }
 }
