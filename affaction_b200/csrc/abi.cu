@@ -57,7 +57,10 @@ __global__ void __launch_bounds__(32) aff_prologue_kernel(const KPlan P)
   {                                                                                                                      \
     extern __shared__ double smem[];                                                                                     \
     const int warp = threadIdx.x >> 5;                                                                                   \
-    double* sm = smem + (size_t)warp * P.warp_doubles;                                                                   \
+    /* the warp's offset is made opaque: otherwise the compiler re-derives it from threadIdx at every use (13 instructions) */ \
+    unsigned smIdx = (unsigned)warp * (unsigned)P.warp_doubles;                                                          \
+    asm volatile("" : "+r"(smIdx));                                                                                     \
+    double* sm = smem + smIdx;                                                                                           \
     const int warpsTotal = gridDim.x * AFF_WARPS_PER_BLOCK;                                                              \
     for (int cand = blockIdx.x * AFF_WARPS_PER_BLOCK + warp; cand < P.nCands; cand += warpsTotal) {                      \
       NS::k_rollout(P, cand, sm);                                                                                        \
