@@ -799,14 +799,14 @@ AFF_DEV bool k_pair_live(const KCtx& c, int meta, const double* baabb, double th
 // threshold (rare) are appended to a scratch list for the ordered cost sum.
 struct KPairAcc { double best; int bestKey; int nCostly; };
 
-AFF_DEV void k_pair_account(KPairAcc& acc, bool on, double d, int key, double thr, int* ckey, double* cdist)
+AFF_DEV void k_pair_account(KPairAcc& acc, int lane, bool on, double d, int key, double thr, int* ckey, double* cdist)
 {
   if (on && (d < acc.best || (d == acc.best && key < acc.bestKey))) { acc.best = d; acc.bestKey = key; }
   const int costly = on && thr > 0.0 && d < thr;
   const unsigned m = w_ballot(costly);
   if (m) {
     if (costly) {
-      const int pos = acc.nCostly + w_popc(m & ((1u << w_lane()) - 1u));
+      const int pos = acc.nCostly + w_popc(m & ((1u << lane) - 1u));
       if (pos < 32) { ckey[pos] = key; cdist[pos] = d; }
     }
     acc.nCostly += w_popc(m);
@@ -950,7 +950,7 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
         }
       }
     }
-    k_pair_account(acc, on, d, key, thr, ckey, cdist);
+    k_pair_account(acc, lane, on, d, key, thr, ckey, cdist);
   }
   // 5b. segment - box and segment - cylinder (the segment is always the first argument)
   for (int base = 0; base < P.nSB; base += 32) {
@@ -992,7 +992,7 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
         }
       }
     }
-    k_pair_account(acc, on, d, key, thr, ckey, cdist);
+    k_pair_account(acc, lane, on, d, key, thr, ckey, cdist);
   }
   // 5c. pairs found by the AABB test (rare)
   for (int base = 0; base < nLive; base += 32) {
@@ -1006,7 +1006,7 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
       const int b1 = bodyA < bodyB ? bodyA : bodyB, b2 = bodyA < bodyB ? bodyB : bodyA;
       key = (b1 << 15) | b2;
     }
-    k_pair_account(acc, i < nLive, d, key, thr, ckey, cdist);
+    k_pair_account(acc, lane, i < nLive, d, key, thr, ckey, cdist);
   }
   KCollResult res;
   double best = acc.best; int bestKey = acc.bestKey;

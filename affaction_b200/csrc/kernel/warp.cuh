@@ -29,7 +29,8 @@ static inline int w_ffs(unsigned v) { return __builtin_ffs((int)v); }
 
 #define AFF_DEV __device__ __forceinline__
 #define AFF_NOINLINE __device__ __noinline__
-AFF_DEV int w_lane() { return (int)(threadIdx.x & 31u); }
+// opaque: kept in a register instead of being re-read from the special register at every use
+AFF_DEV int w_lane() { int l = (int)(threadIdx.x & 31u); asm volatile("" : "+r"(l)); return l; }
 AFF_DEV void w_sync() { __syncwarp(); }
 AFF_DEV double w_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 AFF_DEV int w_shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
