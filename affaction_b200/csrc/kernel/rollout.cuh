@@ -490,10 +490,9 @@ AFF_DEV unsigned k_task_J(const KCtx& c, const KJointFrame& jf, const int* td, c
   unsigned nz = 0u;
   if (kind <= AFF_TASK_Z) {
     double te[3], re[3], tr[3], rr[3], tf[3], rf[3], cr[3], cl[3], out[3];
-    const double zero[3] = {0.0, 0.0, 0.0};
     k_jac_cols(c, jf, eff, geo, te, re);
     k_jac_cols(c, jf, ref, geo + 3, tr, rr);
-    k_jac_cols(c, jf, frame, (frame >= 0) ? k_slot(c, frame) : zero, tf, rf);
+    k_jac_cols(c, jf, frame, k_slot(c, frame >= 0 ? frame : 0), tf, rf);      // without a frame the point is not read
     k_cross(cr, geo + 6, rf);
     for (int k = 0; k < 3; ++k) cl[k] = (te[k] - tr[k]) + cr[k];
     if (frame >= 0) k_mulv(out, k_slot(c, frame) + 3, cl);
