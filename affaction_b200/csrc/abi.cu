@@ -57,12 +57,12 @@ __global__ void __launch_bounds__(32) aff_prologue_kernel(const KPlan P)
   {                                                                                                                      \
     extern __shared__ double smem[];                                                                                     \
     const int warp = threadIdx.x >> 5;                                                                                   \
-    /* The warp's base pointer is made opaque (otherwise it is re-derived from threadIdx and the shared window \
-       at every use, 13+ instructions each time) and declared to point into shared memory, so that accesses   \
-       stay LDS / STS on a register that is simply kept. */                                                    \
-    double* sm = smem + (size_t)warp * P.warp_doubles;                                                                   \
-    asm volatile("" : "+l"(sm));                                                                                        \
-    __builtin_assume(__isShared(sm));                                                                                    \
+    /* The warp's base is kept as an opaque 32-bit shared-memory address (otherwise it is re-derived from    \
+       threadIdx and the shared window at every use, 13+ instructions each time); the pointer made from it   \
+       is known to the compiler as a shared-memory pointer, so accesses stay LDS / STS. */                   \
+    unsigned smAddr = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)warp * (unsigned)P.warp_doubles * 8u;        \
+    asm volatile("" : "+r"(smAddr));                                                                                    \
+    double* sm = (double*)__cvta_shared_to_generic((size_t)smAddr);                                                      \
     const int warpsTotal = gridDim.x * AFF_WARPS_PER_BLOCK;                                                              \
     for (int cand = blockIdx.x * AFF_WARPS_PER_BLOCK + warp; cand < P.nCands; cand += warpsTotal) {                      \
       NS::k_rollout(P, cand, sm);                                                                                        \
