@@ -186,8 +186,7 @@ AFF_DEV void k_fk(const KCtx& c, bool init)
   const int e = lane % 12;
   const int col = (e < 3) ? e : (e - 3) % 3, eo = (e < 3) ? e : 0;
   const KFkEntry* tab = P.fktab + lane;
-  const unsigned long long constRounds = ((unsigned long long)P.fk_const_rounds[1] << 32) | P.fk_const_rounds[0];
-  const unsigned long long objRounds = ((unsigned long long)P.fk_obj_rounds[1] << 32) | P.fk_obj_rounds[0];
+  unsigned constRounds = P.fk_const_rounds[0], objRounds = P.fk_obj_rounds[0];   // bit 0 = this round
   const int scratchDst = 12 * (P.nDyn + P.nStatPar);      // one spare element behind the node array
   for (int r = 0; r < P.nRounds; ++r, tab += 32) {
     const KFkEntry en = ldg_fk(tab);
@@ -208,14 +207,15 @@ AFF_DEV void k_fk(const KCtx& c, bool init)
     const bool compose = (op >= FKOP_FIXED) && (op <= FKOP_TRANS);
     double val = (op == FKOP_COPY) ? x : (compose ? comp : 0.0);
     double s = x, co = cs[qi];
-    if ((constRounds >> r) & 1ull) {
+    if (r == 32) { constRounds = P.fk_const_rounds[1]; objRounds = P.fk_obj_rounds[1]; }
+    if (constRounds & 1u) {
       if (op > FKOP_FIXED && op <= FKOP_TRANS && (en.w1 & 0x80u)) {
         const int n = (int)((en.w1 >> 8) & 255u);
         s = (op == FKOP_TRANS) ? ldg(&P.dynQ[n]) : ldg(&P.dynSC[2 * n]);
         co = ldg(&P.dynSC[2 * n + 1]);
       }
     }
-    if ((objRounds >> r) & 1ull) {
+    if (objRounds & 1u) {
       if (op == FKOP_OBJECT) {
         const int slot = (int)(en.w1 & 3u), n = (int)((en.w1 >> 8) & 255u);
         if ((c.objHasRel >> slot) & 1u) {
@@ -234,6 +234,7 @@ AFF_DEV void k_fk(const KCtx& c, bool init)
     const double rotA = fma(s, other, co * val), rotB = fma(co, val, -(s * other)), trn = fma(s, other, val);
     val = (op == FKOP_ROT_A) ? rotA : ((op == FKOP_ROT_B) ? rotB : ((op == FKOP_TRANS) ? trn : val));
     nodes[dst] = val;
+    constRounds >>= 1; objRounds >>= 1;
     w_sync();
   }
 }
