@@ -12,7 +12,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libaffpredict.so")
+# AFF_LIB_PATH: tuning experiments only (tools/try_variants.sh builds alternative libraries)
+LIB_PATH = os.environ.get("AFF_LIB_PATH") or os.path.join(_HERE, "libaffpredict.so")
 DATA_DIR = os.path.join(_HERE, "data")
 PIZZA_SCENE = os.path.join(DATA_DIR, "pizza.affscene")
 

@@ -22,8 +22,12 @@
 #include "kernel/warp.cuh"
 // The kernel source twice (see the head of rollout.cuh): offsets read from the plan, and the fixed layout
 // with compile-time offsets that the plan compiler picks for every batch within its caps.
+#ifndef AFF_SWEEP_NO_BLOCK_SYNC
+#define AFFT_BLOCK_SYNC 1
+#endif
 namespace kgeneric {
 #include "kernel/rollout.cuh"
+#include "kernel/sweep.cuh"
 }
 #define AFFK_FIXED_LAYOUT 1
 namespace kfixed {
@@ -71,6 +75,25 @@ __global__ void __launch_bounds__(32) aff_prologue_kernel(const KPlan P)
   }
 AFF_ROLLOUT_KERNEL(aff_rollout_kernel, kfixed)            // batches in the fixed layout (KPlan::fixed_layout)
 AFF_ROLLOUT_KERNEL(aff_rollout_kernel_generic, kgeneric)  // anything larger
+
+// Thread-per-candidate kernel (sweep.cuh): thread i runs candidate sweep_order[i]; 32 rollouts per warp.
+// 512 threads x 2 blocks per SM = 32 warps = 1024 rollouts per SM (64 registers per thread; measured
+// round 2: 32 warps / SM in barrier groups of 16 beat 8 / 16 warps and smaller groups)
+#ifndef AFF_SWEEP_THREADS
+#define AFF_SWEEP_THREADS 512
+#endif
+#ifndef AFF_SWEEP_MIN_BLOCKS
+#define AFF_SWEEP_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(AFF_SWEEP_THREADS, AFF_SWEEP_MIN_BLOCKS) aff_sweep_kernel(const __grid_constant__ KPlan P)
+{
+  const int i = blockIdx.x * AFF_SWEEP_THREADS + threadIdx.x;
+  // threads past the end of the batch shadow its last candidate (they take part in the block's barriers
+  // and write nothing)
+  const bool alive = i < P.nCands;
+  kgeneric::TState S;
+  kgeneric::t_rollout(P, __ldg(&P.sweep_order[alive ? i : P.nCands - 1]), S, alive);
+}
 
 // Register-resident DFMA chains: the FP64 roofline denominator.
 __global__ void aff_dfma_peak_kernel(double* out, int iters)
@@ -120,7 +143,7 @@ struct aff_batch
   KPlan plan{};
   DevBuf<double> jq_init, jq0, jq_min, jq_max, jspeed, jacc, jwjl, jwmetric, obj_q6, statA, statSC, dynSC, sshapeA, sbodyAABB, qlog;
   DevBuf<KFkEntry> fktab;
-  DevBuf<int32_t> j_node, j_type, statpar_ref, obj_parent_slot, obj_parent_tree, dyn_under, obj_node, obj_body;
+  DevBuf<int32_t> j_node, j_type, statpar_ref, obj_parent_slot, obj_parent_tree, dyn_under, obj_node, obj_body, dyn_pslot, sweep_order;
   DevBuf<uint32_t> dyn_chain;
   DevBuf<double> dynT, dynQ;
   DevBuf<KPair> pairsSS, pairsSB;
@@ -132,14 +155,15 @@ struct aff_batch
   DevBuf<aff_result> results;
   int grid = 0; size_t smemBytes = 0; int launches = 0;
   size_t h2dBytes = 0;
-  bool prologueDone = false, useFixed = false;
+  bool prologueDone = false, useFixed = false, useSweep = false;
+  int sweepGrid = 0;
   cudaStream_t lastStream = nullptr; bool launched = false;
   void release()
   {
     jq_init.release(); jq0.release(); jq_min.release(); jq_max.release(); jspeed.release(); jacc.release(); jwjl.release();
     jwmetric.release(); obj_q6.release(); statA.release(); statSC.release(); dynSC.release(); sshapeA.release();
     sbodyAABB.release(); qlog.release(); j_node.release(); j_type.release(); fktab.release(); statpar_ref.release(); obj_parent_slot.release(); obj_parent_tree.release(); dyn_under.release(); dyn_chain.release(); dynT.release(); dynQ.release(); pairsSS.release(); pairsSB.release(); sseg.release();
-    obj_node.release(); obj_body.release(); dyn.release(); stat.release(); dshape.release(); sshape.release();
+    obj_node.release(); obj_body.release(); dyn_pslot.release(); sweep_order.release(); dyn.release(); stat.release(); dshape.release(); sshape.release();
     dbody.release(); sbody.release(); tasks.release(); vias.release(); acts.release(); gcons.release(); cands.release();
     results.release();
   }
@@ -198,7 +222,7 @@ static int uploadBatch(aff_batch* b, cudaStream_t st)
   P = H.plan;
 #define UP(name) do { CUDA_TRY(b->name.upload(H.name, st)); b->h2dBytes += H.name.size() * sizeof(H.name[0]); } while (0)
   UP(jq_init); UP(jq0); UP(jq_min); UP(jq_max); UP(jspeed); UP(jacc); UP(jwjl); UP(jwmetric); UP(obj_q6);
-  UP(j_node); UP(j_type); UP(fktab); UP(statpar_ref); UP(obj_parent_slot); UP(obj_parent_tree); UP(dyn_under); UP(dyn_chain); UP(dynT); UP(dynQ); UP(pairsSS); UP(pairsSB); UP(obj_node); UP(obj_body);
+  UP(j_node); UP(j_type); UP(fktab); UP(statpar_ref); UP(obj_parent_slot); UP(obj_parent_tree); UP(dyn_under); UP(dyn_chain); UP(dynT); UP(dynQ); UP(pairsSS); UP(pairsSB); UP(obj_node); UP(obj_body); UP(dyn_pslot); UP(sweep_order);
   UP(dyn); UP(stat); UP(dshape); UP(sshape); UP(dbody); UP(sbody);
   UP(tasks); UP(vias); UP(acts); UP(gcons); UP(cands);
 #undef UP
@@ -221,7 +245,7 @@ static int uploadBatch(aff_batch* b, cudaStream_t st)
   P.jacc = b->jacc.p; P.jwjl = b->jwjl.p; P.jwmetric = b->jwmetric.p; P.j_node = b->j_node.p; P.j_type = b->j_type.p;
   P.dyn = b->dyn.p; P.stat = b->stat.p; P.statA = b->statA.p; P.statSC = b->statSC.p; P.dynSC = b->dynSC.p; P.fktab = b->fktab.p; P.statpar_ref = b->statpar_ref.p; P.obj_parent_slot = b->obj_parent_slot.p; P.obj_parent_tree = b->obj_parent_tree.p; P.dyn_under = b->dyn_under.p; P.dyn_chain = b->dyn_chain.p; P.dynT = b->dynT.p; P.dynQ = b->dynQ.p;
   P.dshape = b->dshape.p; P.dbody = b->dbody.p; P.sshape = b->sshape.p; P.sbody = b->sbody.p; P.sshapeA = b->sshapeA.p;
-  P.sbodyAABB = b->sbodyAABB.p; P.pairsSS = b->pairsSS.p; P.pairsSB = b->pairsSB.p; P.sseg = b->sseg.p; P.obj_node = b->obj_node.p; P.obj_body = b->obj_body.p; P.obj_q6 = b->obj_q6.p;
+  P.sbodyAABB = b->sbodyAABB.p; P.pairsSS = b->pairsSS.p; P.pairsSB = b->pairsSB.p; P.sseg = b->sseg.p; P.obj_node = b->obj_node.p; P.obj_body = b->obj_body.p; P.obj_q6 = b->obj_q6.p; P.dyn_pslot = b->dyn_pslot.p; P.sweep_order = b->sweep_order.p;
   P.tasks = b->tasks.p; P.vias = b->vias.p; P.acts = b->acts.p; P.gcons = b->gcons.p; P.cands = b->cands.p;
   P.results = b->results.p;
   return AFF_OK;
@@ -253,6 +277,21 @@ int aff_batch_create(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, c
                  std::chrono::duration<double, std::milli>(tb2 - tb1).count(), b->h2dBytes / 1e6);
   }
   if (rc != AFF_OK) return rc;
+  // Kernel choice: one rollout per thread for every batch that fits its per-thread caps and has at least
+  // AFF_SWEEP_MIN candidates (default 1: measured faster than one rollout per warp at every size);
+  // AFF_KERNEL=warp / sweep forces one of the two (parity tests run both).
+  {
+    const char* force = getenv("AFF_KERNEL");
+    const char* mn = getenv("AFF_SWEEP_MIN");
+    const size_t minSweep = mn ? (size_t)atoll(mn) : 1;
+    b->useSweep = b->plan.sweep_ok && n_cands >= minSweep;
+    if (force && !strcmp(force, "warp")) b->useSweep = false;
+    if (force && !strcmp(force, "sweep")) {
+      if (!b->plan.sweep_ok) return fail(AFF_ERR_CAPACITY, "aff_batch_create: AFF_KERNEL=sweep but the batch exceeds the per-thread caps");
+      b->useSweep = true;
+    }
+    b->sweepGrid = (int)((n_cands + AFF_SWEEP_THREADS - 1) / AFF_SWEEP_THREADS);
+  }
   // launch geometry: persistent blocks, as many as fit per SM
   b->smemBytes = b->host.smemBytesPerWarp * AFF_WARPS_PER_BLOCK;
   // tuning experiments only (tools/try_variants.sh): extra dynamic shared memory per block, preferred carve-out in percent
@@ -306,7 +345,8 @@ int aff_batch_launch(aff_batch* b, void* stream)
     b->prologueDone = true;
     b->launches++;
   }
-  if (b->useFixed) aff_rollout_kernel<<<b->grid, 32 * AFF_WARPS_PER_BLOCK, b->smemBytes, st>>>(b->plan);
+  if (b->useSweep) aff_sweep_kernel<<<b->sweepGrid, AFF_SWEEP_THREADS, 0, st>>>(b->plan);
+  else if (b->useFixed) aff_rollout_kernel<<<b->grid, 32 * AFF_WARPS_PER_BLOCK, b->smemBytes, st>>>(b->plan);
   else aff_rollout_kernel_generic<<<b->grid, 32 * AFF_WARPS_PER_BLOCK, b->smemBytes, st>>>(b->plan);
   CUDA_TRY(cudaGetLastError());
   b->launches++;

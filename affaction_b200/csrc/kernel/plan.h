@@ -29,6 +29,20 @@
 #define AFFK_HORIZON 1.0       // trajectory horizon, src/ActionBase.cpp:137
 #define AFFK_VIA_LANES 16     // trajectory dimensions solved at the same time (8 would fit a fifth block per SM, but two passes cost more)
 
+// Caps of the per-thread state of the thread-per-candidate kernel (sweep.cuh); batches beyond them
+// run on the warp-per-candidate kernel.
+#ifndef AFFT_MAX_SLOTS
+#define AFFT_MAX_SLOTS 48      // dynamic nodes + copies of the static frames the loop refers to
+#define AFFT_MAX_TASKS 16
+#define AFFT_MAX_XDIM 24
+#define AFFT_MAX_DSHAPE 32
+#define AFFT_MAX_DBODY 24
+#define AFFT_MAX_TREES 6
+#endif
+#define AFFT_MAX_M AFFT_MAX_XDIM
+#define AFFT_MAX_NJ AFFK_MAX_NJ
+#define AFFT_MAX_COSTLY 32
+
 // node reference: >= 0 dynamic node, -1 world, <= -2 static node (-2 - idx)
 #define AFFK_WORLD (-1)
 #define AFFK_STATIC_REF(i) (-2 - (i))
@@ -173,6 +187,10 @@ struct KPlan
   const uint32_t* dyn_chain;       // [nDyn] IK joints moving each dynamic node by construction
   const int32_t* dyn_under;        // [nDyn] slot+1 if the node is a re-parentable object or below one
   int32_t nStatPar;
+  // thread-per-candidate ("sweep") kernel, sweep.cuh
+  const int32_t* dyn_pslot;        // [nDyn] slot of each dynamic node's parent (dynamic node or static-parent copy)
+  const int32_t* sweep_order;      // [nCands] candidates grouped by structure: thread i runs candidate sweep_order[i]
+  int32_t sweep_ok;                // the batch fits the per-thread caps of sweep.cuh
 
   const KShape* dshape; const KShapeBody* dbody;   // dynamic
   const KShape* sshape; const KShapeBody* sbody;   // static

@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <numeric>
+#include <unordered_map>
 
 namespace affk
 {
@@ -289,6 +291,9 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
         }
       }
   }
+  // parent slot of every dynamic node (thread-per-candidate FK walks the nodes in index order)
+  H.dyn_pslot.resize(H.dyn.size());
+  for (size_t n = 0; n < H.dyn.size(); ++n) H.dyn_pslot[n] = slotOfRef(H.dyn[n].parent);
   // objects below objects (a connect parent under another object) would need a dynamic schedule
   for (int b : objBodies) if (S.parent[b] >= 0 && underObj[S.parent[b]]) { err = "objects nested in objects are not supported"; return AFF_ERR_UNSUPPORTED; }
 
@@ -405,7 +410,8 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     // those branches as a whole warp.  The order of the lists has no effect on the results (keyed minimum,
     // costs summed in key order).
     auto kindOf = [](const KPair& p) { return ((p.a >= 0) ? 0 : 1) | ((p.b >= 0) ? 0 : 2) | (((uint32_t)p.meta >> 31) ? 4 : 0); };
-    std::stable_sort(H.pairsSS.begin(), H.pairsSS.end(), [&](const KPair& x, const KPair& y) { return kindOf(x) < kindOf(y); });
+    // within a kind, pairs of the same dynamic shape `a` follow each other (the thread-per-candidate kernel keeps its record in registers)
+    std::stable_sort(H.pairsSS.begin(), H.pairsSS.end(), [&](const KPair& x, const KPair& y) { return kindOf(x) != kindOf(y) ? kindOf(x) < kindOf(y) : x.a < y.a; });
     // segment-box before segment-cylinder (the cylinder distance is an iteration: keep it out of box rounds)
     auto kindSB = [&](const KPair& p) { const int t = (p.b >= 0) ? H.dshape[p.b].type : H.sshape[-1 - p.b].type; return kindOf(p) | (t == AFF_SHAPE_CYLINDER ? 8 : 0); };
     std::stable_sort(H.pairsSB.begin(), H.pairsSB.end(), [&](const KPair& x, const KPair& y) { return kindSB(x) < kindSB(y); });
@@ -426,10 +432,35 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     for (int k = 0; k < 6; ++k) H.obj_q6.push_back(S.qInit[S.firstJoint[b] + k]);
   }
 
-  // ---- tasks
-  H.tasks.resize(nTasksIn);
-  for (size_t i = 0; i < nTasksIn; ++i) {
-    const aff_task_desc& t = tasksIn[i];
+  // ---- tasks.  Candidates with byte-identical task slices (every perturbed candidate of one command and
+  // hand) share one copy: less to upload, and the lanes of a warp of the thread-per-candidate kernel
+  // read the same addresses (one broadcast load instead of 32).
+  std::vector<int32_t> taskBaseOf(nCands, 0);
+  std::vector<aff_task_desc> tasksUniq;
+  {
+    std::unordered_map<std::string, int32_t> seen;
+    int32_t lastIn = -1, lastN = -1, lastOut = -1;
+    for (size_t i = 0; i < nCands; ++i) {
+      const aff_candidate& c = candsIn[i];
+      if (lastOut >= 0 && c.n_tasks == lastN &&
+          (c.first_task == lastIn || std::memcmp(tasksIn + c.first_task, tasksIn + lastIn, sizeof(aff_task_desc) * (size_t)c.n_tasks) == 0)) {
+        taskBaseOf[i] = lastOut;
+        continue;
+      }
+      std::string key((const char*)(tasksIn + c.first_task), sizeof(aff_task_desc) * (size_t)c.n_tasks);
+      auto it = seen.find(key);
+      if (it == seen.end()) {
+        it = seen.emplace(std::move(key), (int32_t)tasksUniq.size()).first;
+        tasksUniq.insert(tasksUniq.end(), tasksIn + c.first_task, tasksIn + c.first_task + c.n_tasks);
+      }
+      taskBaseOf[i] = it->second;
+      lastIn = c.first_task; lastN = c.n_tasks; lastOut = it->second;
+    }
+  }
+  const size_t nTasksU = tasksUniq.size();
+  H.tasks.resize(nTasksU);
+  for (size_t i = 0; i < nTasksU; ++i) {
+    const aff_task_desc& t = tasksUniq[i];
     KTask& k = H.tasks[i];
     std::memset(&k, 0, sizeof(k));
     if (t.kind < AFF_TASK_XYZ || t.kind > AFF_TASK_JOINTS) { err = "unsupported task kind"; return AFF_ERR_UNSUPPORTED; }
@@ -462,11 +493,11 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     KCand& kc = H.cands[i];
     std::memset(&kc, 0, sizeof(kc));
     if (c.n_tasks > AFFK_MAX_TASKS) { err = "too many tasks in one candidate"; return AFF_ERR_CAPACITY; }
-    kc.first_task = c.first_task; kc.n_tasks = c.n_tasks;
+    kc.first_task = taskBaseOf[i]; kc.n_tasks = c.n_tasks;
     int xdim = 0;
     int toff[AFFK_MAX_TASKS + 1];
     for (int t = 0; t < c.n_tasks; ++t) {
-      KTask& k = H.tasks[c.first_task + t];
+      KTask& k = H.tasks[kc.first_task + t];
       k.xoff = xdim; toff[t] = xdim;
       xdim += (k.kind == AFF_TASK_XYZ) ? 3 : (k.kind == AFF_TASK_POLAR ? 2 : (k.kind == AFF_TASK_JOINTS ? k.n_joints : 1));
     }
@@ -580,6 +611,40 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   P.bp_threshold = S.bpThreshold;
   P.nCands = (int)nCands;
   P.opts = opts;
+
+  // ---- thread-per-candidate kernel: candidates grouped by structure, so that the 32 rollouts of a warp
+  // walk the same task list and switch / re-parent at the same steps (the values differ, the branches do not)
+  {
+    auto mix = [](uint64_t h, uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); return h; };
+    auto bitsOf = [](double d) { uint64_t u; std::memcpy(&u, &d, 8); return u; };
+    std::vector<uint64_t> cls(nCands);
+    for (size_t i = 0; i < nCands; ++i) {
+      const KCand& kc = H.cands[i];
+      uint64_t h = mix(mix((uint64_t)kc.first_task, (uint64_t)kc.n_tasks), (uint64_t)kc.n_steps);
+      for (int d = 0; d <= kc.xdim; ++d) h = mix(h, (uint64_t)kc.via_off[d]);
+      const int nv = kc.via_off[kc.xdim];
+      for (int k = 0; k < nv; ++k) { const KVia& v = H.vias[kc.first_via + k]; h = mix(mix(h, bitsOf(v.t)), (uint64_t)v.flag); }
+      for (int t = 0; t <= kc.n_tasks; ++t) h = mix(h, (uint64_t)kc.act_off[t]);
+      const int na = kc.act_off[kc.n_tasks];
+      for (int k = 0; k < na; ++k) { const KAct& a = H.acts[kc.first_act + k]; h = mix(mix(mix(h, bitsOf(a.t)), bitsOf(a.horizon)), (uint64_t)a.on); }
+      for (int k = 0; k < kc.n_gcon; ++k) {
+        const KGraphCon& g = H.gcons[kc.first_gcon + k];
+        h = mix(mix(mix(mix(h, bitsOf(g.t)), (uint64_t)(g.kind * 4 + g.on)), (uint64_t)(g.slot * 64 + g.parent_slot)), (uint64_t)(g.parent_tree + 64));
+      }
+      cls[i] = mix(h, (uint64_t)(kc.pose_slot + 1));
+    }
+    H.sweep_order.resize(nCands);
+    std::iota(H.sweep_order.begin(), H.sweep_order.end(), 0);
+    bool sorted = true;
+    for (size_t i = 1; i < nCands && sorted; ++i) sorted = cls[i] == cls[i - 1];
+    if (!sorted) std::stable_sort(H.sweep_order.begin(), H.sweep_order.end(), [&](int32_t a, int32_t b) { return cls[a] < cls[b]; });
+  }
+  {
+    int maxTasksS = 1;
+    for (const KCand& kc : H.cands) maxTasksS = std::max(maxTasksS, kc.n_tasks);
+    P.sweep_ok = (P.nDyn + (int)H.statpar_ref.size() <= AFFT_MAX_SLOTS && maxTasksS <= AFFT_MAX_TASKS && H.maxXdim <= AFFT_MAX_XDIM &&
+                  P.nDynShapes <= AFFT_MAX_DSHAPE && P.nDynBodies <= AFFT_MAX_DBODY && P.nTrees <= AFFT_MAX_TREES && S.nJ <= AFFT_MAX_NJ) ? 1 : 0;
+  }
 
   // FK table, second pass: operands that depend on the layout (see KFkEntry in rollout.cuh)
   auto patchFkAux = [&]() -> bool {

@@ -116,6 +116,9 @@ struct KCtx
   int objTree0, objTree1;
   int objMode0, objMode1;       // 0 per-shape flags, 1 all on, 2 all off
   unsigned objHasRel;
+  // accessors shared with the thread-per-candidate context of sweep.cuh
+  AFF_MEMBER const double* qv() const { return sm + AFFK_O(*P, q); }
+  AFF_MEMBER const double* shpv() const { return sm + AFFK_O(*P, shp); }
 };
 #if AFFK_MAX_OBJ != 2
 #error "object state is written out for two slots"
@@ -123,16 +126,16 @@ struct KCtx
 #define OBJ_GET(c, f, s) ((s) ? (c).f##1 : (c).f##0)
 #define OBJ_SET(c, f, s, v) do { if (s) (c).f##1 = (v); else (c).f##0 = (v); } while (0)
 
-AFF_DEV const double* k_slot(const KCtx& c, int slot) { return c.nodes + 12 * slot; }
+template <class Ctx> AFF_DEV const double* k_slot(const Ctx& c, int slot) { return c.nodes + 12 * slot; }
 
 // Jacobian columns of this lane's IK joint for a point p fixed to the body in `slot`.
 struct KJointFrame { double ax[3]; double org[3]; int type; int valid; };
 
-AFF_DEV void k_jac_cols(const KCtx& c, const KJointFrame& jf, int slot, const double* p, double* colT, double* colR)
+template <class Ctx> AFF_DEV void k_jac_cols(const Ctx& c, const KJointFrame& jf, int col, int slot, const double* p, double* colT, double* colR)
 {
   colT[0] = colT[1] = colT[2] = 0.0;
   colR[0] = colR[1] = colR[2] = 0.0;
-  if (slot < 0 || !jf.valid || !((c.chain[slot] >> c.lane) & 1u)) return;
+  if (slot < 0 || !jf.valid || !((c.chain[slot] >> col) & 1u)) return;
   if (jf.type < AFF_JNT_ROT_X) { colT[0] = jf.ax[0]; colT[1] = jf.ax[1]; colT[2] = jf.ax[2]; }
   else {
     double r[3];
@@ -397,7 +400,7 @@ AFF_DEV void k_tangent_basis(const double* a, double* e1, double* e2)
   k_cross(e2, a, e1);
 }
 
-AFF_DEV void k_task_geo(const KCtx& c, const int* td, const KTask* tk, double* geo, double* xcur)
+template <class Ctx> AFF_DEV void k_task_geo(const Ctx& c, const int* td, const KTask* tk, double* geo, double* xcur)
 {
   const int kind = td[TD_KIND], eff = td[TD_EFF], ref = td[TD_REF], frame = td[TD_FRAME], axis = td[TD_AXIS];
   const int xoff = td[TD_XOFF];
@@ -440,7 +443,7 @@ AFF_DEV void k_task_geo(const KCtx& c, const int* td, const KTask* tk, double* g
     xcur[xoff] = aff_acos(k_dot(u, v));
   } else {   // JOINTS
     const int nj = td[TD_NJ];
-    const double* q = c.sm + c.P->o_q;
+    const double* q = c.qv();
     for (int i = 0; i < nj; ++i) {
       const int ji = ldg(&tk->jidx[i]);
       xcur[xoff + i] = (ji >= 0) ? q[ji] : ldg(&tk->jconst[i]);
@@ -484,16 +487,15 @@ AFF_DEV void k_task_dx(const int* td, const KTask* tk, const double* geo, const 
 
 // Rows of one task in column `lane` of J (Task::computeJ).  Returns a bit per
 // row that is non-zero in this column.
-AFF_DEV unsigned k_task_J(const KCtx& c, const KJointFrame& jf, const int* td, const KTask* tk, const double* geo, double* Jrow0, int Jstride)
+template <class Ctx> AFF_DEV unsigned k_task_J(const Ctx& c, const KJointFrame& jf, int col, const int* td, const KTask* tk, const double* geo, double* Jrow0, int Jstride)
 {
   const int kind = td[TD_KIND], eff = td[TD_EFF], ref = td[TD_REF], frame = td[TD_FRAME];
-  const int col = c.lane;
   unsigned nz = 0u;
   if (kind <= AFF_TASK_Z) {
     double te[3], re[3], tr[3], rr[3], tf[3], rf[3], cr[3], cl[3], out[3];
-    k_jac_cols(c, jf, eff, geo, te, re);
-    k_jac_cols(c, jf, ref, geo + 3, tr, rr);
-    k_jac_cols(c, jf, frame, k_slot(c, frame >= 0 ? frame : 0), tf, rf);      // without a frame the point is not read
+    k_jac_cols(c, jf, col, eff, geo, te, re);
+    k_jac_cols(c, jf, col, ref, geo + 3, tr, rr);
+    k_jac_cols(c, jf, col, frame, k_slot(c, frame >= 0 ? frame : 0), tf, rf);      // without a frame the point is not read
     k_cross(cr, geo + 6, rf);
     for (int k = 0; k < 3; ++k) cl[k] = (te[k] - tr[k]) + cr[k];
     if (frame >= 0) k_mulv(out, k_slot(c, frame) + 3, cl);
@@ -504,8 +506,8 @@ AFF_DEV unsigned k_task_J(const KCtx& c, const KJointFrame& jf, const int* td, c
     } else { const double v = k_sel3(out, kind - AFF_TASK_X); Jrow0[col] = v; nz = v != 0.0 ? 1u : 0u; }
   } else if (kind == AFF_TASK_POLAR) {
     double te[3], re[3], tr[3], rr[3], wI[3], w[3];
-    k_jac_cols(c, jf, eff, geo + 9, te, re);
-    k_jac_cols(c, jf, ref, geo + 9, tr, rr);
+    k_jac_cols(c, jf, col, eff, geo + 9, te, re);
+    k_jac_cols(c, jf, col, ref, geo + 9, tr, rr);
     for (int k = 0; k < 3; ++k) wI[k] = re[k] - rr[k];
     if (ref >= 0) k_mulv(w, k_slot(c, ref) + 3, wI);
     else { w[0] = wI[0]; w[1] = wI[1]; w[2] = wI[2]; }
@@ -517,8 +519,8 @@ AFF_DEV unsigned k_task_J(const KCtx& c, const KJointFrame& jf, const int* td, c
     const double* n = geo + 6;
     double v = 0.0;
     if (n[0] != 0.0 || n[1] != 0.0 || n[2] != 0.0) {
-      k_jac_cols(c, jf, eff, geo + 9, te, re);
-      k_jac_cols(c, jf, ref, geo + 9, tr, rr);
+      k_jac_cols(c, jf, col, eff, geo + 9, te, re);
+      k_jac_cols(c, jf, col, ref, geo + 9, tr, rr);
       for (int k = 0; k < 3; ++k) wI[k] = re[k] - rr[k];
       v = k_dot(n, wI);
     }
@@ -703,7 +705,7 @@ struct KCollResult { double minDist; int minB1, minB2; double cost; };
 
 // toggleSlotPlus1: slot+1 if the shape's body IS a re-parentable object (the
 // body a CollisionModelConstraint names), else 0.
-AFF_DEV bool k_dshape_active(const KCtx& c, const KShape* sh, int toggleSlotPlus1)
+template <class Ctx> AFF_DEV bool k_dshape_active(const Ctx& c, const KShape* sh, int toggleSlotPlus1)
 {
   if (toggleSlotPlus1) {
     const int mode = OBJ_GET(c, objMode, toggleSlotPlus1 - 1);
@@ -716,12 +718,12 @@ AFF_DEV bool k_dshape_active(const KCtx& c, const KShape* sh, int toggleSlotPlus
 // Distance of a body pair found by the AABB test = min over active shape pairs.
 // ia: dynamic body index; ib >= 0 dynamic body index, ib < 0 static body (-1-ib).
 // (Rare path: only bodies whose boxes come within DistanceThreshold.)
-AFF_DEV double k_pair_distance(const KCtx& c, int ia, int ib)
+template <class Ctx> AFF_DEV double k_pair_distance(const Ctx& c, int ia, int ib)
 {
   const KPlan& P = *c.P;
   const KShapeBody* ba = P.dbody + ia;
   const int fa = ldg(&ba->first_shape), na = ldg(&ba->n_shapes), sa = ldg(&ba->toggle_slot);
-  const double* shp = c.sm + AFFK_O(P, shp);
+  const double* shp = c.shpv();
   double dmin = DBL_MAX;
   for (int k1 = 0; k1 < na; ++k1) {
     const KShape* s1 = P.dshape + fa + k1;
@@ -777,7 +779,7 @@ AFF_DEV double k_pair_distance(const KCtx& c, int ia, int ib)
 // involving a re-parentable object depend on its shape flags and current tree,
 // and a tree body pairs with a non-explicit body outside all trees only while
 // their AABBs (inflated by the threshold) overlap.
-AFF_DEV bool k_pair_live(const KCtx& c, int meta, const double* baabb, double thr)
+template <class Ctx> AFF_DEV bool k_pair_live(const Ctx& c, int meta, const double* baabb, double thr)
 {
   if (!KP_RULE(meta)) return true;
   const int sa = KP_SLOT_A(meta), sb = KP_SLOT_B(meta);
@@ -928,6 +930,7 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
   // A pair whose bounding spheres are farther apart than `need` cannot become the minimum the caller
   // looks at, cannot collide and cannot cost (thr <= 1 mm <= need): its exact distance is skipped.
   const double cullMargin = 1.0e-9;
+  const double cullNeed = (need > thr) ? need : thr;     // pairs closer than the threshold carry a cost term
   // 5a. segment - segment (capsules, spheres)
   for (int base = 0; base < P.nSS; base += 32) {
     const int i = base + lane;
@@ -943,7 +946,7 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
         else { const double* B = P.sseg + 8 * (-1 - pr.b); for (int k = 0; k < 3; ++k) { pB[k] = ldg(&B[k]); dB[k] = ldg(&B[3 + k]); } rB = ldg(&B[6]); bB = ldg(&B[7]); }
         double cd2 = 0.0;
         for (int k = 0; k < 3; ++k) { const double dc = (A[k] + 0.5 * A[3 + k]) - (pB[k] + 0.5 * dB[k]); cd2 += dc * dc; }
-        const double lim = need + (A[7] + bB) + cullMargin;
+        const double lim = cullNeed + (A[7] + bB) + cullMargin;
         if (!(cd2 >= lim * lim)) {
           on = true;
           d = KP_SWAP(pr.meta) ? (k_seg_seg(pB, dB, A, A + 3) - rB) - rA : (k_seg_seg(A, A + 3, pB, dB) - rA) - rB;
@@ -968,7 +971,7 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
         else { const double* B = P.sseg + 8 * (-1 - pr.b); for (int k = 0; k < 3; ++k) cB[k] = ldg(&B[k]); bB = ldg(&B[7]); }
         double cd2 = 0.0;
         for (int k = 0; k < 3; ++k) { const double dc = (pS[k] + 0.5 * dS[k]) - cB[k]; cd2 += dc * dc; }
-        const double lim = need + (bS + bB) + cullMargin;
+        const double lim = cullNeed + (bS + bB) + cullMargin;
         if (!(cd2 >= lim * lim)) {
           on = true;
           // segment into the box / cylinder frame, one row of the frame at a time (few live registers)
@@ -1295,7 +1298,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
       int row = 0;
       for (int t = 0; t < nTasks; ++t) {
         if (!((activeMask >> t) & 1u)) continue;
-        if (lane < nJ) nz |= k_task_J(c, jf, c.tdesc + 8 * t, tasks + t, geo + AFFK_GEO * t, J + row * JS, JS) << row;
+        if (lane < nJ) nz |= k_task_J(c, jf, lane, c.tdesc + 8 * t, tasks + t, geo + AFFK_GEO * t, J + row * JS, JS) << row;
         row += c.tdesc[8 * t + TD_DIM];
       }
     }
@@ -1327,8 +1330,8 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
             if (side == 0) f = k_clip((yE - yS) - boundary, -0.5, 0.0) * 5.0;
             else f = -k_clip((-yE + yS) - boundary, -0.5, 0.0) * 5.0;
             double te[3], re[3], tr[3], rr[3];
-            k_jac_cols(c, jf, el, Ae, te, re);
-            k_jac_cols(c, jf, base, Ab, tr, rr);
+            k_jac_cols(c, jf, lane, el, Ae, te, re);
+            k_jac_cols(c, jf, lane, base, Ab, tr, rr);
             tmp = tmp + (te[1] - tr[1]) * f;
           }
         }
@@ -1345,8 +1348,8 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
           const double dBound = (z > 1.0) ? 0.4 * (z - 1.0) : 0.0;
           const double f = k_clip(x - (0.25 + dBound), -0.5, 0.0) * 5.0;
           double te[3], re[3], tr[3], rr[3];
-          k_jac_cols(c, jf, wr, Aw, te, re);
-          k_jac_cols(c, jf, base, Ab, tr, rr);
+          k_jac_cols(c, jf, lane, wr, Aw, te, re);
+          k_jac_cols(c, jf, lane, base, Ab, tr, rr);
           tmp = tmp + (te[0] - tr[0]) * f;
         }
         ex = (ex + tmp) * alphaEff;

@@ -10,6 +10,7 @@
 #if defined(AFF_EMULATE)
 
 #define AFF_DEV static inline
+#define AFF_MEMBER inline
 #define AFF_NOINLINE static
 int w_lane();
 void w_sync();
@@ -28,6 +29,7 @@ static inline int w_ffs(unsigned v) { return __builtin_ffs((int)v); }
 #else
 
 #define AFF_DEV __device__ __forceinline__
+#define AFF_MEMBER __device__ __forceinline__
 #define AFF_NOINLINE __device__ __noinline__
 // opaque: kept in a register instead of being re-read from the special register at every use
 AFF_DEV int w_lane() { int l = (int)(threadIdx.x & 31u); asm volatile("" : "+r"(l)); return l; }

@@ -46,6 +46,7 @@ unsigned w_ballot(int pred)
 }
 
 #include "kernel/rollout.cuh"
+#include "kernel/sweep.cuh"
 
 static void fiberEntry()
 {
@@ -79,7 +80,7 @@ static void runWarp(std::function<void()> body)
   }
 }
 
-extern "C" int emu_predict_batch(const aff_scene_desc* scene, const aff_task_desc* tasks, size_t nTasks,
+static int emu_run(int sweep, const aff_scene_desc* scene, const aff_task_desc* tasks, size_t nTasks,
                                  const aff_constraint* cons, size_t nCons, const aff_candidate* cands, size_t nCands,
                                  const aff_opts* opts, aff_result* out, double* qlog, size_t qlogRows, char* errbuf, size_t errlen)
 {
@@ -99,11 +100,22 @@ extern "C" int emu_predict_batch(const aff_scene_desc* scene, const aff_task_des
   P.statA = statA.data(); P.statSC = statSC.data(); P.dynSC = dynSC.data(); P.fktab = H.fktab.data(); P.statpar_ref = H.statpar_ref.data(); P.obj_parent_slot = H.obj_parent_slot.data(); P.obj_parent_tree = H.obj_parent_tree.data(); P.dyn_under = H.dyn_under.data(); P.dyn_chain = H.dyn_chain.data(); P.dynT = H.dynT.data(); P.dynQ = H.dynQ.data();
   P.dshape = H.dshape.data(); P.dbody = H.dbody.data(); P.sshape = H.sshape.data(); P.sbody = H.sbody.data();
   P.sshapeA = sshapeA.data(); P.sbodyAABB = sbodyAABB.data(); P.pairsSS = H.pairsSS.data(); P.pairsSB = H.pairsSB.data(); P.sseg = sseg.data();
-  P.obj_node = H.obj_node.data(); P.obj_body = H.obj_body.data(); P.obj_q6 = H.obj_q6.data();
+  P.obj_node = H.obj_node.data(); P.obj_body = H.obj_body.data(); P.obj_q6 = H.obj_q6.data(); P.dyn_pslot = H.dyn_pslot.data(); P.sweep_order = H.sweep_order.data();
   P.tasks = H.tasks.data(); P.vias = H.vias.data(); P.acts = H.acts.data(); P.gcons = H.gcons.data(); P.cands = H.cands.data();
   P.results = results.data();
   P.qlog = qlog; P.qlog_rows = qlog ? (int)qlogRows : 0;
   runWarp([&]() { k_prologue(P); });
+  if (sweep) {
+    // thread-per-candidate kernel: plain sequential code, one call per candidate in the plan's order
+    if (!P.sweep_ok) { if (errbuf && errlen) std::strncpy(errbuf, "batch exceeds the sweep kernel's caps", errlen - 1); return AFF_ERR_CAPACITY; }
+    std::vector<TState> S(1);
+    for (size_t i = 0; i < nCands; ++i) {
+      std::memset(&S[0], 0, sizeof(TState));
+      t_rollout(P, P.sweep_order[i], S[0], true);
+    }
+    for (size_t i = 0; i < nCands; ++i) out[i] = results[i];
+    return AFF_OK;
+  }
   std::vector<double> sm((size_t)P.warp_doubles + 64);
   for (size_t i = 0; i < nCands; ++i) {
     std::fill(sm.begin(), sm.end(), 0.0);
@@ -114,4 +126,19 @@ extern "C" int emu_predict_batch(const aff_scene_desc* scene, const aff_task_des
     std::fprintf(stderr, "emu: nDyn %d nStatic %d rounds %d dynShapes %d dynBodies %d statBodies %d pairs SS %d SB %d warp smem %zu B\n",
                  P.nDyn, P.nStatic, P.nRounds, P.nDynShapes, P.nDynBodies, P.nStatBodies, P.nSS, P.nSB, H.smemBytesPerWarp);
   return AFF_OK;
+}
+
+extern "C" int emu_predict_batch(const aff_scene_desc* scene, const aff_task_desc* tasks, size_t nTasks,
+                                 const aff_constraint* cons, size_t nCons, const aff_candidate* cands, size_t nCands,
+                                 const aff_opts* opts, aff_result* out, double* qlog, size_t qlogRows, char* errbuf, size_t errlen)
+{
+  return emu_run(0, scene, tasks, nTasks, cons, nCons, cands, nCands, opts, out, qlog, qlogRows, errbuf, errlen);
+}
+
+// the thread-per-candidate kernel source (sweep.cuh) on the CPU
+extern "C" int emu_predict_batch_sweep(const aff_scene_desc* scene, const aff_task_desc* tasks, size_t nTasks,
+                                       const aff_constraint* cons, size_t nCons, const aff_candidate* cands, size_t nCands,
+                                       const aff_opts* opts, aff_result* out, double* qlog, size_t qlogRows, char* errbuf, size_t errlen)
+{
+  return emu_run(1, scene, tasks, nTasks, cons, nCons, cands, nCands, opts, out, qlog, qlogRows, errbuf, errlen);
 }

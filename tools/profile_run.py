@@ -1,4 +1,5 @@
-"""Small fixed workload for ncu: N perturbed `get fresh_tomatoes` rollouts, L launches."""
+"""Small fixed workload for ncu: N perturbed get rollouts, L launches.
+usage: python tools/profile_run.py [n] [launches] [command] [kernel: warp|sweep|auto]"""
 import sys
 import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,6 +9,8 @@ import torch
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2368
 launches = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 cmd = sys.argv[3] if len(sys.argv) > 3 else "get fresh_tomatoes"
+if len(sys.argv) > 4 and sys.argv[4] != "auto":
+    os.environ["AFF_KERNEL"] = sys.argv[4]
 s = ab.HostScene()
 b = ab.HostBatch(s)
 b.add_perturbed(cmd, n)
