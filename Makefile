@@ -20,8 +20,8 @@ oracle:
 
 # test-only CPU emulation of the kernel source (never part of the product library)
 emu: tests/emu/libaffemu.so
-tests/emu/libaffemu.so: tests/emu/warp_emu.cpp affaction_b200/csrc/kernel/plan_build.cpp $(KERNEL_HDR)
-	$(CXX) -O2 -std=c++17 -fPIC -shared -ffp-contract=off -mfma -Wno-unknown-pragmas $(INC) tests/emu/warp_emu.cpp affaction_b200/csrc/kernel/plan_build.cpp -o $@
+tests/emu/libaffemu.so: tests/emu/warp_emu.cpp tests/emu/flop_count.cpp affaction_b200/csrc/kernel/plan_build.cpp $(KERNEL_HDR)
+	$(CXX) -O2 -std=c++17 -fPIC -shared -ffp-contract=off -mfma -Wno-unknown-pragmas $(INC) tests/emu/warp_emu.cpp tests/emu/flop_count.cpp affaction_b200/csrc/kernel/plan_build.cpp -o $@
 
 clean:
 	rm -f affaction_b200/libaffpredict.so tests/emu/libaffemu.so build_ptxas.log

@@ -77,7 +77,7 @@ ABI_SYMBOLS = [
     "aff_default_opts", "aff_abi_version", "aff_last_error", "aff_device_count", "aff_scene_create", "aff_scene_destroy",
     "aff_scene_num_ik_joints", "aff_batch_create", "aff_batch_destroy", "aff_batch_launch", "aff_batch_results_device",
     "aff_batch_results", "aff_batch_last_launch_count", "aff_batch_num_steps", "aff_batch_fetch_q", "aff_predict_batch",
-    "aff_rank_results", "aff_measure_fp64_peak", "aff_batch_set_results_buffer", "aff_batch_h2d_bytes", "aff_batch_smem_bytes_per_warp", "aff_batch_grid_blocks",
+    "aff_predict_batch_multi", "aff_batch_kernel_kind", "aff_rank_results", "aff_measure_fp64_peak", "aff_batch_set_results_buffer", "aff_batch_h2d_bytes", "aff_batch_smem_bytes_per_warp", "aff_batch_grid_blocks",
 ]
 HOST_SYMBOLS = [
     "aff_host_last_error", "aff_host_scene_load", "aff_host_scene_destroy", "aff_host_scene_desc", "aff_host_num_bodies",
@@ -107,7 +107,8 @@ def lib():
         "aff_batch_launch": (i32, [vp, vp]), "aff_batch_results_device": (vp, [vp]),
         "aff_batch_results": (i32, [vp, vp, vp, sz]), "aff_batch_set_results_buffer": (i32, [vp, vp]), "aff_batch_last_launch_count": (i32, [vp]),
         "aff_batch_num_steps": (i32, [vp, sz]), "aff_batch_fetch_q": (i32, [vp, sz, vp, sz]),
-        "aff_predict_batch": (i32, [vp, vp, sz, vp, sz, vp, sz, vp, vp]), "aff_rank_results": (None, [vp, sz, vp]),
+        "aff_predict_batch": (i32, [vp, vp, sz, vp, sz, vp, sz, vp, vp]),
+        "aff_predict_batch_multi": (i32, [vp, vp, i32, vp, sz, vp, sz, vp, sz, vp, vp]), "aff_batch_kernel_kind": (i32, [vp]), "aff_rank_results": (None, [vp, sz, vp]),
         "aff_measure_fp64_peak": (dbl, [i32, dbl]), "aff_batch_h2d_bytes": (sz, [vp]),
         "aff_batch_smem_bytes_per_warp": (sz, [vp]), "aff_batch_grid_blocks": (i32, [vp]),
         "aff_host_last_error": (cstr, []), "aff_host_scene_load": (vp, [cstr]), "aff_host_scene_destroy": (None, [vp]),
@@ -387,6 +388,11 @@ class DeviceBatch:
     def grid_blocks(self):
         return lib().aff_batch_grid_blocks(self.h)
 
+    @property
+    def kernel(self):
+        """'sweep' (one rollout per thread) or 'warp' (one rollout per warp)."""
+        return "sweep" if lib().aff_batch_kernel_kind(self.h) else "warp"
+
 
 def predict_batch(scene, batch, opts=None, device=0):
     """aff_predict_batch: host buffers in, host results out (the e2e call)."""
@@ -395,6 +401,17 @@ def predict_batch(scene, batch, opts=None, device=0):
     res = (Result * n)()
     _check(lib().aff_predict_batch(scene.device_scene(device), batch.tasks_ptr, batch.n_tasks, batch.constraints_ptr,
                                    batch.n_constraints, batch.candidates_ptr, n, C.byref(opts), res), "aff_predict_batch")
+    return list(res)
+
+
+def predict_batch_multi(scene, batch, devices, opts=None):
+    """aff_predict_batch_multi: one host process, candidates split statically over `devices`."""
+    opts = opts if opts is not None else default_opts()
+    n = batch.n_candidates
+    res = (Result * n)()
+    dev = (C.c_int * len(devices))(*devices)
+    _check(lib().aff_predict_batch_multi(scene.desc, dev, len(devices), batch.tasks_ptr, batch.n_tasks, batch.constraints_ptr,
+                                         batch.n_constraints, batch.candidates_ptr, n, C.byref(opts), res), "aff_predict_batch_multi")
     return list(res)
 
 

@@ -13,6 +13,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "affpredict.h"
@@ -35,6 +36,9 @@ namespace kfixed {
 }
 #undef AFFK_FIXED_LAYOUT
 
+#ifndef AFF_SWEEP_MIN_DEFAULT
+#define AFF_SWEEP_MIN_DEFAULT 24576
+#endif
 #ifndef AFF_WARPS_PER_BLOCK
 #define AFF_WARPS_PER_BLOCK 4
 #endif
@@ -76,23 +80,23 @@ __global__ void __launch_bounds__(32) aff_prologue_kernel(const KPlan P)
 AFF_ROLLOUT_KERNEL(aff_rollout_kernel, kfixed)            // batches in the fixed layout (KPlan::fixed_layout)
 AFF_ROLLOUT_KERNEL(aff_rollout_kernel_generic, kgeneric)  // anything larger
 
-// Thread-per-candidate kernel (sweep.cuh): thread i runs candidate sweep_order[i]; 32 rollouts per warp.
-// 512 threads x 2 blocks per SM = 32 warps = 1024 rollouts per SM (64 registers per thread; measured
-// round 2: 32 warps / SM in barrier groups of 16 beat 8 / 16 warps and smaller groups)
-#ifndef AFF_SWEEP_THREADS
-#define AFF_SWEEP_THREADS 512
-#endif
-#ifndef AFF_SWEEP_MIN_BLOCKS
-#define AFF_SWEEP_MIN_BLOCKS 2
-#endif
-__global__ void __launch_bounds__(AFF_SWEEP_THREADS, AFF_SWEEP_MIN_BLOCKS) aff_sweep_kernel(const __grid_constant__ KPlan P)
+// Thread-per-candidate kernel (sweep.cuh): 32 rollouts per warp.  Persistent blocks: block b takes the
+// chunks b, b + gridDim, ... of THREADS consecutive entries of sweep_order (candidates grouped by
+// structure), and its warps walk the step loop in lock-step phases (T_SYNC in sweep.cuh).  THREADS x
+// blocks per SM = 1024 rollouts per SM at 64 registers per thread (measured round 2: 32 warps per SM in
+// barrier groups of 16 beat 8 / 16 / 24 warps and smaller groups); the smaller block sizes spread
+// batches below one wave over all SMs.
+template <int THREADS> __global__ void __launch_bounds__(THREADS, 1024 / THREADS) aff_sweep_kernel(const __grid_constant__ KPlan P)
 {
-  const int i = blockIdx.x * AFF_SWEEP_THREADS + threadIdx.x;
-  // threads past the end of the batch shadow its last candidate (they take part in the block's barriers
-  // and write nothing)
-  const bool alive = i < P.nCands;
-  kgeneric::TState S;
-  kgeneric::t_rollout(P, __ldg(&P.sweep_order[alive ? i : P.nCands - 1]), S, alive);
+  for (int base = blockIdx.x * THREADS; base < P.nCands; base += gridDim.x * THREADS) {
+    const int i = base + threadIdx.x;
+    // threads past the end of the batch shadow its last candidate (they take part in the block's
+    // barriers and write nothing)
+    const bool alive = i < P.nCands;
+    kgeneric::TState S;
+    kgeneric::t_rollout(P, __ldg(&P.sweep_order[alive ? i : P.nCands - 1]), S, alive);
+    __syncthreads();
+  }
 }
 
 // Register-resident DFMA chains: the FP64 roofline denominator.
@@ -156,7 +160,7 @@ struct aff_batch
   int grid = 0; size_t smemBytes = 0; int launches = 0;
   size_t h2dBytes = 0;
   bool prologueDone = false, useFixed = false, useSweep = false;
-  int sweepGrid = 0;
+  int sweepGrid = 0, sweepThreads = 512;
   cudaStream_t lastStream = nullptr; bool launched = false;
   void release()
   {
@@ -277,20 +281,26 @@ int aff_batch_create(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, c
                  std::chrono::duration<double, std::milli>(tb2 - tb1).count(), b->h2dBytes / 1e6);
   }
   if (rc != AFF_OK) return rc;
-  // Kernel choice: one rollout per thread for every batch that fits its per-thread caps and has at least
-  // AFF_SWEEP_MIN candidates (default 1: measured faster than one rollout per warp at every size);
-  // AFF_KERNEL=warp / sweep forces one of the two (parity tests run both).
+  // Kernel choice: one rollout per thread for batches that fit its per-thread caps and have at least
+  // AFF_SWEEP_MIN candidates (default below: where it overtakes one rollout per warp, which finishes a
+  // wave of 2368 in 67 ms but needs 9.4 k warp instructions per rollout step); AFF_KERNEL=warp / sweep
+  // forces one of the two (the parity tests run both).
   {
     const char* force = getenv("AFF_KERNEL");
     const char* mn = getenv("AFF_SWEEP_MIN");
-    const size_t minSweep = mn ? (size_t)atoll(mn) : 1;
+    const size_t minSweep = mn ? (size_t)atoll(mn) : AFF_SWEEP_MIN_DEFAULT;
     b->useSweep = b->plan.sweep_ok && n_cands >= minSweep;
     if (force && !strcmp(force, "warp")) b->useSweep = false;
     if (force && !strcmp(force, "sweep")) {
       if (!b->plan.sweep_ok) return fail(AFF_ERR_CAPACITY, "aff_batch_create: AFF_KERNEL=sweep but the batch exceeds the per-thread caps");
       b->useSweep = true;
     }
-    b->sweepGrid = (int)((n_cands + AFF_SWEEP_THREADS - 1) / AFF_SWEEP_THREADS);
+    // block size: the largest that still gives every SM a block; grid: at most one resident wave
+    b->sweepThreads = 512;
+    while (b->sweepThreads > 128 && (n_cands + b->sweepThreads - 1) / b->sweepThreads < (size_t)s->smCount) b->sweepThreads /= 2;
+    if (const char* th = getenv("AFF_SWEEP_THREADS")) { const int v = atoi(th); if (v == 128 || v == 256 || v == 512) b->sweepThreads = v; }
+    const size_t blocksNeededS = (n_cands + b->sweepThreads - 1) / b->sweepThreads;
+    b->sweepGrid = (int)std::min(blocksNeededS, (size_t)s->smCount * (size_t)(1024 / b->sweepThreads));
   }
   // launch geometry: persistent blocks, as many as fit per SM
   b->smemBytes = b->host.smemBytesPerWarp * AFF_WARPS_PER_BLOCK;
@@ -345,7 +355,11 @@ int aff_batch_launch(aff_batch* b, void* stream)
     b->prologueDone = true;
     b->launches++;
   }
-  if (b->useSweep) aff_sweep_kernel<<<b->sweepGrid, AFF_SWEEP_THREADS, 0, st>>>(b->plan);
+  if (b->useSweep) {
+    if (b->sweepThreads == 512) aff_sweep_kernel<512><<<b->sweepGrid, 512, 0, st>>>(b->plan);
+    else if (b->sweepThreads == 256) aff_sweep_kernel<256><<<b->sweepGrid, 256, 0, st>>>(b->plan);
+    else aff_sweep_kernel<128><<<b->sweepGrid, 128, 0, st>>>(b->plan);
+  }
   else if (b->useFixed) aff_rollout_kernel<<<b->grid, 32 * AFF_WARPS_PER_BLOCK, b->smemBytes, st>>>(b->plan);
   else aff_rollout_kernel_generic<<<b->grid, 32 * AFF_WARPS_PER_BLOCK, b->smemBytes, st>>>(b->plan);
   CUDA_TRY(cudaGetLastError());
@@ -376,7 +390,8 @@ int aff_batch_last_launch_count(const aff_batch* b) { return b ? b->launches : 0
 int aff_batch_num_steps(const aff_batch* b, size_t cand) { return (b && cand < b->host.cands.size()) ? b->host.cands[cand].n_steps : -1; }
 size_t aff_batch_h2d_bytes(const aff_batch* b) { return b ? b->h2dBytes : 0; }
 size_t aff_batch_smem_bytes_per_warp(const aff_batch* b) { return b ? b->host.smemBytesPerWarp : 0; }
-int aff_batch_grid_blocks(const aff_batch* b) { return b ? b->grid : 0; }
+int aff_batch_grid_blocks(const aff_batch* b) { return b ? (b->useSweep ? b->sweepGrid : b->grid) : 0; }
+int aff_batch_kernel_kind(const aff_batch* b) { return (b && b->useSweep) ? 1 : 0; }
 
 int aff_batch_fetch_q(aff_batch* b, size_t cand, double* out, size_t max_rows)
 {
@@ -399,7 +414,11 @@ int aff_predict_batch(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, 
   // Large batches go through in chunks of whole waves of the persistent grid: the host compiles and
   // uploads chunk k+1 (default stream) while the kernels of chunk k run on their own stream.
   CUDA_TRY(cudaSetDevice(s->device));
-  size_t wave = (size_t)s->smCount * AFF_BLOCKS_PER_SM * AFF_WARPS_PER_BLOCK;
+  // chunk = one resident wave of the kernel the batch will run on (thread-per-candidate: 1024 rollouts per SM)
+  const char* mnEnv = getenv("AFF_SWEEP_MIN");
+  const char* kEnv = getenv("AFF_KERNEL");
+  const bool sweepLikely = !(kEnv && !strcmp(kEnv, "warp")) && n_cands >= (mnEnv ? (size_t)atoll(mnEnv) : (size_t)AFF_SWEEP_MIN_DEFAULT);
+  size_t wave = sweepLikely ? (size_t)s->smCount * 1024 : (size_t)s->smCount * AFF_BLOCKS_PER_SM * AFF_WARPS_PER_BLOCK;
   // chunks in flight: at most three (running, queued, being compiled); the oldest is collected and freed
   struct Part { aff_batch* b; size_t first; cudaEvent_t done; };
   std::vector<Part> parts;
@@ -422,12 +441,13 @@ int aff_predict_batch(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, 
     aff_batch_destroy(p.b);
     return r;
   };
-  if (n_cands > 2 * wave) {
-    if (cudaStreamCreateWithFlags(&ks, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) {
-      if (ks) cudaStreamDestroy(ks);
-      ks = cs = nullptr; wave = n_cands;
-    }
-  } else wave = n_cands;
+  // kernels and result copies on private non-blocking streams: calls made from several host threads
+  // (aff_predict_batch_multi, or one thread per action variant) overlap on the device
+  if (cudaStreamCreateWithFlags(&ks, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) {
+    if (ks) cudaStreamDestroy(ks);
+    ks = cs = nullptr; wave = n_cands;
+  }
+  if (n_cands <= wave + wave / 2) wave = n_cands;
   for (size_t off = 0; off < n_cands && rc == AFF_OK;) {
     size_t cnt = std::min(wave, n_cands - off);
     if (n_cands - off - cnt < wave / 2) cnt = n_cands - off;        // no short last chunk
@@ -452,8 +472,8 @@ int aff_predict_batch(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, 
     Part part{b, off, nullptr};
     if (nParts == 0 && ks) {
       // the first chunk tells how many rollouts are resident at once with this batch's shared-memory footprint
-      const size_t resident = (size_t)b->grid * AFF_WARPS_PER_BLOCK;
-      if (resident > 0 && resident < wave) wave = resident;
+      const size_t resident = b->useSweep ? (size_t)s->smCount * 1024 : (size_t)b->grid * AFF_WARPS_PER_BLOCK;
+      if (resident > 0 && (resident < wave || !b->useSweep)) wave = std::min(wave, resident);
     }
     rc = aff_batch_launch(b, ks);
     if (rc == AFF_OK && ks && (cudaEventCreateWithFlags(&part.done, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(part.done, ks) != cudaSuccess))
@@ -473,6 +493,46 @@ int aff_predict_batch(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, 
   if (timing) std::fprintf(stderr, "aff_predict_batch: %zu candidates in %zu chunk(s): plan + H2D %.1f ms (overlapped after the first chunk), "
                            "submit + collect %.1f ms, drain %.1f ms, streams %.1f ms\n", n_cands, nParts, planMs, ms(t0, t1), ms(t1, t2), ms(t2, t3));
   return rc;
+}
+
+int aff_predict_batch_multi(const aff_scene_desc* desc, const int* devices, int n_devices,
+                            const aff_task_desc* tasks, size_t n_tasks, const aff_constraint* cons, size_t n_cons,
+                            const aff_candidate* cands, size_t n_cands, const aff_opts* opts, aff_result* out)
+{
+  if (!desc || !devices || n_devices < 1 || !cands || !out) return fail(AFF_ERR_INVALID, "aff_predict_batch_multi: null argument");
+  const int G = n_devices;
+  std::vector<int> rcs((size_t)G, AFF_OK);
+  std::vector<std::string> errs((size_t)G);
+  std::vector<std::thread> pool;
+  for (int r = 0; r < G; ++r) {
+    const size_t lo = n_cands * (size_t)r / (size_t)G, hi = n_cands * (size_t)(r + 1) / (size_t)G;
+    if (hi == lo) continue;
+    pool.emplace_back([&, r, lo, hi]() {
+      aff_scene* sc = nullptr;
+      int rc = aff_scene_create(desc, devices[r], &sc);
+      if (rc == AFF_OK) {
+        // the slice's own window of the task / constraint tables, indices rebased
+        int32_t t0 = INT32_MAX, t1 = 0, c0 = INT32_MAX, c1 = 0;
+        for (size_t i = lo; i < hi; ++i) {
+          t0 = std::min(t0, cands[i].first_task); t1 = std::max(t1, cands[i].first_task + cands[i].n_tasks);
+          c0 = std::min(c0, cands[i].first_constraint); c1 = std::max(c1, cands[i].first_constraint + cands[i].n_constraints);
+        }
+        if (t0 < 0 || c0 < 0 || (size_t)t1 > n_tasks || (size_t)c1 > n_cons) { g_err = "candidate refers outside the tables"; rc = AFF_ERR_INVALID; }
+        else {
+          std::vector<aff_candidate> local(cands + lo, cands + hi);
+          for (aff_candidate& c : local) { c.first_task -= t0; c.first_constraint -= c0; }
+          rc = aff_predict_batch(sc, tasks + t0, (size_t)(t1 - t0), cons + c0, (size_t)(c1 - c0), local.data(), hi - lo, opts, out + lo);
+          if (rc == AFF_OK) for (size_t i = lo; i < hi; ++i) out[i].idx += (int32_t)lo;
+        }
+      }
+      if (rc != AFF_OK) errs[(size_t)r] = g_err;      // g_err is per thread
+      aff_scene_destroy(sc);
+      rcs[(size_t)r] = rc;
+    });
+  }
+  for (std::thread& t : pool) t.join();
+  for (int r = 0; r < G; ++r) if (rcs[(size_t)r] != AFF_OK) return fail(rcs[(size_t)r], "aff_predict_batch_multi: device " + std::to_string(devices[r]) + ": " + errs[(size_t)r]);
+  return AFF_OK;
 }
 
 void aff_rank_results(const aff_result* res, size_t n, int32_t* order)

@@ -12,11 +12,17 @@ full 1555 steps (no early exit).  One "step" = one pass of the predict path over
 one batch of ROLLOUTS_PER_GPU candidates per GPU.
 
   value : rollouts/s with the candidate tables already resident in HBM
-          (kernel launches + NCCL verdict gather only), CUDA events, max over ranks
+          (kernel launches + NCCL verdict gather only), CUDA events, max over ranks.
+          The three variant batches are launched on three streams and share the GPU
+          (one resident wave of the thread-per-candidate kernel = 148 SMs x 1024 rollouts).
   e2e   : the same metric through aff_predict_batch with HOST buffers in and out
-          (plan compile, H2D of the tables, kernels, D2H of the verdicts)
-  roofline: FP64 pipe (the path's bound); peak = DFMA rate measured
-          on this GPU in this run by aff_measure_fp64_peak
+          (plan compile, H2D of the tables, kernels, D2H of the verdicts), one host
+          thread per variant, timed over all --steps iterations
+  roofline: FP64 pipe (the path's bound); flops per rollout COUNTED by
+          running the kernel source with a counting scalar (tools/count_flops.py ->
+          profiles/flops_per_rollout.json); peak = DFMA rate measured on this GPU in
+          this run by aff_measure_fp64_peak.  roofline_hbm: the per-thread state of the
+          sweep kernel streams through HBM; measured DRAM bytes per rollout from ncu
   cpu_baseline / --impl reference: the CPU oracle (a port: the reference cannot
           be built) on all host cores over a bounded sample
 """
@@ -34,7 +40,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 VARIANTS = ["get tomato_sauce_bottle", "get fresh_tomatoes", "get italian_seasoning_bowl"]
-PER_VARIANT = 9472                       # 4 x (148 SMs x 16 resident warps)
+PER_VARIANT = 50176                      # 98 blocks x 512 rollouts: three variants = 294 of the 296 resident blocks of a B200
 ROLLOUTS_PER_GPU = PER_VARIANT * len(VARIANTS)
 STEPS_PER_ROLLOUT = 1555
 METRIC = "candidate IK rollouts/sec"
@@ -44,27 +50,20 @@ L2_FLUSH_BYTES = 256 << 20
 
 # candidate tables read once (tasks, via points, activations, graph constraints, candidate record) + 88-byte verdict
 ALGORITHMIC_BYTES_PER_ROLLOUT = 2300 + 88
-# dram__bytes_read.sum + dram__bytes_write.sum of one aff_rollout_kernel launch / rollouts in it (profiles/r1_summary.md)
-NCU_DRAM_BYTES_PER_ROLLOUT = 2758
+# dram__bytes_read.sum + dram__bytes_write.sum of one aff_sweep_kernel launch / rollouts in it (profiles/r2_summary.md:
+# 5.33 TB for 151 552 rollouts): the per-thread rollout state does not fit on chip and streams through HBM
+NCU_DRAM_BYTES_PER_ROLLOUT = 35150000
 
 
 def algorithmic_flops_per_rollout():
-    """FP64 flops one full-length rollout needs (FMA = 2), counted per step from
-    the problem dimensions of the pizza-scene `get` workload; the terms are
-    derived in DESIGN.md section 5.  Static bodies and unobservable work
-    (trajectories of inactive tasks) are not counted."""
-    nJ, chain, m = 23, 7, 8            # IK joints, joints per arm chain, active task rows
-    traj = 8 * 110                     # active dims x (window solve K~3.5 + evaluation)
-    task = 7 * 45 + 2 * 120            # x / dx of 7 tasks, two POLAR with acos/atan2/sincos
-    jac = 3 * chain * 45 + 2 * chain * 25 + 3      # one XYZ-type + one POLAR-type block + joints rows
-    nullsp = 6 * chain * 9 + nJ * 6    # elbow / wrist terms + joint-limit gradient
-    solve = 108 * 3 + m ** 3 // 3 + 2 * m * m + 2 * m * chain + 2 * m * chain   # sparse J W J^T, Cholesky, solves, rhs, dq
-    limits = nJ * 6
-    fk = 29 * 63 + nJ * 30             # dynamic nodes (compose + joint rotation) + sincos
-    coll = 14 * 57 + 66 * 75 + 24 * 150 + 300      # shape frames + AABBs, seg-seg pairs, seg-box pairs, broad phase
-    costs = nJ * 5 + 60
-    per_step = traj + task + jac + nullsp + solve + limits + fk + coll + costs
-    return per_step * STEPS_PER_ROLLOUT
+    """FP64 flops of one full-length rollout (FMA = 2), mean over the three variants: COUNTED by executing
+    the kernel source with a counting scalar (tests/emu/flop_count.cpp, tools/count_flops.py), not estimated.
+    -> (flops, per-variant dict, source)"""
+    path = os.path.join(ROOT, "profiles", "flops_per_rollout.json")
+    with open(path) as f:
+        d = json.load(f)
+    per = {k: v["flops_per_rollout"] for k, v in d["variants"].items()}
+    return d["flops_per_rollout"], per, "profiles/flops_per_rollout.json (" + d["how"] + ")"
 
 
 class ClockSampler(threading.Thread):
@@ -96,12 +95,16 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def make_batches(ab, scene, rank, per_variant):
+def make_batches(ab, scene, rank, per_variant, world=1):
+    """This rank's contiguous block of every variant's candidate index space (affaction_b200.sharding:
+    rank r of G takes [r N/G, (r+1) N/G)); candidate i of variant v has seed 0xAFFAC7 + v * 2^32 + i, so a
+    smaller batch is a prefix of a larger one and the CPU sample compares like with like."""
+    from affaction_b200.sharding import shard_bounds
     batches = []
     for v, cmd in enumerate(VARIANTS):
+        lo, hi = shard_bounds(per_variant * world, rank, world)
         hb = ab.HostBatch(scene)
-        # seeds do not depend on the batch size: a smaller batch is a prefix of the full one
-        hb.add_perturbed(cmd, per_variant, seed0=0xAFFAC7 + (rank * len(VARIANTS) + v) * PER_VARIANT)
+        hb.add_perturbed(cmd, hi - lo, seed0=0xAFFAC7 + (v << 32) + lo)
         batches.append(hb)
     return batches
 
@@ -156,6 +159,7 @@ def run_cuda(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     import affaction_b200 as ab
+    from affaction_b200.sharding import gather_verdicts
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -164,25 +168,29 @@ def run_cuda(args, rank, local_rank, world):
     scene = ab.HostScene()
     per_variant = args.rollouts // len(VARIANTS) if args.rollouts else PER_VARIANT
     n_local = per_variant * len(VARIANTS)
-    host_batches = make_batches(ab, scene, rank, per_variant)
+    host_batches = make_batches(ab, scene, rank, per_variant, world)
     opts = ab.default_opts()
-    stream = torch.cuda.current_stream().cuda_stream
+    main_stream = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream() for _ in VARIANTS]
     rec = C.sizeof(ab.Result)
 
     # ---- resident arm: candidate tables uploaded once, verdicts written into a torch buffer
     dev_batches = [ab.DeviceBatch(scene, hb, opts, device=dev_index) for hb in host_batches]
+    kernels = sorted(set(db.kernel for db in dev_batches))
     verdicts = torch.empty(n_local * rec, dtype=torch.uint8, device="cuda")
-    gathered = torch.empty(world * n_local * rec, dtype=torch.uint8, device="cuda") if world > 1 else None
+    gathered = torch.empty(world * n_local * rec, dtype=torch.uint8, device="cuda") if (world > 1 and rank == 0) else None
     for i, db in enumerate(dev_batches):
         db.set_results_buffer(verdicts.data_ptr() + i * per_variant * rec)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
 
-    def one_step():
+    def launch_all():
+        """the three variant batches side by side on the GPU: one stream each, joined on the main stream"""
         n_launch = 0
-        for db in dev_batches:
-            n_launch += db.launch(stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, verdicts)     # per-candidate verdicts and costs to every rank
+        for st, db in zip(streams, dev_batches):
+            st.wait_stream(main_stream)
+            n_launch += db.launch(st.cuda_stream)
+        for st in streams:
+            main_stream.wait_stream(st)
         return n_launch
 
     def barrier():
@@ -191,22 +199,21 @@ def run_cuda(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 1)):
-        one_step()
+        launch_all()
+        gather_verdicts(verdicts, world, dist, rank, gathered)
     barrier()
 
     sampler = ClockSampler(dev_index)
     sampler.start()
     kernel_ms, step_ms, launches = [], [], 0
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     for _ in range(args.steps):
         flush.fill_(1)                  # L2 flush between timed iterations
         barrier()
         ev[0].record()
-        for db in dev_batches:
-            launches += db.launch(stream)
+        launches += launch_all()
         ev[1].record()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, verdicts)
+        gather_verdicts(verdicts, world, dist, rank, gathered)      # per-candidate verdicts and costs to rank 0
         ev[2].record()
         barrier()
         kernel_ms.append(ev[0].elapsed_time(ev[1]))
@@ -224,40 +231,55 @@ def run_cuda(args, rank, local_rank, world):
     for r in res:
         mix[ab.CODE_NAMES.get(r.code, str(r.code))] = mix.get(ab.CODE_NAMES.get(r.code, str(r.code)), 0) + 1
 
-    # ---- e2e arm: host buffers in, host verdicts out, through aff_predict_batch
-    e2e_steps = max(1, min(args.steps, 3))
-    ab.predict_batch(scene, host_batches[0], opts, device=dev_index)   # warm-up
+    # ---- e2e arm: host buffers in, host verdicts out, through aff_predict_batch; one host thread per variant
+    # (the call is blocking and thread-safe; its kernels run on private streams and share the GPU)
+    e2e_out = [None] * len(VARIANTS)
+
+    def e2e_call(i):
+        e2e_out[i] = ab.predict_batch(scene, host_batches[i], opts, device=dev_index)
+
+    def e2e_step():
+        th = [threading.Thread(target=e2e_call, args=(i,)) for i in range(len(VARIANTS))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    e2e_step()   # warm-up
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        for hb in host_batches:
-            ab.predict_batch(scene, hb, opts, device=dev_index)
+    for _ in range(args.steps):
+        e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = world * n_local * e2e_steps / e2e_s
+    e2e_value = world * n_local * args.steps / e2e_s
+    e2e_equal = all(a.as_tuple() == b.as_tuple() for i in range(len(VARIANTS))
+                    for a, b in zip(e2e_out[i], res[i * per_variant:(i + 1) * per_variant]))
     h2d = sum(db.h2d_bytes for db in dev_batches)
     d2h = n_local * rec
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
     if rank == 0:
-        # roofline of the dominant kernel (aff_rollout_kernel), live CUDA-event timing of its launches
+        # roofline of the dominant kernel, live CUDA-event timing of its launches
         peak = ab.lib().aff_measure_fp64_peak(dev_index, 0.5)
-        flops = algorithmic_flops_per_rollout() * n_local
+        flops_per, flops_by_variant, flops_src = algorithmic_flops_per_rollout()
+        flops = flops_per * n_local
         avg_kernel_s = (sum(kernel_ms) / len(kernel_ms)) * 1e-3
         achieved = flops / avg_kernel_s * 1e-12
-        per_launch = n_local // len(VARIANTS)
         hbm_peak, hbm_src = 6553.9, "fallback (MEASURED_PEAKS.json missing)"
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
                 hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
         except (OSError, KeyError, ValueError):
             pass
-        hbm_achieved = ALGORITHMIC_BYTES_PER_ROLLOUT * n_local / avg_kernel_s * 1e-9
+        sweep = kernels == ["sweep"]
+        dram_per_rollout = NCU_DRAM_BYTES_PER_ROLLOUT if sweep else 2758
+        hbm_achieved = dram_per_rollout * n_local / avg_kernel_s * 1e-9
         # bounded CPU sample on the box's host cores (N=1 only)
         cpu, agreement = None, None
         if world == 1 and not args.no_cpu:
@@ -278,6 +300,7 @@ def run_cuda(args, rank, local_rank, world):
                         agreement["max_abs_diff"][f] = max(agreement["max_abs_diff"][f], abs(getattr(a, f) - getattr(b, f)))
                 if ab.rank(cpu_res)[0] != ab.rank(list(gpu_res))[0]:
                     agreement["ranked_first_equal"] = False
+        kname = "aff_sweep_kernel" if sweep else "aff_rollout_kernel"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -285,21 +308,25 @@ def run_cuda(args, rank, local_rank, world):
             "config": {"workload": "synthetic sweep of perturbed-goal get candidates (BASELINE.json configs[4]), pizza scene, "
                                    "PowerGrasp/BallGrasp/TopGrasp in equal parts, 1555 steps per rollout, no early exit",
                        "rollouts_per_gpu_per_step": n_local, "steps_per_rollout": STEPS_PER_ROLLOUT,
-                       "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": "candidates sharded statically over %d GPU(s); NCCL all_gather of verdicts" % world,
+                       "kernel": kname + (" (one rollout per thread, 32 per warp)" if sweep else " (one rollout per warp)"),
+                       "l2": "flushed between timed iterations (256 MiB fill)",
+                       "parallelism": "candidates sharded statically over %d GPU(s); NCCL gather of verdicts to rank 0" % world,
                        "verdict_mix_rank0": mix},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "call": "aff_predict_batch (plan compile + H2D + kernels + D2H, pageable host buffers)"},
+                    "steps": args.steps, "records_equal_resident_arm": bool(e2e_equal),
+                    "call": "aff_predict_batch (plan compile + H2D + kernels + D2H, pageable host buffers), one host thread per variant"},
             "gpu_launches": launches * world,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None,
-                         "traffic": NCU_DRAM_BYTES_PER_ROLLOUT * per_launch, "traffic_unit": "bytes per launch (dram read + write, "
-                         "ncu --set full capture profiles/r1_summary.md: 2.76 KB per rollout) - FP64 work does not scale with it",
-                         "kernel": "aff_rollout_kernel",
-                         "flops_per_rollout": algorithmic_flops_per_rollout(), "peak_source": "DFMA microbenchmark measured in this run "
-                         "(MEASURED_PEAKS.json holds no FP64 figure)", "kernel_ms_per_step": sum(kernel_ms) / len(kernel_ms)},
-            # the same kernel against the HBM roof, to show why that roof does not bound it
+                         "traffic": dram_per_rollout * per_variant, "traffic_unit": "bytes per launch (dram read + write of one "
+                         "launch of %d rollouts, ncu --set full capture, profiles/r2_summary.md)" % per_variant,
+                         "kernel": kname, "flops_per_rollout": flops_per, "flops_per_rollout_by_variant": flops_by_variant,
+                         "flops_source": flops_src,
+                         "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json holds no FP64 figure)",
+                         "kernel_ms_per_step": sum(kernel_ms) / len(kernel_ms)},
+            # the same kernel against the HBM roof: MEASURED dram traffic (the rollout state streams through HBM), not algorithmic bytes
             "roofline_hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": hbm_achieved / hbm_peak, "algorithmic_bytes_per_rollout": ALGORITHMIC_BYTES_PER_ROLLOUT,
-                             "peak_source": hbm_src},
+                             "frac": hbm_achieved / hbm_peak, "measured_dram_bytes_per_rollout": dram_per_rollout,
+                             "algorithmic_bytes_per_rollout": ALGORITHMIC_BYTES_PER_ROLLOUT, "peak_source": hbm_src},
             "cpu_baseline": cpu,
             "agreement": agreement,
             "clocks": sampler.summary(),

@@ -272,6 +272,23 @@ int aff_predict_batch(aff_scene* s,
                       const aff_candidate* cands, size_t n_cands,
                       const aff_opts* opts, aff_result* out);
 
+/* The same over several GPUs of one box from ONE host process (the reference's
+ * ActionComponent::actionThread is one process, src/ActionComponent.cpp:163-244):
+ * candidates are split statically, device r of G takes [r n/G, (r+1) n/G)
+ * (independent units: no data-path collective), each slice runs through
+ * aff_predict_batch on its own host thread and device, and the records land in
+ * the caller's array in candidate order.  `devices` may name a device twice.
+ * Returns AFF_OK or the first failing slice's status. */
+int aff_predict_batch_multi(const aff_scene_desc* scene, const int* devices, int n_devices,
+                            const aff_task_desc* tasks, size_t n_tasks,
+                            const aff_constraint* cons, size_t n_cons,
+                            const aff_candidate* cands, size_t n_cands,
+                            const aff_opts* opts, aff_result* out);
+
+/* Which kernel a batch runs on: 0 = one rollout per warp (small batches),
+ * 1 = one rollout per thread (sweeps). */
+int aff_batch_kernel_kind(const aff_batch* b);
+
 /* Argsort of results with PredictionResult::lesser (success first, then
  * jlCost+collCost ascending; src/TrajectoryPredictor.h:61-74), ties broken
  * by idx so the order is deterministic (std::sort in the reference is not). */

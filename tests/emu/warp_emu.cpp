@@ -80,6 +80,9 @@ static void runWarp(std::function<void()> body)
   }
 }
 
+extern "C" void aff_flop_count_rollout(const void* plan, int cand, unsigned long long out[5]);   // flop_count.cpp
+static unsigned long long* g_flops = nullptr;   // when set, emu_run(2, ...) counts instead of predicting
+
 static int emu_run(int sweep, const aff_scene_desc* scene, const aff_task_desc* tasks, size_t nTasks,
                                  const aff_constraint* cons, size_t nCons, const aff_candidate* cands, size_t nCands,
                                  const aff_opts* opts, aff_result* out, double* qlog, size_t qlogRows, char* errbuf, size_t errlen)
@@ -105,6 +108,13 @@ static int emu_run(int sweep, const aff_scene_desc* scene, const aff_task_desc* 
   P.results = results.data();
   P.qlog = qlog; P.qlog_rows = qlog ? (int)qlogRows : 0;
   runWarp([&]() { k_prologue(P); });
+  if (sweep == 2) {
+    // FP64 operation counts of every candidate (add, mul, fma, div, sqrt), kernel source with a counting scalar
+    if (!P.sweep_ok) { if (errbuf && errlen) std::strncpy(errbuf, "batch exceeds the sweep kernel's caps", errlen - 1); return AFF_ERR_CAPACITY; }
+    for (size_t i = 0; i < nCands; ++i) aff_flop_count_rollout(&P, (int)i, g_flops + 5 * i);
+    for (size_t i = 0; i < nCands; ++i) out[i] = results[i];
+    return AFF_OK;
+  }
   if (sweep) {
     // thread-per-candidate kernel: plain sequential code, one call per candidate in the plan's order
     if (!P.sweep_ok) { if (errbuf && errlen) std::strncpy(errbuf, "batch exceeds the sweep kernel's caps", errlen - 1); return AFF_ERR_CAPACITY; }
@@ -141,4 +151,15 @@ extern "C" int emu_predict_batch_sweep(const aff_scene_desc* scene, const aff_ta
                                        const aff_opts* opts, aff_result* out, double* qlog, size_t qlogRows, char* errbuf, size_t errlen)
 {
   return emu_run(1, scene, tasks, nTasks, cons, nCons, cands, nCands, opts, out, qlog, qlogRows, errbuf, errlen);
+}
+
+// FP64 operation counts per candidate: counts[5 * i + {0: add/sub, 1: mul, 2: fma, 3: div, 4: sqrt}]
+extern "C" int emu_count_flops(const aff_scene_desc* scene, const aff_task_desc* tasks, size_t nTasks,
+                               const aff_constraint* cons, size_t nCons, const aff_candidate* cands, size_t nCands,
+                               const aff_opts* opts, aff_result* out, unsigned long long* counts, char* errbuf, size_t errlen)
+{
+  g_flops = counts;
+  const int rc = emu_run(2, scene, tasks, nTasks, cons, nCons, cands, nCands, opts, out, nullptr, 0, errbuf, errlen);
+  g_flops = nullptr;
+  return rc;
 }

@@ -23,6 +23,8 @@ def emu_lib():
         _lib.emu_predict_batch.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, vp, vp, sz, vp, sz]
         _lib.emu_predict_batch_sweep.restype = C.c_int
         _lib.emu_predict_batch_sweep.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, vp, vp, sz, vp, sz]
+        _lib.emu_count_flops.restype = C.c_int
+        _lib.emu_count_flops.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp, sz]
     return _lib
 
 
@@ -44,3 +46,17 @@ def predict(scene, batch, opts, first=0, count=None, log_q=False, n_steps=None, 
     if rc != 0:
         raise RuntimeError("emu_predict_batch failed (%d): %s" % (rc, err.value.decode()))
     return list(res), q
+
+
+def count_flops(scene, batch, opts, first=0, count=None):
+    """FP64 operation counts of candidates [first, first+count): the kernel source (sweep.cuh) run on the
+    CPU with a counting scalar.  -> (results, counts[n, 5]) with columns add/sub, mul, fma, div, sqrt."""
+    n = batch.n_candidates - first if count is None else count
+    res = (Result * n)()
+    counts = np.zeros((n, 5), dtype=np.uint64)
+    err = C.create_string_buffer(512)
+    rc = emu_lib().emu_count_flops(scene.desc, batch.tasks_ptr, batch.n_tasks, batch.constraints_ptr, batch.n_constraints,
+                                   batch.candidate_ptr(first), n, C.byref(opts), res, counts.ctypes.data_as(C.c_void_p), err, 512)
+    if rc != 0:
+        raise RuntimeError("emu_count_flops failed (%d): %s" % (rc, err.value.decode()))
+    return list(res), counts

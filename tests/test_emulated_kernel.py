@@ -15,28 +15,34 @@ def scene(built):
     return ab.HostScene()
 
 
+@pytest.fixture(params=[False, True], ids=["warp", "sweep"])
+def sweep(request):
+    """False: rollout.cuh (one rollout per warp); True: sweep.cuh (one rollout per thread)."""
+    return request.param
+
+
 @pytest.mark.parametrize("cmd,cand", [("get fresh_tomatoes", 0), ("get italian_seasoning_bowl", 1)])
-def test_emulated_kernel_equals_oracle(scene, cmd, cand):
+def test_emulated_kernel_equals_oracle(scene, sweep, cmd, cand):
     b = ab.HostBatch(scene)
     b.add_action(cmd)
     opts = ab.default_opts(log_q=True)
     ref, q_ref = ob.predict(scene, b, cand, opts, log_q=True)
-    (emu,), q_emu = eb.predict(scene, b, opts, first=cand, count=1, log_q=True, n_steps=ref.n_steps - 1)
+    (emu,), q_emu = eb.predict(scene, b, opts, first=cand, count=1, log_q=True, n_steps=ref.n_steps - 1, sweep=sweep)
     assert emu.as_tuple() == ref.as_tuple()
     assert np.array_equal(q_emu[0], q_ref)
 
 
-def test_emulated_kernel_perturbed_candidate(scene):
+def test_emulated_kernel_perturbed_candidate(scene, sweep):
     b = ab.HostBatch(scene)
     b.add_perturbed("get italian_seasoning_bowl", 2, seed0=1234)
     opts = ab.default_opts()
     ref, _ = ob.predict(scene, b, 1, opts)
-    (emu,), _ = eb.predict(scene, b, opts, first=1, count=1)
+    (emu,), _ = eb.predict(scene, b, opts, first=1, count=1, sweep=sweep)
     assert ref.code == -4                     # a colliding candidate with several pairs in contact
     assert emu.as_tuple() == ref.as_tuple()
 
 
-def test_emulated_kernel_put_candidate(built):
+def test_emulated_kernel_put_candidate(built, sweep):
     """`put` after `get`: object starts in the hand (six rigid-body dofs under a moving parent),
     refFrame tasks, BoxInterval task regions, re-parenting onto a static surface."""
     from chain_util import scene_after_get
@@ -45,7 +51,19 @@ def test_emulated_kernel_put_candidate(built):
     assert b.add_action("put italian_seasoning_bowl table") == 6
     opts = ab.default_opts(log_q=True)
     ref, q_ref = ob.predict(scene, b, 4, opts, log_q=True)        # the one candidate that collides
-    (emu,), q_emu = eb.predict(scene, b, opts, first=4, count=1, log_q=True, n_steps=ref.n_steps - 1)
+    (emu,), q_emu = eb.predict(scene, b, opts, first=4, count=1, log_q=True, n_steps=ref.n_steps - 1, sweep=sweep)
     assert ref.code == -4
     assert emu.as_tuple() == ref.as_tuple()
     assert np.array_equal(q_emu[0], q_ref)
+
+
+def test_sweep_kernel_source_on_a_mixed_batch(scene):
+    """sweep.cuh on 24 perturbed candidates of two hands (two structure classes: the plan compiler
+    groups them, results come back in candidate order) against the oracle, record by record."""
+    b = ab.HostBatch(scene)
+    n = b.add_perturbed("get fresh_tomatoes", 24, seed0=4242)
+    opts = ab.default_opts()
+    ref = ob.predict_batch(scene, b, opts, n_threads=4)
+    emu, _ = eb.predict(scene, b, opts, sweep=True)
+    assert [r.as_tuple() for r in emu] == [r.as_tuple() for r in ref]
+    assert len(set(r.code for r in ref)) >= 2

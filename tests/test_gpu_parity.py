@@ -23,6 +23,19 @@ def scene(built):
     return ab.HostScene()
 
 
+@pytest.fixture(autouse=True, params=["warp", "sweep"])
+def kernel(request, monkeypatch):
+    """Every parity test runs on both kernels: one rollout per warp (small batches) and one rollout per
+    thread (sweeps; AFF_SWEEP_MIN=1 selects it for every batch within its per-thread caps, anything larger
+    still runs on the warp kernel)."""
+    if request.param == "warp":
+        monkeypatch.setenv("AFF_KERNEL", "warp")
+    else:
+        monkeypatch.delenv("AFF_KERNEL", raising=False)
+        monkeypatch.setenv("AFF_SWEEP_MIN", "1")
+    return request.param
+
+
 def _compare(scene, batch, opts, dev, idxs, check_q=True):
     gpu = dev.results()
     worst = 0.0
@@ -425,3 +438,36 @@ def test_get_options_match_oracle(scene, cmd):
     dev = ab.DeviceBatch(scene, batch, opts)
     dev.launch()
     assert _compare(scene, batch, opts, dev, range(n)) == 0.0
+
+
+def test_predict_batch_multi_splits_statically(scene):
+    """aff_predict_batch_multi: one host process, candidates split [r n/G, (r+1) n/G) over the listed devices
+    (here the same GPU three times: three host threads, three private streams), records in candidate order."""
+    batch = ab.HostBatch(scene)
+    n = batch.add_perturbed("get fresh_tomatoes", 50, seed0=777)
+    opts = ab.default_opts()
+    one = ab.predict_batch(scene, batch, opts)
+    multi = ab.predict_batch_multi(scene, batch, [0, 0, 0], opts)
+    assert [r.idx for r in multi] == list(range(n))
+    assert [r.as_tuple() for r in multi] == [r.as_tuple() for r in one]
+    with pytest.raises(ab.AffError, match="device"):
+        ab.predict_batch_multi(scene, batch, [0, 99], opts)
+
+
+def test_large_batch_runs_on_the_sweep_kernel_and_matches(scene, kernel, monkeypatch):
+    """A batch above AFF_SWEEP_MIN selects the thread-per-candidate kernel by itself; 4 blocks of 512 with a
+    ragged tail (2000 candidates), sampled against the oracle."""
+    if kernel != "sweep":
+        pytest.skip("kernel selection is only exercised once")
+    monkeypatch.setenv("AFF_SWEEP_MIN", "1500")
+    batch = ab.HostBatch(scene)
+    n = batch.add_perturbed("get italian_seasoning_bowl", 2000, seed0=31337)
+    opts = ab.default_opts()
+    dev = ab.DeviceBatch(scene, batch, opts)
+    assert dev.kernel == "sweep"
+    dev.launch()
+    gpu = dev.results()
+    assert [r.idx for r in gpu] == list(range(n))
+    for i in list(range(0, n, 97)) + [n - 1]:
+        ref, _ = ob.predict(scene, batch, i, opts)
+        assert gpu[i].as_tuple() == ref.as_tuple()
