@@ -42,7 +42,7 @@ class Result(C.Structure):
 
 class Opts(C.Structure):
     _fields_ = [("dt", C.c_double), ("alpha", C.c_double), ("lam", C.c_double), ("q_filt_decay", C.c_double),
-                ("n_after_steps", C.c_int32), ("log_q", C.c_int32)]
+                ("n_after_steps", C.c_int32), ("log_q", C.c_int32), ("early_exit", C.c_int32), ("reserved", C.c_int32)]
 
 
 class TaskDesc(C.Structure):
@@ -63,10 +63,11 @@ class Candidate(C.Structure):
                 ("n_constraints", C.c_int32), ("pose_body", C.c_int32), ("reserved", C.c_int32), ("pose_q6", C.c_double * 6)]
 
 
-def default_opts(log_q=False):
+def default_opts(log_q=False, early_exit=False):
     o = Opts()
     lib().aff_default_opts(C.byref(o))
     o.log_q = 1 if log_q else 0
+    o.early_exit = 1 if early_exit else 0
     return o
 
 

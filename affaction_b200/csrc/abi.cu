@@ -181,7 +181,7 @@ const char* aff_last_error(void) { return g_err.c_str(); }
 void aff_default_opts(aff_opts* o)
 {
   if (!o) return;
-  o->dt = 0.01; o->alpha = 0.05; o->lambda = 1.0e-6; o->q_filt_decay = 0.1; o->n_after_steps = 500; o->log_q = 0;
+  o->dt = 0.01; o->alpha = 0.05; o->lambda = 1.0e-6; o->q_filt_decay = 0.1; o->n_after_steps = 500; o->log_q = 0; o->early_exit = 0; o->reserved = 0;
 }
 
 int aff_device_count(void)
@@ -300,6 +300,12 @@ int aff_batch_create(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, c
     while (b->sweepThreads > 128 && (n_cands + b->sweepThreads - 1) / b->sweepThreads < (size_t)s->smCount) b->sweepThreads /= 2;
     if (const char* th = getenv("AFF_SWEEP_THREADS")) { const int v = atoi(th); if (v == 128 || v == 256 || v == 512) b->sweepThreads = v; }
     const size_t blocksNeededS = (n_cands + b->sweepThreads - 1) / b->sweepThreads;
+    if (!b->plan.warp_ok && !b->useSweep) {
+      if (!b->plan.sweep_ok || (force && !strcmp(force, "warp")))
+        return fail(AFF_ERR_UNSUPPORTED, "aff_batch_create: an object is connected to a body the warp-per-candidate FK schedule computes after it, "
+                                         "and the batch does not fit the thread-per-candidate kernel");
+      b->useSweep = true;
+    }
     b->sweepGrid = (int)std::min(blocksNeededS, (size_t)s->smCount * (size_t)(1024 / b->sweepThreads));
   }
   // launch geometry: persistent blocks, as many as fit per SM

@@ -252,6 +252,40 @@ void Graph::applyRollout(const aff_constraint* cons, int nCons, const double* ql
     }
   }
   setRow(rows - 1);
+  if (restoreParentFirstOrder()) computeForwardKinematics();
+}
+
+bool Graph::restoreParentFirstOrder()
+{
+  const int nb = (int)bodies.size();
+  bool ok = true;
+  for (int i = 0; i < nb && ok; ++i) ok = bodies[i].parent < i;
+  if (ok) return false;
+  // emit a body once its parent is out; bodies that are ready keep their relative order
+  std::vector<int> order, newId(nb, -1);
+  order.reserve(nb);
+  std::vector<char> done(nb, 0);
+  while ((int)order.size() < nb) {
+    const size_t before = order.size();
+    for (int i = 0; i < nb; ++i) {
+      if (done[i]) continue;
+      const int p = bodies[i].parent;
+      if (p >= 0 && !done[p]) continue;
+      done[i] = 1; newId[i] = (int)order.size(); order.push_back(i);
+    }
+    if (order.size() == before) throw std::runtime_error("graph has a parent cycle");
+  }
+  std::vector<Body> nbod;
+  nbod.reserve(nb);
+  for (int i : order) { Body b = bodies[i]; if (b.parent >= 0) b.parent = newId[b.parent]; nbod.push_back(b); }
+  bodies.swap(nbod);
+  for (Joint& j : joints) if (j.body >= 0) j.body = newId[j.body];
+  for (Shape& sh : shapes) if (sh.body >= 0) sh.body = newId[sh.body];
+  for (int& t : bpTrees) t = newId[t];
+  for (int& t : bpBodies) t = newId[t];
+  bodyIndex_.clear();
+  for (int i = 0; i < nb; ++i) bodyIndex_[bodies[i].name] = i;
+  return true;
 }
 
 static void shapeAABB(const Shape& s, const HTr& A, double mn[3], double mx[3])

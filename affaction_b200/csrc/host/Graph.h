@@ -81,6 +81,11 @@ public:
   // every ConnectBody / CollisionModel constraint is applied at the step it fired, with the joint
   // state of that step (qlog row), then the joints take the final row.  qlog: rows x nJ, jacobi order.
   void applyRollout(const struct aff_constraint* cons, int nCons, const double* qlog, int rows, double dt);
+  // After re-parenting, a body may sit behind its new parent's subtree in the arrays; the plain-C scene
+  // description (and the plan compiler behind it) lists parents before children.  Stable re-sort of the
+  // body array (relative order kept), all body indices remapped.  Body ids handed out before the call are
+  // stale afterwards (names are not).  Returns true if anything moved.
+  bool restoreParentFirstOrder();
 
   // RcsGraph_computeBodyAABB over shapes with the distance flag. false if none.
   bool computeBodyAABB(int body, double xyzMin[3], double xyzMax[3]) const;

@@ -83,6 +83,7 @@ int aff_host_scene_connect(aff_host_scene* s, const char* child, const char* par
     const int c = s->graph.getBodyByName(child), p = s->graph.getBodyByName(parent);
     if (c < 0 || p < 0) { g_hostError = "unknown body"; return AFF_ERR_INVALID; }
     s->graph.connectBody(c, p);
+    if (s->graph.restoreParentFirstOrder()) s->graph.computeForwardKinematics();
     s->graph.toDesc();
     if (s->device) { aff_scene_destroy(s->device); s->device = nullptr; }
     return AFF_OK;

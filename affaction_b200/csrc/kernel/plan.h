@@ -191,6 +191,7 @@ struct KPlan
   const int32_t* dyn_pslot;        // [nDyn] slot of each dynamic node's parent (dynamic node or static-parent copy)
   const int32_t* sweep_order;      // [nCands] candidates grouped by structure: thread i runs candidate sweep_order[i]
   int32_t sweep_ok;                // the batch fits the per-thread caps of sweep.cuh
+  int32_t warp_ok;                 // the two-nodes-per-round FK schedule of rollout.cuh computes every possible parent of an object before the object
 
   const KShape* dshape; const KShapeBody* dbody;   // dynamic
   const KShape* sshape; const KShapeBody* sbody;   // static

@@ -234,6 +234,7 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     std::vector<int> used(nR, 0);
     for (int n = 0; n < nD; ++n) { const int r = roundOf[n]; H.rounds[2 * r + used[r]++] = n; }
     P.nRounds = nR;
+    H.roundOf.assign(roundOf.begin(), roundOf.end());
   }
   // ---- static parents get a shared-memory slot behind the dynamic nodes; FK program words
   std::vector<int> statParSlot;   // static node index -> slot, built lazily
@@ -484,6 +485,8 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   }
 
   // ---- candidates
+  P.warp_ok = 1;
+  for (int b : objBodies) { const int pr = H.dyn[bodyRef[b]].parent; if (pr >= 0 && H.roundOf[pr] >= H.roundOf[bodyRef[b]]) P.warp_ok = 0; }
   H.cands.resize(nCands);
   H.vias.reserve(nConsIn); H.acts.reserve(nConsIn);
   std::vector<std::pair<int, int>> order;   // (sort key, constraint index)
@@ -590,6 +593,11 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
       g.parent_tree = -1;
       if (cc[k].kind == AFF_CON_CONNECT) g.parent_tree = underObj[cc[k].body_b] ? -2 - (underObj[cc[k].body_b] - 1) : treeB[cc[k].body_b];
       if (cc[k].kind == AFF_CON_CONNECT && cc[k].body_b >= 0 && underObj[cc[k].body_b] == g.slot + 1) { err = "connect onto the object's own subtree"; return AFF_ERR_INVALID; }
+      // The warp-per-candidate FK composes an object with its parent's pose of the same step only if the
+      // parent sits in an earlier round of the schedule; a parent in a later round (an object listed before
+      // the robot, or put onto another object's subtree) would be read one step late.  Such batches run on
+      // the thread-per-candidate kernel, whose FK walks objects after everything else.
+      if (cc[k].kind == AFF_CON_CONNECT && g.parent >= 0 && H.roundOf[g.parent] >= H.roundOf[bodyRef[cc[k].body_a]]) P.warp_ok = 0;
       H.gcons.push_back(g);
     }
     kc.n_gcon = (int)H.gcons.size() - kc.first_gcon;

@@ -1177,6 +1177,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
   int success = 1, rows = 1;
 
   for (int iter = 0; iter < nSteps; ++iter) {
+    const int successPrev = success;
     // ---- task switch / qFilt (:166-180)
     if (prevMask != activeMask) qFilt = 1.0;
     if (qFiltDecay <= 0.0) qFilt = 0.0;
@@ -1510,6 +1511,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
     if (cm.minDist < r_minDist) { r_minDist = cm.minDist; r_b1 = cm.minB1; r_b2 = cm.minB2; }
     if (qlog && lane < nJ && rows < qrows) qlog[(size_t)rows * nJ + lane] = q[lane];
     rows++;
+    if (P.opts.early_exit && !success && successPrev) break;     // opt-in: the reference's commented-out break (:368-373)
   }
   if (lane == 0) {
     aff_result res;

@@ -34,9 +34,11 @@
 #if defined(AFF_EMULATE) || !defined(AFFT_BLOCK_SYNC)
 #define T_SYNC() do { } while (0)
 #define T_BLOCK_MAX(v) (v)
+#define T_BLOCK_ANY(p) (p)
 #else
 #define T_SYNC() __syncthreads()
 #define T_BLOCK_MAX(v) t_block_max(v)
+#define T_BLOCK_ANY(p) __syncthreads_or(p)
 AFF_DEV int t_block_max(int v)
 {
   __shared__ int smax;
@@ -466,8 +468,11 @@ AFF_DEV void t_rollout(const KPlan& P, int cand, TState& S, bool alive)
   const int loopSteps = T_BLOCK_MAX(alive ? nSteps : 0);
   double blending = 1.0, phaseScale = 0.0, alphaEff = 0.0;
   int m = 0, singular = 0, ikRes = 0, id0 = -1, id1 = -1, fast = 0;
+  bool running = alive;      // early exit (opt-in) stops a failed rollout; its thread keeps meeting the block's barriers
   for (int iter = 0; iter < loopSteps; ++iter) {
-    const bool act = alive && iter < nSteps;
+    if (P.opts.early_exit && !T_BLOCK_ANY(running && iter < nSteps)) break;
+    const bool act = running && iter < nSteps;
+    const int successPrev = success;
     T_SYNC();
     if (act) {   // ======== phase A: trajectories, constraints, activations, task errors
     // ---- task switch / qFilt (:166-180)
@@ -838,6 +843,7 @@ AFF_DEV void t_rollout(const KPlan& P, int cand, TState& S, bool alive)
     if (cm.minDist < r_minDist) { r_minDist = cm.minDist; r_b1 = cm.minB1; r_b2 = cm.minB2; }
     if (qlog && rows < qrows) for (int j = 0; j < nJ; ++j) qlog[(size_t)rows * nJ + j] = q[j];
     rows++;
+    if (P.opts.early_exit && !success && successPrev) running = false;     // the reference's commented-out break (:368-373)
     }
   }
   if (!alive) return;

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define AFF_ABI_VERSION 1
+#define AFF_ABI_VERSION 2
 
 /* ------------------------------------------------------------------ status */
 typedef enum aff_status {
@@ -204,6 +204,12 @@ typedef struct aff_opts {
   double q_filt_decay;  /* 0.1   (:151)                                          */
   int32_t n_after_steps;/* 500   (:102)                                          */
   int32_t log_q;        /* 1: keep q(t) for aff_batch_fetch_q (parity samples)   */
+  int32_t early_exit;   /* 0 (default, the reference's behaviour: every rollout runs all its steps).
+                           1: a rollout stops at the end of the step in which it first failed - the
+                           `break` the reference keeps commented out (:368-373).  Verdict, failure
+                           code / step / ids are unchanged; the costs of FAILED candidates are then
+                           averaged over fewer steps, so their order among themselves may differ. */
+  int32_t reserved;
 } aff_opts;
 
 void aff_default_opts(aff_opts* o);

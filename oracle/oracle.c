@@ -1402,6 +1402,7 @@ int oracle_predict(const aff_scene_desc* scene, const aff_task_desc* tasks_all, 
     int success = 1;
     compute_emask(&P);
     for (int iter = 0; iter < nSteps; ++iter) {
+      const int successPrev = success;
       /* :166-180 */
       int taskSwitch = 0;
       for (int i = 0; i < P.nTasks; ++i) if (a_prev[i] != a_des[i]) taskSwitch = 1;
@@ -1460,6 +1461,8 @@ int oracle_predict(const aff_scene_desc* scene, const aff_task_desc* tasks_all, 
       }
       if (q_log && (size_t)rows < q_log_rows) for (int c = 0; c < nJ; ++c) q_log[(size_t)rows * nJ + c] = g->q[g->ikj[c]];
       rows++;
+      /* :365-373, the reference's commented-out `break`: opt-in only */
+      if (opts->early_exit && !success && successPrev) break;
       t += dt;
     }
     out->jl_cost = out->jl_cost / (double)rows;     /* :383-384 */

@@ -67,3 +67,25 @@ def test_sweep_kernel_source_on_a_mixed_batch(scene):
     emu, _ = eb.predict(scene, b, opts, sweep=True)
     assert [r.as_tuple() for r in emu] == [r.as_tuple() for r in ref]
     assert len(set(r.code for r in ref)) >= 2
+
+
+def test_early_exit_is_opt_in_and_keeps_verdicts(scene, sweep):
+    """opts.early_exit (the reference's commented-out break, src/TrajectoryPredictor.cpp:368-373): a failed
+    rollout stops at the end of its failing step; verdict, code and failure step are those of the full run,
+    and the kernel source agrees with the oracle on every field."""
+    b = ab.HostBatch(scene)
+    n = b.add_perturbed("get italian_seasoning_bowl", 4, seed0=1234)
+    full, early = ab.default_opts(), ab.default_opts(early_exit=True)
+    stopped = 0
+    for i in range(n):
+        r0, _ = ob.predict(scene, b, i, full)
+        r1, _ = ob.predict(scene, b, i, early)
+        (e1,), _ = eb.predict(scene, b, early, first=i, count=1, sweep=sweep)
+        assert e1.as_tuple() == r1.as_tuple()
+        assert (r0.success, r0.first_code, r0.first_fail_step) == (r1.success, r1.first_code, r1.first_fail_step)
+        if not r1.success:
+            assert r1.n_steps == r1.first_fail_step + 2 < r0.n_steps      # rows = initial row + steps up to the failing one
+            stopped += 1
+        else:
+            assert r1.as_tuple() == r0.as_tuple()
+    assert stopped >= 1

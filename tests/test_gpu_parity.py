@@ -471,3 +471,13 @@ def test_large_batch_runs_on_the_sweep_kernel_and_matches(scene, kernel, monkeyp
     for i in list(range(0, n, 97)) + [n - 1]:
         ref, _ = ob.predict(scene, batch, i, opts)
         assert gpu[i].as_tuple() == ref.as_tuple()
+
+
+def test_early_exit_matches_oracle_on_the_gpu(scene):
+    batch = ab.HostBatch(scene)
+    n = batch.add_perturbed("get italian_seasoning_bowl", 40, seed0=1234)
+    opts = ab.default_opts(early_exit=True)
+    gpu = ab.predict_batch(scene, batch, opts)
+    ref = ob.predict_batch(scene, batch, opts, n_threads=os.cpu_count() or 1)
+    assert [r.as_tuple() for r in gpu] == [r.as_tuple() for r in ref]
+    assert any(r.n_steps < 1556 for r in gpu) and any(r.n_steps == 1556 for r in gpu)

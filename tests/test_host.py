@@ -292,3 +292,26 @@ def test_apply_rollout_attaches_at_the_grasp_step(built):
     # held: a second get of the same object is refused the way the reference words it
     with pytest.raises(ab.AffError, match="already held|SUCCESS"):
         ab.HostBatch(scene).add_action("get italian_seasoning_bowl")
+
+
+def test_reparenting_onto_a_later_body_keeps_the_scene_valid(built):
+    """Graph::restoreParentFirstOrder: after a connect onto a body with a HIGHER index the body array is
+    re-sorted (parents first), ids are remapped by name, the world pose is kept, and prediction works."""
+    import numpy as np
+    import oracle_binding as ob
+    import emu_binding as eb
+    s = ab.HostScene()
+    before = s.body_id("italian_seasoning_bowl")
+    assert before < s.body_id("tray_pos2")
+    pose = ob.fk(s)[before].copy()
+    s.connect("italian_seasoning_bowl", "tray_pos2")
+    after = s.body_id("italian_seasoning_bowl")
+    assert after > s.body_id("tray_pos2") and after != before
+    assert np.abs(ob.fk(s)[after] - pose).max() < 1e-12
+    b = ab.HostBatch(s)
+    assert b.add_action("get italian_seasoning_bowl") == 2
+    opts = ab.default_opts()
+    ref, _ = ob.predict(s, b, 0, opts)
+    for sweep in (False, True):
+        (emu,), _ = eb.predict(s, b, opts, first=0, count=1, sweep=sweep)
+        assert emu.as_tuple() == ref.as_tuple()

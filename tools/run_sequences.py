@@ -7,7 +7,10 @@ with 0 failed actions" (/root/reference/examples/TestLLMSim.cpp:246, unittest.sh
 config/xml/pizza/g_scenario_pizza.xml:38-184).  The sequence texts are copied into
 tests/golden/pizza_sequences.json so this runs without /root/reference.
 
-usage: python tools/run_sequences.py [name ...]      (default: all)
+usage: python tools/run_sequences.py [--lift-arm-speed-limits] [name ...]      (default: all)
+
+--lift-arm-speed-limits: the discriminating experiment of DESIGN.md section 2: the same sequences on a
+copy of the scene whose seven arm joints per side have no speed limit (the fingers keep theirs).
 """
 import json
 import os
@@ -40,13 +43,30 @@ def expand(name, seqs, depth=0):
     return out
 
 
+SCENE_PATH = [ab.PIZZA_SCENE]
+
+
+def lifted_scene():
+    out = []
+    for line in open(ab.PIZZA_SCENE).read().split("\n"):
+        if line.startswith("joint j2s7s300_joint_") and "finger" not in line:
+            p = line.split(" ")
+            p[8] = repr(1.0e308)       # joint <name> <type> <constrained> q_init q0 q_min q_max SPEED acc ...
+            line = " ".join(p)
+        out.append(line)
+    path = "/tmp/pizza_no_arm_speed_limit.affscene"
+    with open(path, "w") as f:
+        f.write("\n".join(out))
+    return path
+
+
 def run_actions(actions, verbose=True, n_threads=8, stop_on_fail=True):
     """-> list of (action, status, detail).  status: ok / infeasible / unsupported / reset"""
-    scene = ab.HostScene()
+    scene = ab.HostScene(SCENE_PATH[0])
     rows = []
     for a in actions:
         if a.startswith("reset"):
-            scene = ab.HostScene()
+            scene = ab.HostScene(SCENE_PATH[0])
             rows.append((a, "reset", ""))
             continue
         b = ab.HostBatch(scene)
@@ -83,7 +103,12 @@ def run_actions(actions, verbose=True, n_threads=8, stop_on_fail=True):
 
 def main():
     seqs = load_sequences()
-    names = sys.argv[1:] or list(seqs)
+    args = sys.argv[1:]
+    if "--lift-arm-speed-limits" in args:
+        args.remove("--lift-arm-speed-limits")
+        SCENE_PATH[0] = lifted_scene()
+        print("arm joint speed limits lifted (%s)" % SCENE_PATH[0])
+    names = args or list(seqs)
     summary = {}
     for nm in names:
         actions = expand(nm, seqs)
