@@ -86,7 +86,7 @@ HOST_SYMBOLS = [
     "aff_host_scene_device", "aff_host_batch_create", "aff_host_batch_destroy", "aff_host_batch_clear",
     "aff_host_batch_add_action", "aff_host_batch_add_perturbed", "aff_host_batch_num_tasks", "aff_host_batch_num_constraints",
     "aff_host_batch_num_candidates", "aff_host_batch_tasks", "aff_host_batch_constraints", "aff_host_batch_candidates",
-    "aff_host_batch_task_name", "aff_host_predict", "aff_host_format_message", "aff_host_check_trajectory", "aff_host_scene_apply_rollout", "aff_host_predict_sequence",
+    "aff_host_batch_task_name", "aff_host_predict", "aff_host_format_message", "aff_host_check_trajectory", "aff_host_scene_apply_rollout", "aff_host_predict_sequence", "aff_host_rollout_transforms", "aff_host_format_message_q",
 ]
 
 
@@ -126,6 +126,8 @@ def lib():
         "aff_host_predict": (i32, [vp, vp, dbl, i32, i32, vp, vp, sz]),
         "aff_host_format_message": (i32, [vp, vp, vp, dbl, vp, sz]),
         "aff_host_scene_apply_rollout": (i32, [vp, vp, sz, vp, i32, dbl]),
+        "aff_host_rollout_transforms": (i32, [vp, vp, sz, vp, i32, dbl, vp]),
+        "aff_host_format_message_q": (i32, [vp, vp, vp, dbl, vp, vp, sz]),
         "aff_host_predict_sequence": (i32, [vp, cstr, dbl, i32, vp, vp, vp, sz, i32]),
         "aff_host_check_trajectory": (i32, [vp, vp, sz, i32, i32, i32, dbl, i32, vp, vp, vp, vp, vp, vp, sz, vp, sz]),
     }
@@ -206,6 +208,17 @@ class HostScene:
         rc = lib().aff_host_scene_apply_rollout(self.h, batch.h, cand, q.ctypes.data_as(C.c_void_p), q.shape[0], dt)
         if rc != AFF_OK:
             raise AffError("apply_rollout failed: %s" % lib().aff_host_last_error().decode())
+
+    def rollout_transforms(self, batch, cand, q, dt=0.01):
+        """PredictionResult::bodyTransforms of one candidate: rows x n_bodies x 12 from its joint log q."""
+        import numpy as np
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        out = np.zeros((q.shape[0], self.n_bodies, 12))
+        rc = lib().aff_host_rollout_transforms(self.h, batch.h, cand, q.ctypes.data_as(C.c_void_p), q.shape[0], dt,
+                                               out.ctypes.data_as(C.c_void_p))
+        if rc != AFF_OK:
+            raise AffError("rollout_transforms failed: %s" % lib().aff_host_last_error().decode())
+        return out
 
     def predict_sequence(self, text, dt=0.01, device=0, max_actions=16, msg_len=768):
         """aff_host_predict_sequence: [(winner record, number of candidates, message)] per action."""
@@ -320,9 +333,15 @@ class HostBatch:
         return {"action_result": bool(ar.value), "ok": bool(ok.value), "quality": quality.value, "set_trajectory": bool(st.value),
                 "message": msg.value.decode(), "raw": raw, "q": q[:min(rows, max_rows)].copy()}
 
-    def format_message(self, result, dt=0.01):
-        buf = C.create_string_buffer(1024)
-        lib().aff_host_format_message(self.scene.h, self.h, C.byref(result), dt, buf, 1024)
+    def format_message(self, result, dt=0.01, q_fail=None):
+        """q_fail: joint values of the failing step (row fail_step + 1 of the q log) for the per-joint detail."""
+        buf = C.create_string_buffer(4096)
+        if q_fail is None:
+            lib().aff_host_format_message(self.scene.h, self.h, C.byref(result), dt, buf, 4096)
+        else:
+            import numpy as np
+            qf = np.ascontiguousarray(q_fail, dtype=np.float64)
+            lib().aff_host_format_message_q(self.scene.h, self.h, C.byref(result), dt, qf.ctypes.data_as(C.c_void_p), buf, 4096)
         return buf.value.decode()
 
 

@@ -255,6 +255,37 @@ void Graph::applyRollout(const aff_constraint* cons, int nCons, const double* ql
   if (restoreParentFirstOrder()) computeForwardKinematics();
 }
 
+void Graph::rolloutTransforms(const aff_constraint* cons, int nCons, const double* qlog, int rows, double dt, double* out) const
+{
+  if (!qlog || rows < 1 || !out) throw std::runtime_error("rolloutTransforms: no joint log");
+  Graph g = *this;                      // body ids stay those of the batch: no re-sort in here
+  const size_t nb = g.bodies.size();
+  auto setRow = [&](int row) {
+    for (Joint& j : g.joints) if (j.jacobiIndex >= 0) j.q_init = qlog[(size_t)row * nJ + j.jacobiIndex];
+    g.computeForwardKinematics();
+  };
+  auto record = [&](int row) {
+    double* dst = out + (size_t)row * nb * 12;
+    for (size_t b = 0; b < nb; ++b) g.bodies[b].A_BI.to12(dst + 12 * b);
+  };
+  setRow(0);
+  record(0);
+  std::vector<char> fired((size_t)std::max(nCons, 0), 0);
+  double tnow = 0.0;
+  for (int iter = 0; iter + 1 < rows; ++iter) {
+    tnow = tnow + dt;
+    // events of iteration `iter` act on the poses of row `iter` (still set), row iter + 1 sees their effect
+    for (int k = 0; k < nCons; ++k) {
+      if (fired[k]) continue;
+      const aff_constraint& c = cons[k];
+      if (c.kind == AFF_CON_CONNECT && c.t - tnow < 1.0e-8) { g.connectBody(c.body_a, c.body_b, c.dim == 1); fired[k] = 1; }
+      else if (c.kind == AFF_CON_COLLISION && c.t - tnow < 0.0) fired[k] = 1;      // shape flags do not move anything
+    }
+    setRow(iter + 1);
+    record(iter + 1);
+  }
+}
+
 bool Graph::restoreParentFirstOrder()
 {
   const int nb = (int)bodies.size();

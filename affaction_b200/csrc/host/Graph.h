@@ -86,6 +86,13 @@ public:
   // body array (relative order kept), all body indices remapped.  Body ids handed out before the call are
   // stale afterwards (names are not).  Returns true if anything moved.
   bool restoreParentFirstOrder();
+  // World transforms of EVERY body for every row of a rollout's joint log: what the reference keeps in
+  // PredictionResult::bodyTransforms ((nSteps+1) x nBodies x 12: org + rot row-major per body,
+  // src/TrajectoryPredictor.cpp:111-118,356-363) and ActionComponent replays as the ghost animation
+  // (src/ActionComponent.cpp:429-462).  Replayed on a copy of the graph from the GPU's q(t): row 0 is the
+  // initial state, row i+1 the state after step i with the constraints that fired in it applied.
+  // out: rows x bodies.size() x 12 doubles.  *this is not modified.
+  void rolloutTransforms(const struct aff_constraint* cons, int nCons, const double* qlog, int rows, double dt, double* out) const;
 
   // RcsGraph_computeBodyAABB over shapes with the distance flag. false if none.
   bool computeBodyAABB(int body, double xyzMin[3], double xyzMax[3]) const;

@@ -23,7 +23,7 @@ static bool isArticulated(const Graph& g, int body)
 }
 
 TrajectoryPredictor::PredictionResult TrajectoryPredictor::convert(const aff_result& r, const Graph& graph,
-                                                                   const std::vector<std::string>& taskNames, double dt)
+                                                                   const std::vector<std::string>& taskNames, double dt, const double* qFail)
 {
   PredictionResult p;
   p.raw = r;
@@ -52,6 +52,14 @@ TrajectoryPredictor::PredictionResult TrajectoryPredictor::convert(const aff_res
     case AFF_CODE_JOINT_LIMIT:
       p.message = "ERROR: REASON: Joint limit problem. The robot is not able to do move well enough. ";
       p.message += " DEVELOPER: " + std::to_string(r.fail_id0) + " joint limit violations";
+      if (qFail) {
+        for (const Joint& j : graph.joints) {
+          if (j.constrained || j.jacobiIndex < 0) continue;
+          const double qi = qFail[j.jacobiIndex];
+          if (qi < j.q_min || qi > j.q_max)
+            p.message += " Joint " + j.name + ": " + std::to_string(qi) + " outside [" + std::to_string(j.q_min) + " ... " + std::to_string(j.q_max) + "]";
+        }
+      }
       break;
     case AFF_CODE_COLLISION: {
       const std::string b1 = bodyName(graph, r.fail_id0), b2 = bodyName(graph, r.fail_id1);

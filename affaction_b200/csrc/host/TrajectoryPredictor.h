@@ -41,7 +41,7 @@ public:
     std::string minDistBdy1, minDistBdy2;
     std::vector<double> jMask;             // nJ entries, 0 / 1
     std::vector<double> optimizationParameters;
-    std::vector<double> bodyTransforms;    // opt-in only: see fetchJointTrajectory
+    std::vector<double> bodyTransforms;    // opt-in only (68 MB per candidate): Graph::rolloutTransforms / aff_host_rollout_transforms
     aff_result raw;                        // the record the GPU wrote
   };
 
@@ -53,7 +53,9 @@ public:
 
   // aff_result -> PredictionResult, rebuilding `message` as checkState() /
   // predict() word it (src/TrajectoryPredictor.cpp:137,309-324,770,807-818,844-867).
-  static PredictionResult convert(const aff_result& r, const Graph& graph, const std::vector<std::string>& taskNames, double dt);
+  // qFail (optional): joint values of the failing step, jacobi order -> per-joint detail of a joint-limit message (:810-818)
+  static PredictionResult convert(const aff_result& r, const Graph& graph, const std::vector<std::string>& taskNames, double dt,
+                                  const double* qFail = nullptr);
 };
 
 }   // namespace aff

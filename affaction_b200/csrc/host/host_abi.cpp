@@ -114,6 +114,16 @@ int aff_host_scene_apply_rollout(aff_host_scene* s, const aff_host_batch* b, siz
   } catch (const std::exception& e) { g_hostError = e.what(); return AFF_ERR_INVALID; }
 }
 
+int aff_host_rollout_transforms(aff_host_scene* s, const aff_host_batch* b, size_t cand, const double* qlog, int rows, double dt, double* out)
+{
+  try {
+    if (!s || !b || cand >= b->batch.candidates.size()) { g_hostError = "rollout_transforms: candidate out of range"; return AFF_ERR_INVALID; }
+    const aff_candidate& c = b->batch.candidates[cand];
+    s->graph.rolloutTransforms(b->batch.constraints.data() + c.first_constraint, c.n_constraints, qlog, rows, dt, out);
+    return AFF_OK;
+  } catch (const std::exception& e) { g_hostError = e.what(); return AFF_ERR_INVALID; }
+}
+
 aff_scene* aff_host_scene_device(aff_host_scene* s, int device)
 {
   if (!s->device) {
@@ -248,6 +258,16 @@ int aff_host_format_message(aff_host_scene* s, aff_host_batch* b, const aff_resu
   static const std::vector<std::string> none;
   const auto& names = (r->idx >= 0 && (size_t)r->idx < b->batch.taskNames.size()) ? b->batch.taskNames[r->idx] : none;
   const auto p = TrajectoryPredictor::convert(*r, s->graph, names, dt);
+  std::strncpy(out, p.message.c_str(), n - 1);
+  out[n - 1] = '\0';
+  return (int)p.message.size();
+}
+
+int aff_host_format_message_q(aff_host_scene* s, aff_host_batch* b, const aff_result* r, double dt, const double* qFail, char* out, size_t n)
+{
+  static const std::vector<std::string> none;
+  const auto& names = (r->idx >= 0 && (size_t)r->idx < b->batch.taskNames.size()) ? b->batch.taskNames[r->idx] : none;
+  const auto p = TrajectoryPredictor::convert(*r, s->graph, names, dt, qFail);
   std::strncpy(out, p.message.c_str(), n - 1);
   out[n - 1] = '\0';
   return (int)p.message.size();

@@ -41,6 +41,14 @@ int aff_host_scene_set_ik_state(aff_host_scene* s, const double* q, int n);
  * ConnectBody / CollisionModel constraints applied at the steps they fired (with the joint state of
  * those steps), then the final joint state.  qlog = rows x nJ from aff_batch_fetch_q. */
 int aff_host_scene_apply_rollout(aff_host_scene* s, const aff_host_batch* b, size_t cand, const double* qlog, int rows, double dt);
+/* PredictionResult::bodyTransforms of ONE candidate (the winner, for the ghost animation of reference
+ * src/ActionComponent.cpp:429-462): world transform of every body for every row of its joint log,
+ * rows x aff_host_num_bodies x 12 doubles (org, then rot row-major; the layout of
+ * src/TrajectoryPredictor.cpp:356-363), replayed on the host from the q(t) the GPU logged
+ * (aff_batch_fetch_q; 68 MB per candidate in the pizza scene, so it is opt-in and never part of a
+ * throughput run).  The scene is not modified. */
+int aff_host_rollout_transforms(aff_host_scene* s, const aff_host_batch* b, size_t cand, const double* qlog, int rows,
+                                double dt, double* out);
 /* Device-side scene handle (created on first use). NULL on CUDA failure. */
 aff_scene* aff_host_scene_device(aff_host_scene* s, int device);
 
@@ -66,6 +74,11 @@ const char* aff_host_batch_task_name(const aff_host_batch* b, size_t cand, int t
 int aff_host_predict(aff_host_scene* s, aff_host_batch* b, double dt, int sort_results, int device,
                      aff_result* raw_out, char* messages, size_t msg_stride);
 int aff_host_format_message(aff_host_scene* s, aff_host_batch* b, const aff_result* r, double dt, char* out, size_t n);
+/* The same with the joint values of the failing step (row r->fail_step + 1 of the candidate's q log,
+ * jacobi order): a joint-limit message then lists every violated joint with its value and range as
+ * reference src/TrajectoryPredictor.cpp:810-818 does. */
+int aff_host_format_message_q(aff_host_scene* s, aff_host_batch* b, const aff_result* r, double dt, const double* q_fail,
+                              char* out, size_t n);
 
 /* An action sequence "a; b; c" predicted the way the reference runs one (each action is predicted
  * from the state the previous one left, examples/ExampleActionsECS.cpp:924-979): per action all

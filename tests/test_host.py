@@ -315,3 +315,52 @@ def test_reparenting_onto_a_later_body_keeps_the_scene_valid(built):
     for sweep in (False, True):
         (emu,), _ = eb.predict(s, b, opts, first=0, count=1, sweep=sweep)
         assert emu.as_tuple() == ref.as_tuple()
+
+
+def test_rollout_transforms_replay(built):
+    """aff_host_rollout_transforms: PredictionResult::bodyTransforms of one candidate from its q(t)
+    (reference src/TrajectoryPredictor.cpp:111-118,356-363).  Row 0 is the scene's FK, the last row is the
+    FK of the state apply_rollout leaves, static bodies never move, and after the grasp the object
+    travels with the hand frame it was connected to."""
+    import numpy as np
+    import oracle_binding as ob
+    s = ab.HostScene()
+    b = ab.HostBatch(s)
+    b.add_action("get fresh_tomatoes")
+    r, q = ob.predict(s, b, 0, ab.default_opts(log_q=True), log_q=True)
+    assert r.success == 1
+    T = s.rollout_transforms(b, 0, q)
+    assert T.shape == (q.shape[0], s.n_bodies, 12)
+    assert np.abs(T[0] - ob.fk(s)).max() < 1e-12       # host FK (libm) vs the oracle's: same transforms, not the same bits
+    table, obj = s.body_id("table"), s.body_id("fresh_tomatoes1")       # the body the get connects to the hand
+    assert np.abs(T[:, table] - T[0, table]).max() == 0.0
+    rot = T[:, :, 3:].reshape(T.shape[0], s.n_bodies, 3, 3)
+    assert np.abs(np.einsum("rbij,rbkj->rbik", rot[::97], rot[::97]) - np.eye(3)).max() < 1e-9      # orthonormal
+    # lifted by about liftHeight at the end, untouched before the grasp (t_grasp = 0.05 + 0.66 * 10 s)
+    assert np.abs(T[:600, obj] - T[0, obj]).max() == 0.0
+    assert 0.08 < T[-1, obj, 2] - T[0, obj, 2] < 0.2
+    s2 = ab.HostScene()
+    b2 = ab.HostBatch(s2)
+    b2.add_action("get fresh_tomatoes")
+    s2.apply_rollout(b2, 0, q)
+    A_end = ob.fk(s2)
+    for name in ("fresh_tomatoes1", "hand_left", "hand_right", "table"):
+        assert np.abs(A_end[s2.body_id(name)] - T[-1, s.body_id(name)]).max() < 1e-12
+
+
+def test_joint_limit_message_lists_the_joints(built):
+    """reference src/TrajectoryPredictor.cpp:807-818: with the joint values of the failing step the
+    joint-limit message names every violated joint with its value and range."""
+    import oracle_binding as ob
+    s = ab.HostScene()
+    b = ab.HostBatch(s)
+    b.add_perturbed("get italian_seasoning_bowl", 64, seed0=0xAFFAC7)
+    opts = ab.default_opts(log_q=True)
+    for i in range(64):
+        r, q = ob.predict(s, b, i, opts, log_q=True)
+        if r.code == -3:
+            short = b.format_message(r)
+            long = b.format_message(r, q_fail=q[r.fail_step + 1])
+            assert long.startswith(short) and long.count(" outside [") == r.fail_id0 >= 1
+            return
+    pytest.skip("no joint-limit verdict among the first 64 perturbed candidates")
