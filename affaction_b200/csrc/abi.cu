@@ -416,6 +416,50 @@ int aff_predict_batch(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, 
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
   if (!s || !out) return fail(AFF_ERR_INVALID, "aff_predict_batch: null argument");
+  // One device batch tracks at most AFFK_MAX_OBJ re-parentable objects (they are explicit state of the
+  // kernels).  A call whose candidates name more objects in total - e.g. the candidates of three different
+  // `get` commands - is split into groups of candidates whose objects fit, each group is predicted as its
+  // own batch, and the records come back in the caller's order.
+  {
+    auto objectsOf = [&](const aff_candidate& c, int32_t* objs) {
+      int n = 0;
+      auto add = [&](int32_t b) { for (int k = 0; k < n; ++k) if (objs[k] == b) return; if (n < 8) objs[n] = b; ++n; };
+      if (c.pose_body >= 0) add(c.pose_body);
+      if (c.first_constraint >= 0 && (size_t)(c.first_constraint + c.n_constraints) <= n_cons)
+        for (int k = 0; k < c.n_constraints; ++k) {
+          const aff_constraint& cc = cons[c.first_constraint + k];
+          if (cc.kind == AFF_CON_CONNECT || cc.kind == AFF_CON_COLLISION) add(cc.body_a);
+        }
+      return n;
+    };
+    std::vector<std::vector<int32_t>> groupObjs;
+    std::vector<std::vector<size_t>> groupCands;
+    bool single = true;
+    for (size_t i = 0; i < n_cands; ++i) {
+      int32_t objs[8];
+      const int no = std::min(objectsOf(cands[i], objs), 8);
+      size_t g = 0;
+      for (; g < groupObjs.size(); ++g) {
+        std::vector<int32_t> u = groupObjs[g];
+        for (int k = 0; k < no; ++k) if (std::find(u.begin(), u.end(), objs[k]) == u.end()) u.push_back(objs[k]);
+        if ((int)u.size() <= AFFK_MAX_OBJ || u.size() == groupObjs[g].size()) { groupObjs[g] = u; break; }
+      }
+      if (g == groupObjs.size()) { groupObjs.emplace_back(objs, objs + no); groupCands.emplace_back(); }
+      groupCands[g].push_back(i);
+      if (g > 0) single = false;
+    }
+    if (!single) {
+      for (size_t g = 0; g < groupCands.size(); ++g) {
+        std::vector<aff_candidate> local;
+        for (size_t i : groupCands[g]) local.push_back(cands[i]);
+        std::vector<aff_result> res(local.size());
+        const int rc = aff_predict_batch(s, tasks, n_tasks, cons, n_cons, local.data(), local.size(), opts, res.data());
+        if (rc != AFF_OK) return rc;
+        for (size_t k = 0; k < local.size(); ++k) { out[groupCands[g][k]] = res[k]; out[groupCands[g][k]].idx = (int32_t)groupCands[g][k]; }
+      }
+      return AFF_OK;
+    }
+  }
   const auto t0 = now();
   // Large batches go through in chunks of whole waves of the persistent grid: the host compiles and
   // uploads chunk k+1 (default stream) while the kernels of chunk k run on their own stream.

@@ -108,4 +108,29 @@ ActionDoubleGet::ActionDoubleGet(const ActionScene& domain, const Graph& graph, 
   explanation = "Getting " + params[0] + " and " + params[1];
 }
 
+ActionDoubleGetPairs::ActionDoubleGetPairs(const ActionScene& domain, const Graph& graph, std::vector<std::string> params)
+{
+  if (params.size() != 2)
+    throw ActionException("ERROR REASON: Action command received with " + std::to_string(params.size()) + " arguments, but 2 are expected",
+                          ActionException::ParamInvalid);
+  addAction(std::unique_ptr<ActionBase>(new ActionGet(domain, graph, {params[0]})));
+  addAction(std::unique_ptr<ActionBase>(new ActionGet(domain, graph, {params[1]})));
+  const size_t n1 = actions[0]->getNumSolutions(), n2 = actions[1]->getNumSolutions();
+  for (size_t i = 0; i < n1; ++i)
+    for (size_t j = 0; j < n2; ++j) {
+      if (!actions[0]->initialize(domain, graph, i) || !actions[1]->initialize(domain, graph, j)) continue;
+      const std::vector<std::string> h1 = actions[0]->getManipulators(), h2 = actions[1]->getManipulators();
+      if (!h1.empty() && !h2.empty() && h1[0] != h2[0]) pairs.emplace_back(i, j);
+    }
+  if (pairs.empty())
+    throw ActionException("ERROR REASON: No pair of free hands can get " + params[0] + " and " + params[1], ActionException::KinematicallyImpossible);
+  explanation = "Getting " + params[0] + " and " + params[1] + " (every hand pairing)";
+}
+
+bool ActionDoubleGetPairs::initialize(const ActionScene& domain, const Graph& graph, size_t solutionRank)
+{
+  if (solutionRank >= pairs.size()) return false;
+  return actions[0]->initialize(domain, graph, pairs[solutionRank].first) && actions[1]->initialize(domain, graph, pairs[solutionRank].second);
+}
+
 }   // namespace aff

@@ -44,6 +44,26 @@ private:
   std::string explanation;
 };
 
+// Extension named in SURVEY 8(d) config 3 / BASELINE.json configs[2] ("bimanual candidate pairs"):
+// "double_get_pairs <object 1> <object 2>".  The candidate set is the Cartesian product
+// affordanceMap(object 1) x affordanceMap(object 2) of the two gets' Capability x Affordance solutions,
+// minus the pairs that would use one hand twice; candidate order = the product's mixed-radix order.
+// The reference's double_get (above) pins one hand pairing and so yields exactly one candidate.
+class ActionDoubleGetPairs : public ActionComposite
+{
+public:
+  ActionDoubleGetPairs(const ActionScene& domain, const Graph& graph, std::vector<std::string> params);
+  ActionDoubleGetPairs(const ActionDoubleGetPairs& other) : ActionComposite(other), pairs(other.pairs), explanation(other.explanation) {}
+  std::unique_ptr<ActionBase> clone() const override { return std::unique_ptr<ActionBase>(new ActionDoubleGetPairs(*this)); }
+  std::string explain() const override { return explanation; }
+  size_t getNumSolutions() const override { return pairs.size(); }
+  bool initialize(const ActionScene& domain, const Graph& graph, size_t solutionRank) override;
+
+private:
+  std::vector<std::pair<size_t, size_t>> pairs;     // (solution of get 1, solution of get 2), hands distinct
+  std::string explanation;
+};
+
 }   // namespace aff
 
 #endif

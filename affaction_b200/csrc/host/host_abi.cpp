@@ -400,13 +400,14 @@ std::unique_ptr<ActionBase> ActionFactory::create(const ActionScene& domain, con
   if (name == "get") a.reset(new ActionGet(domain, graph, params));
   else if (name == "put") a.reset(new ActionPut(domain, graph, params));
   else if (name == "double_get") a.reset(new ActionDoubleGet(domain, graph, params));
+  else if (name == "double_get_pairs") a.reset(new ActionDoubleGetPairs(domain, graph, params));
   else if (name == "drop") a.reset(new ActionDrop(domain, graph, params));
   else if (name == "pose") a.reset(new ActionPose(domain, graph, params));
   else if (name == "finger_push" || name == "poke") a.reset(new ActionFingerPush(domain, graph, params));
   else if (name == "pour") a.reset(new ActionPour(domain, graph, params));
   else
     throw ActionException("ERROR: REASON: Action '" + name + "' is not part of the GPU predict path" +
-                          " SUGGESTION: Use one of: get, put, pour, drop, pose, finger_push, double_get", ActionException::ParamNotFound);
+                          " SUGGESTION: Use one of: get, put, pour, drop, pose, finger_push, double_get, double_get_pairs", ActionException::ParamNotFound);
   a->setName(name);
   a->setActionParams(params);
   return a;

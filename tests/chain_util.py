@@ -18,3 +18,22 @@ def scene_after_get(obj, require_success=True):
     # and then travels with the hand to the final joint state (Graph::applyRollout)
     scene.apply_rollout(b, 0, q)
     return scene
+
+
+MANY_SCENE = "unittest_predict_many.affscene"
+
+
+def scene_many_after_get():
+    """The reference's 120-Supportable unit-test table (config/xml/unittest/g_scenario_unittest_predict_many.xml,
+    resources/g_table_multi.xml; flattened by tools/flatten_scene.py with TwoArmJaco7 on the search path for
+    its stale ../g_robo.xml include) after `get block`: the state `put block table` starts from
+    (test_multi_2 of that file).  BASELINE.json configs[1] at its stated size: 120 surface candidates."""
+    import os
+    scene = ab.HostScene(os.path.join(ab.DATA_DIR, MANY_SCENE))
+    b = ab.HostBatch(scene)
+    b.add_action("get block")
+    opts = ab.default_opts(log_q=True)
+    res = [ob.predict(scene, b, i, opts, log_q=True) for i in range(b.n_candidates)]
+    best = ab.rank([r for r, _ in res])[0]
+    scene.apply_rollout(b, best, res[best][1])
+    return scene

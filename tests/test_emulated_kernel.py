@@ -89,3 +89,17 @@ def test_early_exit_is_opt_in_and_keeps_verdicts(scene, sweep):
         else:
             assert r1.as_tuple() == r0.as_tuple()
     assert stopped >= 1
+
+
+def test_put_on_the_120_supportable_table(built, sweep):
+    """The reference's 120-Supportable unit-test scene (second flattened scene): candidate generation gives
+    120 put candidates; a sample runs through the kernel source and equals the oracle."""
+    from chain_util import scene_many_after_get
+    scene = scene_many_after_get()
+    b = ab.HostBatch(scene)
+    assert b.add_action("put block table") == 120
+    opts = ab.default_opts()
+    for i in (0, 59, 119):
+        ref, _ = ob.predict(scene, b, i, opts)
+        (emu,), _ = eb.predict(scene, b, opts, first=i, count=1, sweep=sweep)
+        assert emu.as_tuple() == ref.as_tuple()

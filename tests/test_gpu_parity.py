@@ -80,13 +80,39 @@ def test_ranked_first_matches_oracle(scene, cmd):
     assert ab.rank(gpu) == ab.rank(ref)
 
 
-def test_too_many_objects_is_reported(scene):
-    """Capacity errors are loud, not silent fallbacks."""
+def test_too_many_objects_in_one_device_batch_is_reported(scene):
+    """Capacity errors are loud, not silent fallbacks: one device batch tracks AFFK_MAX_OBJ objects."""
     batch = ab.HostBatch(scene)
     for cmd in GET_COMMANDS[:3]:
         batch.add_action(cmd)
     with pytest.raises(ab.AffError, match="AFFK_MAX_OBJ"):
-        ab.predict_batch(scene, batch, ab.default_opts())
+        ab.DeviceBatch(scene, batch, ab.default_opts())
+
+
+def test_mixed_commands_share_one_predict_call(scene):
+    """aff_predict_batch splits a call whose candidates name more objects than one device batch tracks
+    (three different gets = three objects) into groups and returns the records in the caller's order."""
+    batch = ab.HostBatch(scene)
+    for cmd in GET_COMMANDS[:3]:
+        batch.add_action(cmd)
+    opts = ab.default_opts()
+    gpu = ab.predict_batch(scene, batch, opts)
+    ref = ob.predict_batch(scene, batch, opts, n_threads=os.cpu_count() or 1)
+    assert [r.idx for r in gpu] == list(range(6))
+    assert [r.as_tuple() for r in gpu] == [r.as_tuple() for r in ref]
+
+
+def test_double_get_pairs_extension(scene):
+    """BASELINE.json configs[2]: the bimanual candidate set as the Cartesian product of the two gets'
+    solutions (hands distinct) - `double_get_pairs`, an extension; the reference's double_get pins one pairing."""
+    batch = ab.HostBatch(scene)
+    assert batch.add_action("double_get_pairs italian_seasoning_bowl tomato_sauce_bottle") == 2
+    opts = ab.default_opts(log_q=True)
+    dev = ab.DeviceBatch(scene, batch, opts)
+    dev.launch()
+    _compare(scene, batch, opts, dev, range(2))
+    hands = [(batch.task_name(i, 0), batch.task_name(i, 7)) for i in range(2)]
+    assert "hand_right" in hands[0][0] and "hand_left" in hands[0][1] and "hand_left" in hands[1][0] and "hand_right" in hands[1][1]
 
 
 def test_perturbed_sweep_matches_oracle(scene):
@@ -481,3 +507,19 @@ def test_early_exit_matches_oracle_on_the_gpu(scene):
     ref = ob.predict_batch(scene, batch, opts, n_threads=os.cpu_count() or 1)
     assert [r.as_tuple() for r in gpu] == [r.as_tuple() for r in ref]
     assert any(r.n_steps < 1556 for r in gpu) and any(r.n_steps == 1556 for r in gpu)
+
+
+def test_put_120_candidates_match_oracle(built):
+    """BASELINE.json configs[1] at its stated size: `put block table` on the reference's unit-test table with
+    120 Supportables (config/xml/unittest/g_scenario_unittest_predict_many.xml:157-160,
+    unittest/resources/g_table_multi.xml): every Capability x Affordance candidate, all fields, and the ranking."""
+    from chain_util import scene_many_after_get
+    scene = scene_many_after_get()
+    batch = ab.HostBatch(scene)
+    assert batch.add_action("put block table") == 120
+    opts = ab.default_opts()
+    gpu = ab.predict_batch(scene, batch, opts)
+    ref = ob.predict_batch(scene, batch, opts, n_threads=os.cpu_count() or 1)
+    assert [r.as_tuple() for r in gpu] == [r.as_tuple() for r in ref]
+    assert ab.rank(gpu) == ab.rank(ref)
+    assert len(set(r.first_code for r in ref)) >= 2
