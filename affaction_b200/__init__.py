@@ -1,8 +1,9 @@
 """affaction_b200 — ctypes binding of the B200 action-feasibility predictor.
 
-The product is the shared library ``libaffpredict.so`` (hand-written sm_100a
-CUDA kernels behind the C ABI of ``include/affpredict.h`` plus the C++ host
-shim of ``include/affpredict_host.h``).  This module only binds it for the
+The product is two shared libraries: ``libaffpredict.so`` (hand-written sm_100a
+CUDA kernels behind the C ABI of ``include/affpredict.h``) and ``libaffhost.so``
+(the C++ host shim of ``include/affpredict_host.h``: pure C++, it reaches the CUDA
+library through dlopen when something is predicted).  This module only binds it for the
 tests and for ``bench.py``; there is no Python or CPU implementation of the
 predict path here, and importing the library fails loudly if it has not been
 built (``make`` / ``__graft_entry__.build()``).
@@ -14,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
 # AFF_LIB_PATH: tuning experiments only (tools/try_variants.sh builds alternative libraries)
 LIB_PATH = os.environ.get("AFF_LIB_PATH") or os.path.join(_HERE, "libaffpredict.so")
+HOST_LIB_PATH = os.path.join(_HERE, "libaffhost.so")
 DATA_DIR = os.path.join(_HERE, "data")
 PIZZA_SCENE = os.path.join(DATA_DIR, "pizza.affscene")
 
@@ -71,8 +73,6 @@ def default_opts(log_q=False, early_exit=False):
     return o
 
 
-_lib = None
-
 # every symbol include/affpredict.h and include/affpredict_host.h declare
 ABI_SYMBOLS = [
     "aff_default_opts", "aff_abi_version", "aff_last_error", "aff_device_count", "aff_scene_create", "aff_scene_destroy",
@@ -90,16 +90,40 @@ HOST_SYMBOLS = [
 ]
 
 
-def lib():
-    """Load libaffpredict.so (once).  Raises if the CUDA library is missing."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.isfile(LIB_PATH):
-        raise RuntimeError("%s is missing: build it with `make` (there is no CPU fallback for the predict path)" % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+class _Libs:
+    """Attribute lookup over the two libraries: host-shim symbols come from libaffhost.so, the rest from
+    libaffpredict.so (loaded on first use of one of ITS symbols, so that code which only builds candidates -
+    the CPU reference arm of bench.py - never maps the CUDA library)."""
+
+    def __init__(self):
+        self._host = None
+        self._gpu = None
+
+    def host(self):
+        if self._host is None:
+            if not os.path.isfile(HOST_LIB_PATH):
+                raise RuntimeError("%s is missing: build it with `make`" % HOST_LIB_PATH)
+            self._host = C.CDLL(HOST_LIB_PATH)
+            _declare(self._host, HOST_SYMBOLS + ["aff_default_opts", "aff_abi_version", "aff_rank_results"])
+        return self._host
+
+    def gpu(self):
+        if self._gpu is None:
+            if not os.path.isfile(LIB_PATH):
+                raise RuntimeError("%s is missing: build it with `make` (there is no CPU fallback for the predict path)" % LIB_PATH)
+            self._gpu = C.CDLL(LIB_PATH)
+            _declare(self._gpu, ABI_SYMBOLS)
+        return self._gpu
+
+    def __getattr__(self, name):
+        if name.startswith("aff_host_") or name in ("aff_default_opts", "aff_abi_version", "aff_rank_results"):
+            return getattr(self.host(), name)
+        return getattr(self.gpu(), name)
+
+
+def _signatures():
     vp, sz, dbl, i32, cstr = C.c_void_p, C.c_size_t, C.c_double, C.c_int, C.c_char_p
-    sig = {
+    return {
         "aff_last_error": (cstr, []), "aff_abi_version": (i32, []), "aff_device_count": (i32, []),
         "aff_default_opts": (None, [vp]),
         "aff_scene_create": (i32, [vp, i32, C.POINTER(vp)]), "aff_scene_destroy": (None, [vp]),
@@ -131,12 +155,28 @@ def lib():
         "aff_host_predict_sequence": (i32, [vp, cstr, dbl, i32, vp, vp, vp, sz, i32]),
         "aff_host_check_trajectory": (i32, [vp, vp, sz, i32, i32, i32, dbl, i32, vp, vp, vp, vp, vp, vp, sz, vp, sz]),
     }
-    for name, (res, args) in sig.items():
+
+
+def _declare(L, names):
+    sig = _signatures()
+    for name in names:
+        if name not in sig:
+            continue
         fn = getattr(L, name)
-        fn.restype = res
-        fn.argtypes = args
-    _lib = L
-    return L
+        fn.restype, fn.argtypes = sig[name]
+
+
+_libs = _Libs()
+
+
+def lib():
+    """Both libraries behind one attribute lookup (see _Libs).  Raises if a library is missing."""
+    return _libs
+
+
+def gpu_library_loaded():
+    """True once libaffpredict.so has been mapped by this module (the CPU reference arm checks that it never is)."""
+    return _libs._gpu is not None
 
 
 class AffError(RuntimeError):

@@ -175,14 +175,7 @@ struct aff_batch
 
 extern "C" {
 
-int aff_abi_version(void) { return AFF_ABI_VERSION; }
 const char* aff_last_error(void) { return g_err.c_str(); }
-
-void aff_default_opts(aff_opts* o)
-{
-  if (!o) return;
-  o->dt = 0.01; o->alpha = 0.05; o->lambda = 1.0e-6; o->q_filt_decay = 0.1; o->n_after_steps = 500; o->log_q = 0; o->early_exit = 0; o->reserved = 0;
-}
 
 int aff_device_count(void)
 {
@@ -583,18 +576,6 @@ int aff_predict_batch_multi(const aff_scene_desc* desc, const int* devices, int 
   for (std::thread& t : pool) t.join();
   for (int r = 0; r < G; ++r) if (rcs[(size_t)r] != AFF_OK) return fail(rcs[(size_t)r], "aff_predict_batch_multi: device " + std::to_string(devices[r]) + ": " + errs[(size_t)r]);
   return AFF_OK;
-}
-
-void aff_rank_results(const aff_result* res, size_t n, int32_t* order)
-{
-  for (size_t i = 0; i < n; ++i) order[i] = (int32_t)i;
-  std::stable_sort(order, order + n, [&](int32_t a, int32_t b) {
-    const aff_result& x = res[a]; const aff_result& y = res[b];
-    if ((x.success != 0) != (y.success != 0)) return x.success != 0;
-    const double qx = x.jl_cost + x.coll_cost, qy = y.jl_cost + y.coll_cost;
-    if (qx != qy) return qx < qy;
-    return x.idx < y.idx;
-  });
 }
 
 double aff_measure_fp64_peak(int device, double seconds)

@@ -4,7 +4,7 @@
 #include <cstring>
 #include <sstream>
 
-namespace aff
+namespace affgpu
 {
 
 int TaskSpec::dim() const
@@ -187,4 +187,4 @@ TrajectoryPredictor::PredictionResult ActionBase::predict(aff_scene* scene, cons
   return TrajectoryPredictor::predictBatch(scene, graph, batch, dt)[0];
 }
 
-}   // namespace aff
+}   // namespace affgpu

@@ -20,7 +20,7 @@
 #include "TrajectoryPredictor.h"
 #include "affpredict.h"
 
-namespace aff
+namespace affgpu
 {
 
 class ActionException : public std::runtime_error
@@ -128,6 +128,6 @@ public:
   static std::unique_ptr<ActionBase> create(const ActionScene& domain, const Graph& graph, const std::string& text);
 };
 
-}   // namespace aff
+}   // namespace affgpu
 
 #endif

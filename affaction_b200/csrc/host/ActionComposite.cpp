@@ -6,7 +6,7 @@
 
 #include "ActionGet.h"
 
-namespace aff
+namespace affgpu
 {
 
 ActionComposite::ActionComposite(const ActionComposite& other) : ActionBase(other)
@@ -133,4 +133,4 @@ bool ActionDoubleGetPairs::initialize(const ActionScene& domain, const Graph& gr
   return actions[0]->initialize(domain, graph, pairs[solutionRank].first) && actions[1]->initialize(domain, graph, pairs[solutionRank].second);
 }
 
-}   // namespace aff
+}   // namespace affgpu

@@ -6,7 +6,7 @@
 
 #include "ActionBase.h"
 
-namespace aff
+namespace affgpu
 {
 
 class ActionComposite : public ActionBase
@@ -64,6 +64,6 @@ private:
   std::string explanation;
 };
 
-}   // namespace aff
+}   // namespace affgpu
 
 #endif

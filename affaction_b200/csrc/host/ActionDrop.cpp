@@ -2,7 +2,7 @@
 
 #include <cmath>
 
-namespace aff
+namespace affgpu
 {
 
 static const double kFingersOpen = 0.01;   // reference src/ActionDrop.cpp:44
@@ -95,4 +95,4 @@ ActivationSet ActionDrop::createTrajectory(double t_start, double t_end) const
   return a1;
 }
 
-}   // namespace aff
+}   // namespace affgpu

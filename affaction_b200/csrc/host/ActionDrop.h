@@ -8,7 +8,7 @@
 
 #include "ActionBase.h"
 
-namespace aff
+namespace affgpu
 {
 
 class ActionDrop : public ActionBase
@@ -34,6 +34,6 @@ private:
   std::string taskInclination, taskPosition, taskFingers, explanation;
 };
 
-}   // namespace aff
+}   // namespace affgpu
 
 #endif

@@ -3,7 +3,7 @@
 #include <cfloat>
 #include <cmath>
 
-namespace aff
+namespace affgpu
 {
 
 static const double kFingersClosed = 1.32;   // reference src/ActionFingerPush.cpp:48
@@ -122,4 +122,4 @@ ActivationSet ActionFingerPush::createTrajectory(double t_start, double t_end) c
   return a1;
 }
 
-}   // namespace aff
+}   // namespace affgpu

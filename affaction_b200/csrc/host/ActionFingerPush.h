@@ -7,7 +7,7 @@
 
 #include "ActionBase.h"
 
-namespace aff
+namespace affgpu
 {
 
 class ActionFingerPush : public ActionBase
@@ -30,6 +30,6 @@ private:
   std::string taskPushPos, taskPushOri, taskFingers, explanation;
 };
 
-}   // namespace aff
+}   // namespace affgpu
 
 #endif

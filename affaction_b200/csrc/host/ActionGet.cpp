@@ -3,7 +3,7 @@
 #include <algorithm>
 #include <cmath>
 
-namespace aff
+namespace affgpu
 {
 
 // reference src/ActionGet.cpp:54-60
@@ -330,4 +330,4 @@ ActivationSet ActionGet::trajectoryTopGrasp(double t_start, double t_grasp, doub
   return a1;
 }
 
-}   // namespace aff
+}   // namespace affgpu

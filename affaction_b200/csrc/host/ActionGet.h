@@ -6,7 +6,7 @@
 
 #include "ActionBase.h"
 
-namespace aff
+namespace affgpu
 {
 
 class ActionGet : public ActionBase
@@ -48,6 +48,6 @@ private:
   std::string taskObjHandPos, taskObjPosX, taskObjPosY, taskObjPosZ, taskObjOri, taskHandObjOri, taskFingers, taskHandOverHand;
 };
 
-}   // namespace aff
+}   // namespace affgpu
 
 #endif

@@ -1,6 +1,6 @@
 #include "ActionPose.h"
 
-namespace aff
+namespace affgpu
 {
 
 ActionPose::ActionPose(const ActionScene& domain, const Graph& graph, std::vector<std::string> params)
@@ -46,4 +46,4 @@ ActivationSet ActionPose::createTrajectory(double t_start, double t_end) const
   return a1;
 }
 
-}   // namespace aff
+}   // namespace affgpu

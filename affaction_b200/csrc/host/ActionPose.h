@@ -8,7 +8,7 @@
 
 #include "ActionBase.h"
 
-namespace aff
+namespace affgpu
 {
 
 class ActionPose : public ActionBase
@@ -29,6 +29,6 @@ private:
   std::string explanation;
 };
 
-}   // namespace aff
+}   // namespace affgpu
 
 #endif

@@ -3,7 +3,7 @@
 #include <algorithm>
 #include <cmath>
 
-namespace aff
+namespace affgpu
 {
 
 static std::vector<const Affordance*> affordancesOfType(const AffordanceEntity* e, Affordance::Type t)
@@ -186,4 +186,4 @@ ActivationSet ActionPour::createTrajectory(double t_start, double t_end) const
   return a1;
 }
 
-}   // namespace aff
+}   // namespace affgpu

@@ -6,7 +6,7 @@
 
 #include "ActionBase.h"
 
-namespace aff
+namespace affgpu
 {
 
 class ActionPour : public ActionBase
@@ -33,6 +33,6 @@ private:
   std::vector<std::string> usedManipulators, particlesToPour;
 };
 
-}   // namespace aff
+}   // namespace affgpu
 
 #endif

@@ -4,7 +4,7 @@
 #include <cfloat>
 #include <cmath>
 
-namespace aff
+namespace affgpu
 {
 
 static const double kFingersOpen = 0.01;      // reference src/ActionPut.cpp:50-ff (same values as ActionGet)
@@ -238,4 +238,4 @@ ActivationSet ActionPut::createTrajectory(double t_start, double t_release) cons
   return a1;
 }
 
-}   // namespace aff
+}   // namespace affgpu

@@ -7,7 +7,7 @@
 
 #include "ActionBase.h"
 
-namespace aff
+namespace affgpu
 {
 
 class ActionPut : public ActionBase
@@ -42,6 +42,6 @@ private:
       taskObjSurfacePolar, taskHandPolar, taskHandObjPolar, taskSurfaceOri, taskFingers;
 };
 
-}   // namespace aff
+}   // namespace affgpu
 
 #endif

@@ -6,7 +6,7 @@
 #include <sstream>
 #include <stdexcept>
 
-namespace aff
+namespace affgpu
 {
 
 static bool iequals(const std::string& a, const std::string& b)
@@ -265,4 +265,4 @@ void sort(const Graph& graph, std::vector<AffAffPair>& pairs, double wLin, doubl
   });
 }
 
-}   // namespace aff
+}   // namespace affgpu

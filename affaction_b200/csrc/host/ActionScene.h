@@ -12,7 +12,7 @@
 
 #include "Graph.h"
 
-namespace aff
+namespace affgpu
 {
 
 struct Affordance
@@ -108,6 +108,6 @@ std::vector<AffAffPair> match(Affordance::Type T1, Affordance::Type T2, const Af
 void sort(const Graph& graph, std::vector<AffCapPair>& pairs, double wLin, double wAng);
 void sort(const Graph& graph, std::vector<AffAffPair>& pairs, double wLin, double wAng);
 
-}   // namespace aff
+}   // namespace affgpu
 
 #endif

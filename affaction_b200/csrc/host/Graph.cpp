@@ -9,7 +9,7 @@
 #include <sstream>
 #include <stdexcept>
 
-namespace aff
+namespace affgpu
 {
 
 HTr HTr::identity()
@@ -434,4 +434,4 @@ const aff_scene_desc* Graph::toDesc()
   return &desc_;
 }
 
-}   // namespace aff
+}   // namespace affgpu

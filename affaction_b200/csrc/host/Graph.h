@@ -15,7 +15,7 @@
 
 #include "affpredict.h"
 
-namespace aff
+namespace affgpu
 {
 
 struct HTr
@@ -120,6 +120,6 @@ private:
   std::vector<double> d_abp_, d_ajp_, d_qinit_, d_q0_, d_qmin_, d_qmax_, d_speed_, d_acc_, d_wjl_, d_wm_, d_acb_, d_ext_;
 };
 
-}   // namespace aff
+}   // namespace affgpu
 
 #endif

@@ -1,8 +1,9 @@
+#include "gpu_api.h"
 #include "TrajectoryComponent.h"
 
 #include <stdexcept>
 
-namespace aff
+namespace affgpu
 {
 
 TrajectoryComponent::TrajectoryComponent(aff_scene* scene_, const Graph& graph_, double dt_)
@@ -37,21 +38,21 @@ TrajectoryComponent::CheckOutcome TrajectoryComponent::checkerThread(const Candi
   opts.dt = dt;
   opts.log_q = 1;
   aff_batch* b = nullptr;
-  if (aff_batch_create(scene, batch.tasks.data(), batch.tasks.size(), batch.constraints.data(), batch.constraints.size(),
+  if (gpu().batch_create(scene, batch.tasks.data(), batch.tasks.size(), batch.constraints.data(), batch.constraints.size(),
                        batch.candidates.data(), 1, &opts, &b) != AFF_OK)
-    throw std::runtime_error(std::string("TrajectoryComponent: ") + aff_last_error());
+    throw std::runtime_error(std::string("TrajectoryComponent: ") + gpu().last_error());
   aff_result raw;
-  int rc = aff_batch_launch(b, nullptr);
-  if (rc == AFF_OK) rc = aff_batch_results(b, nullptr, &raw, 1);
+  int rc = gpu().batch_launch(b, nullptr);
+  if (rc == AFF_OK) rc = gpu().batch_results(b, nullptr, &raw, 1);
   if (rc == AFF_OK) {
-    const int rows = aff_batch_num_steps(b, 0) + 1, cols = aff_scene_num_ik_joints(scene);
+    const int rows = gpu().batch_num_steps(b, 0) + 1, cols = gpu().scene_num_ik_joints(scene);
     std::vector<double> newPredictions((size_t)rows * cols);
-    const int got = aff_batch_fetch_q(b, 0, newPredictions.data(), (size_t)rows);
+    const int got = gpu().batch_fetch_q(b, 0, newPredictions.data(), (size_t)rows);
     if (got < 0) rc = got;
     else { newPredictions.resize((size_t)got * cols); tPred.swap(newPredictions); tPredRows = got; tPredCols = cols; }
   }
-  aff_batch_destroy(b);
-  if (rc != AFF_OK) throw std::runtime_error(std::string("TrajectoryComponent: ") + aff_last_error());
+  gpu().batch_destroy(b);
+  if (rc != AFF_OK) throw std::runtime_error(std::string("TrajectoryComponent: ") + gpu().last_error());
 
   out.checked = true;
   out.result = TrajectoryPredictor::convert(raw, graph, batch.taskNames[0], dt);
@@ -72,4 +73,4 @@ TrajectoryComponent::CheckOutcome TrajectoryComponent::checkerThread(const Candi
   return out;
 }
 
-}   // namespace aff
+}   // namespace affgpu

@@ -12,7 +12,7 @@
 
 #include "ActionBase.h"
 
-namespace aff
+namespace affgpu
 {
 
 class TrajectoryComponent
@@ -62,6 +62,6 @@ private:
   int tPredRows, tPredCols;
 };
 
-}   // namespace aff
+}   // namespace affgpu
 
 #endif

@@ -1,3 +1,4 @@
+#include "gpu_api.h"
 #include "TrajectoryPredictor.h"
 
 #include <algorithm>
@@ -5,7 +6,7 @@
 
 #include "ActionBase.h"
 
-namespace aff
+namespace affgpu
 {
 
 static std::string bodyName(const Graph& g, int id)
@@ -96,9 +97,9 @@ std::vector<TrajectoryPredictor::PredictionResult> TrajectoryPredictor::predictB
   aff_default_opts(&opts);
   opts.dt = dt;
   std::vector<aff_result> raw(batch.candidates.size());
-  const int rc = aff_predict_batch(scene, batch.tasks.data(), batch.tasks.size(), batch.constraints.data(),
+  const int rc = gpu().predict_batch(scene, batch.tasks.data(), batch.tasks.size(), batch.constraints.data(),
                                    batch.constraints.size(), batch.candidates.data(), batch.candidates.size(), &opts, raw.data());
-  if (rc != AFF_OK) throw std::runtime_error(std::string("aff_predict_batch failed: ") + aff_last_error());
+  if (rc != AFF_OK) throw std::runtime_error(std::string("aff_predict_batch failed: ") + gpu().last_error());
   std::vector<PredictionResult> res;
   res.reserve(raw.size());
   for (size_t i = 0; i < raw.size(); ++i) res.push_back(convert(raw[i], graph, batch.taskNames[i], dt));
@@ -106,4 +107,4 @@ std::vector<TrajectoryPredictor::PredictionResult> TrajectoryPredictor::predictB
   return res;
 }
 
-}   // namespace aff
+}   // namespace affgpu

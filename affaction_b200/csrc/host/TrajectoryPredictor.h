@@ -12,7 +12,7 @@
 #include "Graph.h"
 #include "affpredict.h"
 
-namespace aff
+namespace affgpu
 {
 
 struct CandidateBatch;
@@ -58,6 +58,6 @@ public:
                                   const double* qFail = nullptr);
 };
 
-}   // namespace aff
+}   // namespace affgpu
 
 #endif

@@ -2,6 +2,7 @@
 // from text commands, batch prediction with message strings.  This is what a
 // non-C++ front end (the ctypes binding in affaction_b200/__init__.py, the
 // pybind module of the reference's python/module.cpp) binds.
+#include "gpu_api.h"
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -20,7 +21,7 @@
 #include "TrajectoryPredictor.h"
 #include "affpredict_host.h"
 
-using namespace aff;
+using namespace affgpu;
 
 struct aff_host_scene
 {
@@ -59,7 +60,7 @@ aff_host_scene* aff_host_scene_load(const char* path)
 void aff_host_scene_destroy(aff_host_scene* s)
 {
   if (!s) return;
-  if (s->device) aff_scene_destroy(s->device);
+  if (s->device) gpu().scene_destroy(s->device);
   delete s;
 }
 
@@ -85,7 +86,7 @@ int aff_host_scene_connect(aff_host_scene* s, const char* child, const char* par
     s->graph.connectBody(c, p);
     if (s->graph.restoreParentFirstOrder()) s->graph.computeForwardKinematics();
     s->graph.toDesc();
-    if (s->device) { aff_scene_destroy(s->device); s->device = nullptr; }
+    if (s->device) { gpu().scene_destroy(s->device); s->device = nullptr; }
     return AFF_OK;
   } catch (const std::exception& e) { g_hostError = e.what(); return AFF_ERR_INVALID; }
 }
@@ -98,7 +99,7 @@ int aff_host_scene_set_ik_state(aff_host_scene* s, const double* q, int n)
   for (Joint& j : s->graph.joints) if (j.jacobiIndex >= 0) j.q_init = q[j.jacobiIndex];
   s->graph.computeForwardKinematics();
   s->graph.toDesc();
-  if (s->device) { aff_scene_destroy(s->device); s->device = nullptr; }
+  if (s->device) { gpu().scene_destroy(s->device); s->device = nullptr; }
   return AFF_OK;
 }
 
@@ -109,7 +110,7 @@ int aff_host_scene_apply_rollout(aff_host_scene* s, const aff_host_batch* b, siz
     const aff_candidate& c = b->batch.candidates[cand];
     s->graph.applyRollout(b->batch.constraints.data() + c.first_constraint, c.n_constraints, qlog, rows, dt);
     s->graph.toDesc();
-    if (s->device) { aff_scene_destroy(s->device); s->device = nullptr; }
+    if (s->device) { gpu().scene_destroy(s->device); s->device = nullptr; }
     return AFF_OK;
   } catch (const std::exception& e) { g_hostError = e.what(); return AFF_ERR_INVALID; }
 }
@@ -127,7 +128,7 @@ int aff_host_rollout_transforms(aff_host_scene* s, const aff_host_batch* b, size
 aff_scene* aff_host_scene_device(aff_host_scene* s, int device)
 {
   if (!s->device) {
-    if (aff_scene_create(s->graph.toDesc(), device, &s->device) != AFF_OK) { g_hostError = aff_last_error(); return nullptr; }
+    if (gpu().scene_create(s->graph.toDesc(), device, &s->device) != AFF_OK) { g_hostError = gpu().last_error(); return nullptr; }
   }
   return s->device;
 }
@@ -305,24 +306,24 @@ int aff_host_predict_sequence(aff_host_scene* s, const char* text, double dt, in
       opts.dt = dt;
       opts.log_q = 1;                 // the winner's joint trajectory is the next action's start
       aff_batch* db = nullptr;
-      if (aff_batch_create(dev, batch.tasks.data(), batch.tasks.size(), batch.constraints.data(), batch.constraints.size(),
-                           batch.candidates.data(), batch.candidates.size(), &opts, &db) != AFF_OK) { g_hostError = aff_last_error(); return AFF_ERR_CUDA; }
+      if (gpu().batch_create(dev, batch.tasks.data(), batch.tasks.size(), batch.constraints.data(), batch.constraints.size(),
+                           batch.candidates.data(), batch.candidates.size(), &opts, &db) != AFF_OK) { g_hostError = gpu().last_error(); return AFF_ERR_CUDA; }
       std::vector<aff_result> raw(batch.candidates.size());
-      int rc = aff_batch_launch(db, nullptr);
-      if (rc == AFF_OK) rc = aff_batch_results(db, nullptr, raw.data(), raw.size());
+      int rc = gpu().batch_launch(db, nullptr);
+      if (rc == AFF_OK) rc = gpu().batch_results(db, nullptr, raw.data(), raw.size());
       std::vector<int32_t> order(raw.size());
       aff_rank_results(raw.data(), raw.size(), order.data());
       const aff_result best = raw[order[0]];
       std::vector<double> q;
       int rows = 0;
       if (rc == AFF_OK && best.success) {
-        rows = aff_batch_num_steps(db, (size_t)best.idx) + 1;
+        rows = gpu().batch_num_steps(db, (size_t)best.idx) + 1;
         q.resize((size_t)rows * s->graph.nJ);
-        rows = aff_batch_fetch_q(db, (size_t)best.idx, q.data(), (size_t)rows);
+        rows = gpu().batch_fetch_q(db, (size_t)best.idx, q.data(), (size_t)rows);
         if (rows < 0) rc = rows;
       }
-      aff_batch_destroy(db);
-      if (rc != AFF_OK) { g_hostError = aff_last_error(); return AFF_ERR_CUDA; }
+      gpu().batch_destroy(db);
+      if (rc != AFF_OK) { g_hostError = gpu().last_error(); return AFF_ERR_CUDA; }
       if (winners) winners[done] = best;
       if (nCandidates) nCandidates[done] = (int)raw.size();
       if (messages && msgStride > 0) {
@@ -335,7 +336,7 @@ int aff_host_predict_sequence(aff_host_scene* s, const char* text, double dt, in
       const aff_candidate& c = batch.candidates[best.idx];
       s->graph.applyRollout(batch.constraints.data() + c.first_constraint, c.n_constraints, q.data(), rows, dt);
       s->graph.toDesc();
-      if (s->device) { aff_scene_destroy(s->device); s->device = nullptr; }
+      if (s->device) { gpu().scene_destroy(s->device); s->device = nullptr; }
     }
     return done;
   } catch (const std::exception& e) {
@@ -385,7 +386,7 @@ int aff_host_check_trajectory(aff_host_scene* s, aff_host_batch* b, size_t cand,
 
 }   // extern "C"
 
-namespace aff
+namespace affgpu
 {
 
 std::unique_ptr<ActionBase> ActionFactory::create(const ActionScene& domain, const Graph& graph, const std::string& text)
@@ -413,4 +414,4 @@ std::unique_ptr<ActionBase> ActionFactory::create(const ActionScene& domain, con
   return a;
 }
 
-}   // namespace aff
+}   // namespace affgpu

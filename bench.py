@@ -151,6 +151,8 @@ def run_reference(args, rank, world):
                          "sample": "%d rollouts per step x %d steps" % (sample, args.steps)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # candidates come from the pure C++ host shim (libaffhost.so); the CUDA library is never mapped by this arm
+        "cuda_library_loaded": ab.gpu_library_loaded(),
     }
     print(json.dumps(line))
 
@@ -350,7 +352,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     import __graft_entry__ as ge
     if rank == 0 or not os.path.isfile(os.path.join(ROOT, "affaction_b200", "libaffpredict.so")):
-        ge.build()
+        ge.build(check_gpu_library=args.impl != "reference")
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -59,3 +59,23 @@ def test_product_does_not_reference_oracle():
                     if re.search(r'#include\s+"[^"]*oracle|import\s+oracle|liboracle|libaffemu', txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def _build_c_client():
+    import subprocess
+    libdir = os.path.join(ab.REPO_ROOT, "affaction_b200")
+    exe = os.path.join(ab.REPO_ROOT, "tests", "c_client", "abi_client")
+    src = exe + ".c"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I" + os.path.join(ab.REPO_ROOT, "include"), src, "-o", exe,
+                    "-L" + libdir, "-laffhost", "-laffpredict", "-Wl,-rpath," + libdir], check=True)
+    return exe
+
+
+def test_compiled_c_client(built):
+    """include/*.h compile as C11 and link against the two libraries; a C program loads the scene, builds the
+    candidates of a text command and reaches the device boundary (which fails loudly without a GPU)."""
+    import subprocess
+    exe = _build_c_client()
+    out = subprocess.run([exe, ab.PIZZA_SCENE, "get fresh_tomatoes"], check=True, capture_output=True, text=True).stdout
+    assert "bodies 455 ik_joints 23 candidates 2" in out
+    assert "device present" in out or "no device: status %d" % -2 in out

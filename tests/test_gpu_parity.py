@@ -523,3 +523,21 @@ def test_put_120_candidates_match_oracle(built):
     assert [r.as_tuple() for r in gpu] == [r.as_tuple() for r in ref]
     assert ab.rank(gpu) == ab.rank(ref)
     assert len(set(r.first_code for r in ref)) >= 2
+
+
+def test_compiled_c_client_predicts(scene):
+    """The plain C client of tests/c_client (gcc, no Python in the call path) through aff_host_predict."""
+    import subprocess
+    from test_abi import _build_c_client
+    exe = _build_c_client()
+    out = subprocess.run([exe, ab.PIZZA_SCENE, "get fresh_tomatoes", "--predict"], check=True, capture_output=True, text=True).stdout
+    rows = [l for l in out.splitlines()[1:] if "|" in l]
+    batch = ab.HostBatch(scene)
+    batch.add_action("get fresh_tomatoes")
+    ref = ob.predict_batch(scene, batch, ab.default_opts(), n_threads=2)
+    ranked = [ref[i] for i in ab.rank(ref)]
+    assert len(rows) == 2
+    for line, r in zip(rows, ranked):
+        f = line.split("|")[0].split()
+        assert (int(f[0]), int(f[1]), int(f[2]), int(f[3])) == (r.idx, r.success, r.code, r.first_fail_step)
+        assert float(f[4]) == r.jl_cost + r.coll_cost
