@@ -28,6 +28,7 @@ struct aff_host_scene
   Graph graph;
   ActionScene domain;
   aff_scene* device = nullptr;
+  int deviceIndex = -1;          // the CUDA device `device` was created on
 };
 
 struct aff_host_batch
@@ -127,9 +128,14 @@ int aff_host_rollout_transforms(aff_host_scene* s, const aff_host_batch* b, size
 
 aff_scene* aff_host_scene_device(aff_host_scene* s, int device)
 {
-  if (!s->device) {
-    if (gpu().scene_create(s->graph.toDesc(), device, &s->device) != AFF_OK) { g_hostError = gpu().last_error(); return nullptr; }
-  }
+  // one cached device scene per host scene; asking for another device replaces it
+  try {
+    if (s->device && s->deviceIndex != device) { gpu().scene_destroy(s->device); s->device = nullptr; }
+    if (!s->device) {
+      if (gpu().scene_create(s->graph.toDesc(), device, &s->device) != AFF_OK) { g_hostError = gpu().last_error(); return nullptr; }
+      s->deviceIndex = device;
+    }
+  } catch (const std::exception& e) { g_hostError = e.what(); return nullptr; }    // the CUDA library is missing
   return s->device;
 }
 
