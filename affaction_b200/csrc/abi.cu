@@ -300,6 +300,13 @@ int aff_batch_create(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, c
       b->useSweep = true;
     }
     b->sweepGrid = (int)std::min(blocksNeededS, (size_t)s->smCount * (size_t)(1024 / b->sweepThreads));
+    if (b->useSweep) {
+      // the kernel uses no shared memory to speak of: give the whole unified array to L1 (the per-thread state lives in local memory)
+      const char* co = getenv("AFF_TUNE_SWEEP_CARVEOUT");
+      const int carve = co ? atoi(co) : 0;
+      const void* kf = b->sweepThreads == 512 ? (const void*)aff_sweep_kernel<512> : (b->sweepThreads == 256 ? (const void*)aff_sweep_kernel<256> : (const void*)aff_sweep_kernel<128>);
+      CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    }
   }
   // launch geometry: persistent blocks, as many as fit per SM
   b->smemBytes = b->host.smemBytesPerWarp * AFF_WARPS_PER_BLOCK;
@@ -577,6 +584,16 @@ int aff_predict_batch_multi(const aff_scene_desc* desc, const int* devices, int 
   for (int r = 0; r < G; ++r) if (rcs[(size_t)r] != AFF_OK) return fail(rcs[(size_t)r], "aff_predict_batch_multi: device " + std::to_string(devices[r]) + ": " + errs[(size_t)r]);
   return AFF_OK;
 }
+
+#ifdef AFFT_PROFILE
+// tuning builds only: cycles thread 0 of block 0 spent in phases A..F (+ loop head) of the sweep kernel
+int aff_debug_phase_clocks(unsigned long long out[8], int reset)
+{
+  if (cudaMemcpyFromSymbol(out, kgeneric::g_phaseClocks, sizeof(unsigned long long) * 8) != cudaSuccess) return AFF_ERR_CUDA;
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(kgeneric::g_phaseClocks, z, sizeof(z)); }
+  return AFF_OK;
+}
+#endif
 
 double aff_measure_fp64_peak(int device, double seconds)
 {

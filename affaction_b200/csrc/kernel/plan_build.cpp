@@ -415,7 +415,7 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     std::stable_sort(H.pairsSS.begin(), H.pairsSS.end(), [&](const KPair& x, const KPair& y) { return kindOf(x) != kindOf(y) ? kindOf(x) < kindOf(y) : x.a < y.a; });
     // segment-box before segment-cylinder (the cylinder distance is an iteration: keep it out of box rounds)
     auto kindSB = [&](const KPair& p) { const int t = (p.b >= 0) ? H.dshape[p.b].type : H.sshape[-1 - p.b].type; return kindOf(p) | (t == AFF_SHAPE_CYLINDER ? 8 : 0); };
-    std::stable_sort(H.pairsSB.begin(), H.pairsSB.end(), [&](const KPair& x, const KPair& y) { return kindSB(x) < kindSB(y); });
+    std::stable_sort(H.pairsSB.begin(), H.pairsSB.end(), [&](const KPair& x, const KPair& y) { return kindSB(x) != kindSB(y) ? kindSB(x) < kindSB(y) : x.a < y.a; });
     if (H.dbody.size() > 31) { err = "too many dynamic shape bodies"; return AFF_ERR_CAPACITY; }
   }
 

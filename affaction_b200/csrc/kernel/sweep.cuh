@@ -51,6 +51,16 @@ AFF_DEV int t_block_max(int v)
 #endif
 #endif
 
+// -DAFFT_PROFILE (tuning builds only): thread 0 of block 0 adds the clock cycles between the phase barriers
+#if defined(AFFT_PROFILE) && !defined(AFF_EMULATE)
+__device__ unsigned long long g_phaseClocks[8];
+#define T_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now_ = clock64(); g_phaseClocks[i] += (unsigned long long)(now_ - tmark_); tmark_ = now_; } } while (0)
+#define T_MARK_INIT long long tmark_ = clock64()
+#else
+#define T_MARK(i) do { } while (0)
+#define T_MARK_INIT do { } while (0)
+#endif
+
 #ifndef AFFT_PHASE
 #ifdef AFFT_PHASE_NOINLINE
 #define AFFT_PHASE AFF_NOINLINE
@@ -269,10 +279,30 @@ AFFT_PHASE void t_collision(TCtx& c, double need, KCollResult* out)
     if ((d) < best || ((d) == best && (key) < bestKey)) { best = (d); bestKey = (key); }                  \
     if (thr > 0.0 && (d) < thr) { if (nCostly < AFFT_MAX_COSTLY) { S.ckey[nCostly] = (key); S.cdist[nCostly] = (d); } ++nCostly; } \
   } while (0)
+  // Tree-level pre-filter: two broad-phase trees whose boxes are at least cullNeed apart cannot hold a pair
+  // that becomes the minimum or carries a cost (a tree's box contains every active shape of its bodies), so
+  // their pairs are skipped before any shape record is read - in a `get`, all of arm x arm.  A pure filter:
+  // pairs it drops would have been dropped by the bounding-sphere test or lost against `need` anyway.
+  unsigned long long treeFar = 0ull;
+  {
+    const double lim = cullNeed + cullMargin;
+    for (int ta = 0; ta < P.nTrees; ++ta)
+      for (int tb = ta + 1; tb < P.nTrees; ++tb) {
+        double g2 = 0.0;
+        for (int k = 0; k < 3; ++k) {
+          const double g1 = taabb[6 * ta + k] - taabb[6 * tb + 3 + k], g2k = taabb[6 * tb + k] - taabb[6 * ta + 3 + k];
+          const double g = g1 > g2k ? g1 : g2k;
+          if (g > 0.0) g2 += g * g;
+        }
+        if (g2 >= lim * lim) treeFar |= (1ull << (ta * 8 + tb)) | (1ull << (tb * 8 + ta));
+      }
+  }
+#define T_TREES_FAR(meta) (!KP_RULE(meta) && KP_TREE_A(meta) >= 0 && KP_TREE_B(meta) >= 0 && ((treeFar >> (KP_TREE_A(meta) * 8 + KP_TREE_B(meta))) & 1ull))
   int lastA = -1;
   double A[8];
   for (int i = 0; i < P.nSS; ++i) {
     const KPair pr = ldg_pair(&P.pairsSS[i]);
+    if (T_TREES_FAR(pr.meta)) continue;
     if (!k_pair_live(c, pr.meta, baabb, thr)) continue;
     if (pr.a != lastA) { const double* Ap = shp + 12 * pr.a; for (int k = 0; k < 8; ++k) A[k] = Ap[k]; lastA = pr.a; }
     const double rA = A[6];
@@ -288,10 +318,15 @@ AFFT_PHASE void t_collision(TCtx& c, double need, KCollResult* out)
   }
   for (int i = 0; i < P.nSB; ++i) {
     const KPair pr = ldg_pair(&P.pairsSB[i]);
+    if (T_TREES_FAR(pr.meta)) continue;
     if (!k_pair_live(c, pr.meta, baabb, thr)) continue;
     double pS[3], dS[3], rS, bS, cB[3], bB;
-    if (pr.a >= 0) { const double* A = shp + 12 * pr.a; for (int k = 0; k < 3; ++k) { pS[k] = A[k]; dS[k] = A[3 + k]; } rS = A[6]; bS = A[7]; }
-    else { const double* A = P.sseg + 8 * (-1 - pr.a); for (int k = 0; k < 3; ++k) { pS[k] = ldg(&A[k]); dS[k] = ldg(&A[3 + k]); } rS = ldg(&A[6]); bS = ldg(&A[7]); }
+    if (pr.a >= 0) {
+      if (pr.a != lastA) { const double* Ap = shp + 12 * pr.a; for (int k = 0; k < 8; ++k) A[k] = Ap[k]; lastA = pr.a; }
+      for (int k = 0; k < 3; ++k) { pS[k] = A[k]; dS[k] = A[3 + k]; }
+      rS = A[6]; bS = A[7];
+    }
+    else { const double* As = P.sseg + 8 * (-1 - pr.a); for (int k = 0; k < 3; ++k) { pS[k] = ldg(&As[k]); dS[k] = ldg(&As[3 + k]); } rS = ldg(&As[6]); bS = ldg(&As[7]); }
     if (pr.b >= 0) { const double* B = shp + 12 * pr.b; for (int k = 0; k < 3; ++k) cB[k] = B[k]; bB = ldg(&P.dshape[pr.b].bound); }
     else { const double* B = P.sseg + 8 * (-1 - pr.b); for (int k = 0; k < 3; ++k) cB[k] = ldg(&B[k]); bB = ldg(&B[7]); }
     double cd2 = 0.0;
@@ -328,6 +363,7 @@ AFFT_PHASE void t_collision(TCtx& c, double need, KCollResult* out)
     T_ACCOUNT(d, key);
   }
 #undef T_ACCOUNT
+#undef T_TREES_FAR
   KCollResult res;
   if (best < need) {
     res.minDist = best;
@@ -468,12 +504,14 @@ AFF_DEV void t_rollout(const KPlan& P, int cand, TState& S, bool alive)
   const int loopSteps = T_BLOCK_MAX(alive ? nSteps : 0);
   double blending = 1.0, phaseScale = 0.0, alphaEff = 0.0;
   int m = 0, singular = 0, ikRes = 0, id0 = -1, id1 = -1, fast = 0;
+  T_MARK_INIT;
   bool running = alive;      // early exit (opt-in) stops a failed rollout; its thread keeps meeting the block's barriers
   for (int iter = 0; iter < loopSteps; ++iter) {
     if (P.opts.early_exit && !T_BLOCK_ANY(running && iter < nSteps)) break;
     const bool act = running && iter < nSteps;
     const int successPrev = success;
     T_SYNC();
+    T_MARK(6);
     if (act) {   // ======== phase A: trajectories, constraints, activations, task errors
     // ---- task switch / qFilt (:166-180)
     if (prevMask != activeMask) qFilt = 1.0;
@@ -579,6 +617,7 @@ AFF_DEV void t_rollout(const KPlan& P, int cand, TState& S, bool alive)
       if ((activeMask >> t) & 1u) t_task_dx(c, t, tasks, dxv + S.rowOf[t]);
     }
     T_SYNC();
+    T_MARK(0);
     if (act) {   // ======== phase B: Jacobian columns, null-space gradient
     // Elbow / wrist terms (:448-570): the factors do not depend on the joint, only the Jacobian entries do
     // (the warp-per-candidate kernel recomputes them on every lane; same operations, same values).
@@ -638,12 +677,15 @@ AFF_DEV void t_rollout(const KPlan& P, int cand, TState& S, bool alive)
     }
     // per joint: J column, dH (joint-limit gradient + elbow / wrist terms)
     unsigned aMask = 0u;
+    unsigned anyChain = nsChain;
+    for (int t = 0; t < nTasks; ++t) anyChain |= taskChain[t];
     for (int r = 0; r < m; ++r) S.rmask[r] = 0u;
     for (int j = 0; j < nJ; ++j) {
       KJointFrame jf;
       const int jtype = ldg(&P.j_type[j]);
       jf.valid = 1; jf.type = jtype;
-      {
+      for (int k = 0; k < 3; ++k) { jf.ax[k] = 0.0; jf.org[k] = 0.0; }
+      if ((anyChain >> j) & 1u) {       // the frame of a joint outside every chain is never used
         const double* A = k_slot(c, ldg(&P.j_node[j]));
         const int ar = (jtype < AFF_JNT_ROT_X) ? jtype : jtype - AFF_JNT_ROT_X;
         for (int k = 0; k < 3; ++k) { jf.ax[k] = A[3 + 3 * ar + k]; jf.org[k] = A[k]; }
@@ -703,6 +745,7 @@ AFF_DEV void t_rollout(const KPlan& P, int cand, TState& S, bool alive)
     jmaskBits |= aMask;
     }
     T_SYNC();
+    T_MARK(1);
     if (act) {   // ======== phase C: right inverse, limits, integration
     // ---- solveRightInverse
     for (int i = 0; i < m; ++i) {
@@ -783,11 +826,14 @@ AFF_DEV void t_rollout(const KPlan& P, int cand, TState& S, bool alive)
     }
     }
     T_SYNC();
+    T_MARK(2);
     // integration, FK, collision model, checkState (:730-752)
     if (act && !singular) t_fk(c, false);                                                       // ======== phase D
     T_SYNC();
+    T_MARK(3);
     if (act && !singular) t_collision(c, r_minDist > 0.001 ? r_minDist : 0.001, &cm);           // ======== phase E
     T_SYNC();
+    T_MARK(4);
     if (act) {   // ======== phase F: checkState, costs, tracking error
     if (!singular) {
       int viol = 0;
@@ -845,6 +891,7 @@ AFF_DEV void t_rollout(const KPlan& P, int cand, TState& S, bool alive)
     rows++;
     if (P.opts.early_exit && !success && successPrev) running = false;     // the reference's commented-out break (:368-373)
     }
+    T_MARK(5);
   }
   if (!alive) return;
   aff_result res;

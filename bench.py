@@ -13,8 +13,8 @@ one batch of ROLLOUTS_PER_GPU candidates per GPU.
 
   value : rollouts/s with the candidate tables already resident in HBM
           (kernel launches + NCCL verdict gather only), CUDA events, max over ranks.
-          The three variant batches are launched on three streams and share the GPU
-          (one resident wave of the thread-per-candidate kernel = 148 SMs x 1024 rollouts).
+          One launch per variant, each one resident wave of the thread-per-candidate kernel
+          (148 SMs x 1024 rollouts), back to back on one stream.
   e2e   : the same metric through aff_predict_batch with HOST buffers in and out
           (plan compile, H2D of the tables, kernels, D2H of the verdicts), one host
           thread per variant, timed over all --steps iterations
@@ -40,7 +40,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 VARIANTS = ["get tomato_sauce_bottle", "get fresh_tomatoes", "get italian_seasoning_bowl"]
-PER_VARIANT = 50176                      # 98 blocks x 512 rollouts: three variants = 294 of the 296 resident blocks of a B200
+PER_VARIANT = 151552                     # one resident wave of the thread-per-candidate kernel: 148 SMs x 2 blocks x 512 rollouts
 ROLLOUTS_PER_GPU = PER_VARIANT * len(VARIANTS)
 STEPS_PER_ROLLOUT = 1555
 METRIC = "candidate IK rollouts/sec"
@@ -172,8 +172,7 @@ def run_cuda(args, rank, local_rank, world):
     n_local = per_variant * len(VARIANTS)
     host_batches = make_batches(ab, scene, rank, per_variant, world)
     opts = ab.default_opts()
-    main_stream = torch.cuda.current_stream()
-    streams = [torch.cuda.Stream() for _ in VARIANTS]
+    stream = torch.cuda.current_stream().cuda_stream
     rec = C.sizeof(ab.Result)
 
     # ---- resident arm: candidate tables uploaded once, verdicts written into a torch buffer
@@ -186,13 +185,10 @@ def run_cuda(args, rank, local_rank, world):
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
 
     def launch_all():
-        """the three variant batches side by side on the GPU: one stream each, joined on the main stream"""
+        """one full-wave launch per variant, back to back"""
         n_launch = 0
-        for st, db in zip(streams, dev_batches):
-            st.wait_stream(main_stream)
-            n_launch += db.launch(st.cuda_stream)
-        for st in streams:
-            main_stream.wait_stream(st)
+        for db in dev_batches:
+            n_launch += db.launch(stream)
         return n_launch
 
     def barrier():
