@@ -147,7 +147,7 @@ struct aff_batch
   KPlan plan{};
   DevBuf<double> jq_init, jq0, jq_min, jq_max, jspeed, jacc, jwjl, jwmetric, obj_q6, statA, statSC, dynSC, sshapeA, sbodyAABB, qlog;
   DevBuf<KFkEntry> fktab;
-  DevBuf<int32_t> j_node, j_type, statpar_ref, obj_parent_slot, obj_parent_tree, dyn_under, obj_node, obj_body, dyn_pslot, sweep_order;
+  DevBuf<int32_t> j_node, j_type, statpar_ref, obj_parent_slot, obj_parent_tree, dyn_under, obj_node, obj_body, dyn_pslot, sweep_order, node_shape_off, node_shape_idx, dyn_store;
   DevBuf<uint32_t> dyn_chain;
   DevBuf<double> dynT, dynQ;
   DevBuf<KPair> pairsSS, pairsSB;
@@ -167,7 +167,7 @@ struct aff_batch
     jq_init.release(); jq0.release(); jq_min.release(); jq_max.release(); jspeed.release(); jacc.release(); jwjl.release();
     jwmetric.release(); obj_q6.release(); statA.release(); statSC.release(); dynSC.release(); sshapeA.release();
     sbodyAABB.release(); qlog.release(); j_node.release(); j_type.release(); fktab.release(); statpar_ref.release(); obj_parent_slot.release(); obj_parent_tree.release(); dyn_under.release(); dyn_chain.release(); dynT.release(); dynQ.release(); pairsSS.release(); pairsSB.release(); sseg.release();
-    obj_node.release(); obj_body.release(); dyn_pslot.release(); sweep_order.release(); dyn.release(); stat.release(); dshape.release(); sshape.release();
+    obj_node.release(); obj_body.release(); dyn_pslot.release(); sweep_order.release(); node_shape_off.release(); node_shape_idx.release(); dyn_store.release(); dyn.release(); stat.release(); dshape.release(); sshape.release();
     dbody.release(); sbody.release(); tasks.release(); vias.release(); acts.release(); gcons.release(); cands.release();
     results.release();
   }
@@ -219,7 +219,7 @@ static int uploadBatch(aff_batch* b, cudaStream_t st)
   P = H.plan;
 #define UP(name) do { CUDA_TRY(b->name.upload(H.name, st)); b->h2dBytes += H.name.size() * sizeof(H.name[0]); } while (0)
   UP(jq_init); UP(jq0); UP(jq_min); UP(jq_max); UP(jspeed); UP(jacc); UP(jwjl); UP(jwmetric); UP(obj_q6);
-  UP(j_node); UP(j_type); UP(fktab); UP(statpar_ref); UP(obj_parent_slot); UP(obj_parent_tree); UP(dyn_under); UP(dyn_chain); UP(dynT); UP(dynQ); UP(pairsSS); UP(pairsSB); UP(obj_node); UP(obj_body); UP(dyn_pslot); UP(sweep_order);
+  UP(j_node); UP(j_type); UP(fktab); UP(statpar_ref); UP(obj_parent_slot); UP(obj_parent_tree); UP(dyn_under); UP(dyn_chain); UP(dynT); UP(dynQ); UP(pairsSS); UP(pairsSB); UP(obj_node); UP(obj_body); UP(dyn_pslot); UP(sweep_order); UP(node_shape_off); UP(node_shape_idx); UP(dyn_store);
   UP(dyn); UP(stat); UP(dshape); UP(sshape); UP(dbody); UP(sbody);
   UP(tasks); UP(vias); UP(acts); UP(gcons); UP(cands);
 #undef UP
@@ -242,7 +242,7 @@ static int uploadBatch(aff_batch* b, cudaStream_t st)
   P.jacc = b->jacc.p; P.jwjl = b->jwjl.p; P.jwmetric = b->jwmetric.p; P.j_node = b->j_node.p; P.j_type = b->j_type.p;
   P.dyn = b->dyn.p; P.stat = b->stat.p; P.statA = b->statA.p; P.statSC = b->statSC.p; P.dynSC = b->dynSC.p; P.fktab = b->fktab.p; P.statpar_ref = b->statpar_ref.p; P.obj_parent_slot = b->obj_parent_slot.p; P.obj_parent_tree = b->obj_parent_tree.p; P.dyn_under = b->dyn_under.p; P.dyn_chain = b->dyn_chain.p; P.dynT = b->dynT.p; P.dynQ = b->dynQ.p;
   P.dshape = b->dshape.p; P.dbody = b->dbody.p; P.sshape = b->sshape.p; P.sbody = b->sbody.p; P.sshapeA = b->sshapeA.p;
-  P.sbodyAABB = b->sbodyAABB.p; P.pairsSS = b->pairsSS.p; P.pairsSB = b->pairsSB.p; P.sseg = b->sseg.p; P.obj_node = b->obj_node.p; P.obj_body = b->obj_body.p; P.obj_q6 = b->obj_q6.p; P.dyn_pslot = b->dyn_pslot.p; P.sweep_order = b->sweep_order.p;
+  P.sbodyAABB = b->sbodyAABB.p; P.pairsSS = b->pairsSS.p; P.pairsSB = b->pairsSB.p; P.sseg = b->sseg.p; P.obj_node = b->obj_node.p; P.obj_body = b->obj_body.p; P.obj_q6 = b->obj_q6.p; P.dyn_pslot = b->dyn_pslot.p; P.sweep_order = b->sweep_order.p; P.node_shape_off = b->node_shape_off.p; P.node_shape_idx = b->node_shape_idx.p; P.dyn_store = b->dyn_store.p;
   P.tasks = b->tasks.p; P.vias = b->vias.p; P.acts = b->acts.p; P.gcons = b->gcons.p; P.cands = b->cands.p;
   P.results = b->results.p;
   return AFF_OK;
@@ -587,10 +587,10 @@ int aff_predict_batch_multi(const aff_scene_desc* desc, const int* devices, int 
 
 #ifdef AFFT_PROFILE
 // tuning builds only: cycles thread 0 of block 0 spent in phases A..F (+ loop head) of the sweep kernel
-int aff_debug_phase_clocks(unsigned long long out[8], int reset)
+int aff_debug_phase_clocks(unsigned long long out[16], int reset)
 {
-  if (cudaMemcpyFromSymbol(out, kgeneric::g_phaseClocks, sizeof(unsigned long long) * 8) != cudaSuccess) return AFF_ERR_CUDA;
-  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(kgeneric::g_phaseClocks, z, sizeof(z)); }
+  if (cudaMemcpyFromSymbol(out, kgeneric::g_phaseClocks, sizeof(unsigned long long) * 16) != cudaSuccess) return AFF_ERR_CUDA;
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(kgeneric::g_phaseClocks, z, sizeof(z)); }
   return AFF_OK;
 }
 #endif

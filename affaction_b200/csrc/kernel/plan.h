@@ -189,7 +189,11 @@ struct KPlan
   int32_t nStatPar;
   // thread-per-candidate ("sweep") kernel, sweep.cuh
   const int32_t* dyn_pslot;        // [nDyn] slot of each dynamic node's parent (dynamic node or static-parent copy)
+  const int32_t* node_shape_off;   // [nDyn + 1] CSR: dynamic shapes hanging on each dynamic node ...
+  const int32_t* node_shape_idx;   // ... their indices in dshape (the sweep FK writes their world records)
+  const int32_t* dyn_store;        // [nDyn] 1: the node's frame is read again after the FK walk (or by a non-adjacent child) and must be kept
   const int32_t* sweep_order;      // [nCands] candidates grouped by structure: thread i runs candidate sweep_order[i]
+  uint32_t sweep_joint_mask;       // IK joints whose frames the sweep kernel keeps (they can appear in a task / null-space chain)
   int32_t sweep_ok;                // the batch fits the per-thread caps of sweep.cuh
   int32_t warp_ok;                 // the two-nodes-per-round FK schedule of rollout.cuh computes every possible parent of an object before the object
 

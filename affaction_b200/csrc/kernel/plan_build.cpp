@@ -337,6 +337,17 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   P.nStatNear = (int)H.sbody.size();
   for (int b = 0; b < nB; ++b) if (shapeBody[b] && !dynamicB[b] && !nearCandidate(b)) addShapes(b, false);
   if ((int)H.dshape.size() > AFFK_MAX_DSHAPE || (int)H.dbody.size() > AFFK_MAX_DBODY) { err = "too many dynamic shapes"; return AFF_ERR_CAPACITY; }
+  // dynamic shapes by the node they hang on (CSR): the thread-per-candidate FK writes their world records
+  {
+    const int nD = (int)H.dyn.size();
+    H.node_shape_off.assign((size_t)nD + 1, 0);
+    for (const KShape& sh : H.dshape) if (sh.node >= 0 && sh.node < nD) H.node_shape_off[(size_t)sh.node + 1]++;
+    for (int n = 0; n < nD; ++n) H.node_shape_off[(size_t)n + 1] += H.node_shape_off[(size_t)n];
+    H.node_shape_idx.assign(H.dshape.size() + 1, 0);
+    std::vector<int32_t> fill(H.node_shape_off.begin(), H.node_shape_off.end() - 1);
+    for (size_t si = 0; si < H.dshape.size(); ++si) { const int n = H.dshape[si].node; if (n >= 0 && n < nD) H.node_shape_idx[(size_t)fill[(size_t)n]++] = (int32_t)si; }
+    for (const KShape& sh : H.dshape) if (sh.node < 0 || sh.node >= nD) { err = "internal: dynamic shape on a static node"; return AFF_ERR_INVALID; }
+  }
   // ---- precompiled shape pairs of the collision model, by type.  A body pair is listed when it can
   // ever be live without the AABB test: two dynamic bodies that are (or may come to be) in different
   // trees or one of which is explicit / an object, and dynamic tree bodies against explicit static bodies.
@@ -619,6 +630,48 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   P.bp_threshold = S.bpThreshold;
   P.nCands = (int)nCands;
   P.opts = opts;
+
+  // ---- thread-per-candidate kernel: which node frames have to be kept in the node array.  Its FK walk carries
+  // the frame of the node it has just computed in registers and writes the world records of the shapes on it at
+  // once; the array is read again only for (a) parents that are not the node processed immediately before their
+  // child, (b) frames of IK joints that can appear in the chain of a task / null-space body (Jacobian columns),
+  // (c) task effector / reference / frame bodies, null-space bodies, objects and everything an object can be
+  // connected to.  In a pizza `get` that leaves out the finger and fingertip frames: 12 of 31 nodes.
+  {
+    const int nD = (int)H.dyn.size();
+    H.dyn_store.assign((size_t)std::max(nD, 1), 0);
+    auto keepSlot = [&](int slot) { if (slot >= 0 && slot < nD) H.dyn_store[(size_t)slot] = 1; };
+    // (a) processing order: nodes outside objects in index order, then objects and their subtrees
+    std::vector<int> order;
+    for (int pass = 0; pass < 2; ++pass) for (int n = 0; n < nD; ++n) if ((H.dyn[n].under_obj != 0) == (pass == 1)) order.push_back(n);
+    for (size_t k = 0; k < order.size(); ++k) {
+      const int n = order[k];
+      if (H.dyn[n].kind == AFFK_NODE_OBJECT) continue;               // parents of objects: (c)
+      const int ps = H.dyn_pslot[(size_t)n];
+      if (k == 0 || order[k - 1] != ps) keepSlot(ps);
+    }
+    // (c) slots the step loop names, and the chains they can have
+    uint32_t chains = 0u;
+    std::vector<int> objParents;                                     // every slot an object can hang on
+    for (int sl : H.obj_parent_slot) objParents.push_back(sl);
+    for (const KGraphCon& g : H.gcons) if (g.kind == AFF_CON_CONNECT) objParents.push_back(g.parent_slot);
+    uint32_t objParentChains = 0u;
+    for (int sl : objParents) { keepSlot(sl); if (sl >= 0 && sl < nD) objParentChains |= H.dyn[(size_t)sl].chain; }
+    // an object connected below another object inherits that object's parents' chains as well: already in the union
+    auto useSlot = [&](int slot) {
+      if (slot < 0) return;
+      keepSlot(slot);
+      if (slot < nD) { chains |= H.dyn[(size_t)slot].chain; if (H.dyn[(size_t)slot].under_obj) chains |= objParentChains; }
+    };
+    for (const KTask& k : H.tasks) { useSlot(k.eff); useSlot(k.ref); useSlot(k.frame); }
+    useSlot(P.ns_base);
+    for (int k = 0; k < 2; ++k) { useSlot(P.ns_upperarm[k]); useSlot(P.ns_forearm[k]); useSlot(P.ns_hand[k]); }
+    for (int n : H.obj_node) keepSlot(n);
+    for (int n = 0; n < nD; ++n) if (H.dyn[n].kind == AFFK_NODE_OBJECT) keepSlot(n);
+    // (b) frames of the IK joints in those chains
+    for (int cj = 0; cj < S.nJ; ++cj) if ((chains >> cj) & 1u) keepSlot(H.j_node[(size_t)cj]);
+    P.sweep_joint_mask = chains;
+  }
 
   // ---- thread-per-candidate kernel: candidates grouped by structure, so that the 32 rollouts of a warp
   // walk the same task list and switch / re-parent at the same steps (the values differ, the branches do not)

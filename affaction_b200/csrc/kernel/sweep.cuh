@@ -53,12 +53,16 @@ AFF_DEV int t_block_max(int v)
 
 // -DAFFT_PROFILE (tuning builds only): thread 0 of block 0 adds the clock cycles between the phase barriers
 #if defined(AFFT_PROFILE) && !defined(AFF_EMULATE)
-__device__ unsigned long long g_phaseClocks[8];
+__device__ unsigned long long g_phaseClocks[16];
 #define T_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now_ = clock64(); g_phaseClocks[i] += (unsigned long long)(now_ - tmark_); tmark_ = now_; } } while (0)
 #define T_MARK_INIT long long tmark_ = clock64()
+#define T_SUBMARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now_ = clock64(); g_phaseClocks[i] += (unsigned long long)(now_ - smark_); smark_ = now_; } } while (0)
+#define T_SUBMARK_INIT long long smark_ = clock64()
 #else
 #define T_MARK(i) do { } while (0)
 #define T_MARK_INIT do { } while (0)
+#define T_SUBMARK(i) do { } while (0)
+#define T_SUBMARK_INIT do { } while (0)
 #endif
 
 #ifndef AFFT_PHASE
@@ -121,6 +125,23 @@ AFF_DEV void t_compose(double* out, const double* T, const double* Pp)
   for (int e = 0; e < 12; ++e) out[e] = r[e];
 }
 
+// World record of dynamic shape s from the frame An of its body (the arithmetic of k_collision step 1).
+AFF_DEV void t_shape_record(const KPlan& P, int s, const double* An, double* W)
+{
+  const KShape* sh = P.dshape + s;
+  const int type = ldg(&sh->type);
+  if (type == AFF_SHAPE_SSL || type == AFF_SHAPE_SPHERE) {
+    for (int e = 0; e < 3; ++e) W[e] = k_compose_elem(sh->A_CB, An, e);
+    if (type == AFF_SHAPE_SSL) {
+      const double len = ldg(&sh->ext[2]);
+      for (int e = 0; e < 3; ++e) { const double ax = k_compose_elem(sh->A_CB, An, 9 + e); W[9 + e] = ax; W[3 + e] = len * ax; }
+    } else { W[3] = 0.0; W[4] = 0.0; W[5] = 0.0; }
+    W[6] = ldg(&sh->ext[0]); W[7] = ldg(&sh->bound);
+  } else {
+    for (int e = 0; e < 12; ++e) W[e] = k_compose_elem(sh->A_CB, An, e);
+  }
+}
+
 // RcsGraph_setState for the dynamic nodes, parents first: nodes that do not hang below a
 // re-parentable object in index order, then the objects and their subtrees (an object's current
 // parent may be any node of the first group).
@@ -128,6 +149,10 @@ AFFT_PHASE void t_fk(TCtx& c, bool init)
 {
   const KPlan& P = *c.P;
   TState& S = *c.S;
+  // A holds the frame of node `held` (the node computed last): along a kinematic chain the parent of the next
+  // node is that node, and its frame is taken from registers instead of being read back from the node array
+  double A[12];
+  int held = -1;
   for (int pass = 0; pass < 2; ++pass) {
     if (pass == 1 && P.nObj == 0) break;
     for (int n = 0; n < P.nDyn; ++n) {
@@ -136,46 +161,53 @@ AFFT_PHASE void t_fk(TCtx& c, bool init)
       const KNode* nd = P.dyn + n;
       const int kind = ldg(&nd->kind);
       double* out = S.nodes + 12 * n;
+      // the world records of the shapes that hang on this node are made here, from the frame in registers
+      // (k_collision step 1), instead of re-reading the node array in the collision phase
+      const int sh0 = ldg(&P.node_shape_off[n]), sh1 = ldg(&P.node_shape_off[n + 1]);
       if (kind == AFFK_NODE_OBJECT) {
         const int slot = ldg(&nd->qidx);
-        if ((c.objHasRel >> slot) & 1u) t_compose(out, S.objrel + 12 * slot, S.nodes + 12 * OBJ_GET(c, objParentSlot, slot));
-        else if (init || OBJ_GET(c, objParentDynamic, slot)) {
-          double A[12];
-          const double* Pp = S.nodes + 12 * OBJ_GET(c, objParentSlot, slot);
-          for (int e = 0; e < 12; ++e) A[e] = Pp[e];
-          for (int k = 0; k < 6; ++k) k_apply_joint(A, k, S.objq6[6 * slot + k]);
-          for (int e = 0; e < 12; ++e) out[e] = A[e];
-        }
-        continue;
-      }
-      // parent: a dynamic node, or one of the static frames copied behind the dynamic nodes
-      const double* Pp = S.nodes + 12 * ldg(&P.dyn_pslot[n]);
-      if (kind == AFFK_NODE_FIXED && ldg(&nd->identityT)) { for (int e = 0; e < 12; ++e) out[e] = Pp[e]; continue; }
-      double A[12], T[12];
-      for (int e = 0; e < 12; ++e) T[e] = ldg(&nd->T[e]);
-      t_compose(A, T, Pp);
-      if (kind != AFFK_NODE_FIXED) {
-        const int jt = ldg(&nd->jtype);
-        double s, co;
-        if (kind == AFFK_NODE_JOINT_IK) {
-          const double qv = S.q[ldg(&nd->qidx)];
-          if (jt >= AFF_JNT_ROT_X) aff_sincos(qv, &s, &co); else { s = qv; co = 0.0; }
+        const int ps = OBJ_GET(c, objParentSlot, slot);
+        if (((c.objHasRel >> slot) & 1u) || init || OBJ_GET(c, objParentDynamic, slot)) {
+          if (ps != held) { const double* Pp = S.nodes + 12 * ps; for (int e = 0; e < 12; ++e) A[e] = Pp[e]; }
+          if ((c.objHasRel >> slot) & 1u) t_compose(A, S.objrel + 12 * slot, A);
+          else for (int k = 0; k < 6; ++k) k_apply_joint(A, k, S.objq6[6 * slot + k]);
         } else {
-          s = (jt >= AFF_JNT_ROT_X) ? ldg(&P.dynSC[2 * n]) : ldg(&P.dynQ[n]);
-          co = ldg(&P.dynSC[2 * n + 1]);
+          for (int e = 0; e < 12; ++e) A[e] = out[e];        // static parent, not re-parented: the pose stands
         }
-        if (jt >= AFF_JNT_ROT_X) {
-          const int d = jt - AFF_JNT_ROT_X, a = (d + 1) % 3, b = (d + 2) % 3;
-          for (int k = 0; k < 3; ++k) {
-            const double ra = A[3 + 3 * a + k], rb = A[3 + 3 * b + k];
-            A[3 + 3 * a + k] = fma(s, rb, co * ra);
-            A[3 + 3 * b + k] = fma(co, rb, -(s * ra));
+      } else {
+        // parent: a dynamic node, or one of the static frames copied behind the dynamic nodes
+        const int ps = ldg(&P.dyn_pslot[n]);
+        if (ps != held) { const double* Pp = S.nodes + 12 * ps; for (int e = 0; e < 12; ++e) A[e] = Pp[e]; }
+        if (!(kind == AFFK_NODE_FIXED && ldg(&nd->identityT))) {
+          double T[12];
+          for (int e = 0; e < 12; ++e) T[e] = ldg(&nd->T[e]);
+          t_compose(A, T, A);
+          if (kind != AFFK_NODE_FIXED) {
+            const int jt = ldg(&nd->jtype);
+            double s, co;
+            if (kind == AFFK_NODE_JOINT_IK) {
+              const double qv = S.q[ldg(&nd->qidx)];
+              if (jt >= AFF_JNT_ROT_X) aff_sincos(qv, &s, &co); else { s = qv; co = 0.0; }
+            } else {
+              s = (jt >= AFF_JNT_ROT_X) ? ldg(&P.dynSC[2 * n]) : ldg(&P.dynQ[n]);
+              co = ldg(&P.dynSC[2 * n + 1]);
+            }
+            if (jt >= AFF_JNT_ROT_X) {
+              const int d = jt - AFF_JNT_ROT_X, a = (d + 1) % 3, b = (d + 2) % 3;
+              for (int k = 0; k < 3; ++k) {
+                const double ra = A[3 + 3 * a + k], rb = A[3 + 3 * b + k];
+                A[3 + 3 * a + k] = fma(s, rb, co * ra);
+                A[3 + 3 * b + k] = fma(co, rb, -(s * ra));
+              }
+            } else {
+              for (int k = 0; k < 3; ++k) A[k] = fma(s, A[3 + 3 * jt + k], A[k]);
+            }
           }
-        } else {
-          for (int k = 0; k < 3; ++k) A[k] = fma(s, A[3 + 3 * jt + k], A[k]);
         }
       }
-      for (int e = 0; e < 12; ++e) out[e] = A[e];
+      held = n;
+      if (ldg(&P.dyn_store[n])) for (int e = 0; e < 12; ++e) out[e] = A[e];      // frames nobody reads again stay in registers
+      for (int k = sh0; k < sh1; ++k) { const int si = ldg(&P.node_shape_idx[k]); t_shape_record(P, si, A, S.shp + 12 * si); }
     }
   }
 }
@@ -191,24 +223,11 @@ AFFT_PHASE void t_collision(TCtx& c, double need, KCollResult* out)
   const double thr = P.bp_threshold;
   double* shp = S.shp; double* baabb = S.baabb; double* taabb = S.taabb;
   int* btree = S.btree;
-  // 1. world records of the dynamic shapes
-  for (int s = 0; s < P.nDynShapes; ++s) {
-    const KShape* sh = P.dshape + s;
-    const double* An = S.nodes + 12 * ldg(&sh->node);
-    const int type = ldg(&sh->type);
-    double* W = shp + 12 * s;
-    if (type == AFF_SHAPE_SSL || type == AFF_SHAPE_SPHERE) {
-      for (int e = 0; e < 3; ++e) W[e] = k_compose_elem(sh->A_CB, An, e);
-      if (type == AFF_SHAPE_SSL) {
-        const double len = ldg(&sh->ext[2]);
-        for (int e = 0; e < 3; ++e) { const double ax = k_compose_elem(sh->A_CB, An, 9 + e); W[9 + e] = ax; W[3 + e] = len * ax; }
-      } else { W[3] = 0.0; W[4] = 0.0; W[5] = 0.0; }
-      W[6] = ldg(&sh->ext[0]); W[7] = ldg(&sh->bound);
-    } else {
-      for (int e = 0; e < 12; ++e) W[e] = k_compose_elem(sh->A_CB, An, e);
-    }
-  }
-  // 2. per dynamic body: active flag, tree, AABB
+  T_SUBMARK_INIT;
+  // 1. the world records of the dynamic shapes were written by the FK walk (t_fk)
+  T_SUBMARK(8);
+  // 2. per dynamic body: active flag, tree, AABB; 3. the tree boxes are the running min / max over their bodies
+  for (int i = 0; i < 6 * P.nTrees; ++i) taabb[i] = (i % 6 < 3) ? DBL_MAX : -DBL_MAX;
   for (int bi = 0; bi < P.nDynBodies; ++bi) {
     const KShapeBody* b = P.dbody + bi;
     const int f = ldg(&b->first_shape), n = ldg(&b->n_shapes), os = ldg(&b->obj_slot), ts = ldg(&b->toggle_slot);
@@ -236,20 +255,13 @@ AFFT_PHASE void t_collision(TCtx& c, double need, KCollResult* out)
       }
     }
     for (int q = 0; q < 3; ++q) { baabb[6 * bi + q] = mn[q]; baabb[6 * bi + 3 + q] = mx[q]; }
-    btree[bi] = act ? (os ? OBJ_GET(c, objTree, os - 1) : ldg(&b->tree)) : -2;
+    const int bt = act ? (os ? OBJ_GET(c, objTree, os - 1) : ldg(&b->tree)) : -2;
+    btree[bi] = bt;
+    if (bt >= 0)
+      for (int q = 0; q < 3; ++q) { if (mn[q] < taabb[6 * bt + q]) taabb[6 * bt + q] = mn[q]; if (mx[q] > taabb[6 * bt + 3 + q]) taabb[6 * bt + 3 + q] = mx[q]; }
   }
-  // 3. tree AABBs
-  for (int t = 0; t < P.nTrees; ++t)
-    for (int k = 0; k < 6; ++k) {
-      const bool isMin = k < 3;
-      double v = isMin ? DBL_MAX : -DBL_MAX;
-      for (int b = 0; b < P.nDynBodies; ++b) {
-        const double x = baabb[6 * b + k];
-        const bool take = (btree[b] == t) && (isMin ? x < v : x > v);
-        v = take ? x : v;
-      }
-      taabb[6 * t + k] = v;
-    }
+  T_SUBMARK(9);
+  T_SUBMARK(10);
   // 4. static bodies that are not explicit: tree box first, then the tree's bodies
   int nLive = 0;
   double uni[6] = {DBL_MAX, DBL_MAX, DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX};     // union of the tree boxes: a pure pre-filter
@@ -270,6 +282,7 @@ AFFT_PHASE void t_collision(TCtx& c, double need, KCollResult* out)
     }
   }
   if (nLive > AFFK_MAX_NEAR) nLive = AFFK_MAX_NEAR;
+  T_SUBMARK(11);
   // 5. narrow phase
   double best = DBL_MAX; int bestKey = 0x7fffffff; int nCostly = 0;
   const double cullMargin = 1.0e-9;
@@ -316,6 +329,7 @@ AFFT_PHASE void t_collision(TCtx& c, double need, KCollResult* out)
     const double d = KP_SWAP(pr.meta) ? (k_seg_seg(pB, dB, A, A + 3) - rB) - rA : (k_seg_seg(A, A + 3, pB, dB) - rA) - rB;
     T_ACCOUNT(d, pr.key);
   }
+  T_SUBMARK(12);
   for (int i = 0; i < P.nSB; ++i) {
     const KPair pr = ldg_pair(&P.pairsSB[i]);
     if (T_TREES_FAR(pr.meta)) continue;
@@ -353,6 +367,7 @@ AFFT_PHASE void t_collision(TCtx& c, double need, KCollResult* out)
     else d = k_seg_cyl(pl, dl, 0.5 * ext[2], ext[0]) - rS;
     T_ACCOUNT(d, pr.key);
   }
+  T_SUBMARK(13);
   for (int i = 0; i < nLive; ++i) {
     const int ia = S.live[2 * i], ib = S.live[2 * i + 1];
     const double d = t_pair_distance(c, ia, ib);
@@ -685,7 +700,7 @@ AFF_DEV void t_rollout(const KPlan& P, int cand, TState& S, bool alive)
       const int jtype = ldg(&P.j_type[j]);
       jf.valid = 1; jf.type = jtype;
       for (int k = 0; k < 3; ++k) { jf.ax[k] = 0.0; jf.org[k] = 0.0; }
-      if ((anyChain >> j) & 1u) {       // the frame of a joint outside every chain is never used
+      if ((anyChain >> j) & 1u) {       // the frame of a joint outside every chain is never used (and not kept: KPlan::dyn_store)
         const double* A = k_slot(c, ldg(&P.j_node[j]));
         const int ar = (jtype < AFF_JNT_ROT_X) ? jtype : jtype - AFF_JNT_ROT_X;
         for (int k = 0; k < 3; ++k) { jf.ax[k] = A[3 + 3 * ar + k]; jf.org[k] = A[k]; }

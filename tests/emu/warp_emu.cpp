@@ -103,7 +103,7 @@ static int emu_run(int sweep, const aff_scene_desc* scene, const aff_task_desc* 
   P.statA = statA.data(); P.statSC = statSC.data(); P.dynSC = dynSC.data(); P.fktab = H.fktab.data(); P.statpar_ref = H.statpar_ref.data(); P.obj_parent_slot = H.obj_parent_slot.data(); P.obj_parent_tree = H.obj_parent_tree.data(); P.dyn_under = H.dyn_under.data(); P.dyn_chain = H.dyn_chain.data(); P.dynT = H.dynT.data(); P.dynQ = H.dynQ.data();
   P.dshape = H.dshape.data(); P.dbody = H.dbody.data(); P.sshape = H.sshape.data(); P.sbody = H.sbody.data();
   P.sshapeA = sshapeA.data(); P.sbodyAABB = sbodyAABB.data(); P.pairsSS = H.pairsSS.data(); P.pairsSB = H.pairsSB.data(); P.sseg = sseg.data();
-  P.obj_node = H.obj_node.data(); P.obj_body = H.obj_body.data(); P.obj_q6 = H.obj_q6.data(); P.dyn_pslot = H.dyn_pslot.data(); P.sweep_order = H.sweep_order.data();
+  P.obj_node = H.obj_node.data(); P.obj_body = H.obj_body.data(); P.obj_q6 = H.obj_q6.data(); P.dyn_pslot = H.dyn_pslot.data(); P.sweep_order = H.sweep_order.data(); P.node_shape_off = H.node_shape_off.data(); P.node_shape_idx = H.node_shape_idx.data(); P.dyn_store = H.dyn_store.data();
   P.tasks = H.tasks.data(); P.vias = H.vias.data(); P.acts = H.acts.data(); P.gcons = H.gcons.data(); P.cands = H.cands.data();
   P.results = results.data();
   P.qlog = qlog; P.qlog_rows = qlog ? (int)qlogRows : 0;

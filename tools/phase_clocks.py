@@ -14,7 +14,7 @@ s = ab.HostScene(); b = ab.HostBatch(s); b.add_perturbed(cmd, n)
 dev = ab.DeviceBatch(s, b, ab.default_opts())
 st = torch.cuda.current_stream().cuda_stream
 G = ab.lib().gpu()
-out = (C.c_ulonglong * 8)()
+out = (C.c_ulonglong * 16)()
 dev.launch(st); torch.cuda.synchronize()
 G.aff_debug_phase_clocks(out, 1)
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -26,3 +26,6 @@ tot = sum(out[i] for i in range(7))
 print("%s n=%d: %.1f ms = %.0f rollouts/s" % (cmd, n, ms, n / ms * 1e3))
 for i, nm in enumerate(names):
     print("  %-24s %6.1f %%   %8.0f cycles/step" % (nm, 100.0 * out[i] / tot, out[i] / 1555.0))
+sub = ["E1 shape records", "E2 body boxes", "E3 tree boxes", "E4 static near test", "E5 seg-seg pairs", "E6 seg-box/cyl pairs"]
+for i, nm in enumerate(sub):
+    print("    %-22s %6.1f %%   %8.0f cycles/step" % (nm, 100.0 * out[8 + i] / tot, out[8 + i] / 1555.0))
