@@ -65,6 +65,13 @@ __device__ unsigned long long g_phaseClocks[16];
 #define T_SUBMARK_INIT do { } while (0)
 #endif
 
+// barrier k of the step loop (0: loop head, 1: A|B, 2: B|C, 3: C|D, 4: D|E, 5: E|F); AFFT_SYNC_MASK selects which
+// are real (tuning builds; default: all)
+#ifndef AFFT_SYNC_MASK
+#define AFFT_SYNC_MASK 0x15      /* measured round 2: loop head, B|C and D|E are enough to keep the warps of a block within a phase of each other */
+#endif
+#define T_SYNCI(k) do { if ((AFFT_SYNC_MASK >> (k)) & 1) T_SYNC(); } while (0)
+
 #ifndef AFFT_PHASE
 #ifdef AFFT_PHASE_NOINLINE
 #define AFFT_PHASE AFF_NOINLINE
@@ -525,7 +532,7 @@ AFF_DEV void t_rollout(const KPlan& P, int cand, TState& S, bool alive)
     if (P.opts.early_exit && !T_BLOCK_ANY(running && iter < nSteps)) break;
     const bool act = running && iter < nSteps;
     const int successPrev = success;
-    T_SYNC();
+    T_SYNCI(0);
     T_MARK(6);
     if (act) {   // ======== phase A: trajectories, constraints, activations, task errors
     // ---- task switch / qFilt (:166-180)
@@ -631,7 +638,7 @@ AFF_DEV void t_rollout(const KPlan& P, int cand, TState& S, bool alive)
     for (int t = 0; t < nTasks; ++t)
       if ((activeMask >> t) & 1u) t_task_dx(c, t, tasks, dxv + S.rowOf[t]);
     }
-    T_SYNC();
+    T_SYNCI(1);
     T_MARK(0);
     if (act) {   // ======== phase B: Jacobian columns, null-space gradient
     // Elbow / wrist terms (:448-570): the factors do not depend on the joint, only the Jacobian entries do
@@ -759,7 +766,7 @@ AFF_DEV void t_rollout(const KPlan& P, int cand, TState& S, bool alive)
     }
     jmaskBits |= aMask;
     }
-    T_SYNC();
+    T_SYNCI(2);
     T_MARK(1);
     if (act) {   // ======== phase C: right inverse, limits, integration
     // ---- solveRightInverse
@@ -840,14 +847,14 @@ AFF_DEV void t_rollout(const KPlan& P, int cand, TState& S, bool alive)
       }
     }
     }
-    T_SYNC();
+    T_SYNCI(3);
     T_MARK(2);
     // integration, FK, collision model, checkState (:730-752)
     if (act && !singular) t_fk(c, false);                                                       // ======== phase D
-    T_SYNC();
+    T_SYNCI(4);
     T_MARK(3);
     if (act && !singular) t_collision(c, r_minDist > 0.001 ? r_minDist : 0.001, &cm);           // ======== phase E
-    T_SYNC();
+    T_SYNCI(5);
     T_MARK(4);
     if (act) {   // ======== phase F: checkState, costs, tracking error
     if (!singular) {

@@ -1,5 +1,3 @@
-for v in t512b2 t256b4 t128b8 t256b3 t256b5 t256b6; do
-  for n in 151552 227328; do
-    echo "== $v n=$n $(AFF_LIB_PATH=/root/repo/build_variants/$v.so python tools/profile_run.py $n 2 'get fresh_tomatoes' sweep | grep best)"
-  done
+for v in s0x37 s0x2f s0x27 s0x2b s0x15; do
+  echo "== $v $(AFF_LIB_PATH=/root/repo/build_variants/$v.so python tools/profile_run.py 151552 2 'get fresh_tomatoes' sweep | grep best)"
 done
