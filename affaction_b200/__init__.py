@@ -86,7 +86,7 @@ HOST_SYMBOLS = [
     "aff_host_scene_device", "aff_host_batch_create", "aff_host_batch_destroy", "aff_host_batch_clear",
     "aff_host_batch_add_action", "aff_host_batch_add_perturbed", "aff_host_batch_num_tasks", "aff_host_batch_num_constraints",
     "aff_host_batch_num_candidates", "aff_host_batch_tasks", "aff_host_batch_constraints", "aff_host_batch_candidates",
-    "aff_host_batch_task_name", "aff_host_predict", "aff_host_format_message", "aff_host_check_trajectory", "aff_host_scene_apply_rollout", "aff_host_predict_sequence", "aff_host_rollout_transforms", "aff_host_format_message_q",
+    "aff_host_batch_task_name", "aff_host_predict", "aff_host_format_message", "aff_host_check_trajectory", "aff_host_scene_apply_rollout", "aff_host_predict_sequence", "aff_host_rollout_transforms", "aff_host_format_message_q", "aff_host_scene_desc_roundtrip",
 ]
 
 
@@ -151,6 +151,7 @@ def _signatures():
         "aff_host_format_message": (i32, [vp, vp, vp, dbl, vp, sz]),
         "aff_host_scene_apply_rollout": (i32, [vp, vp, sz, vp, i32, dbl]),
         "aff_host_rollout_transforms": (i32, [vp, vp, sz, vp, i32, dbl, vp]),
+        "aff_host_scene_desc_roundtrip": (i32, [vp]),
         "aff_host_format_message_q": (i32, [vp, vp, vp, dbl, vp, vp, sz]),
         "aff_host_predict_sequence": (i32, [vp, cstr, dbl, i32, vp, vp, vp, sz, i32]),
         "aff_host_check_trajectory": (i32, [vp, vp, sz, i32, i32, i32, dbl, i32, vp, vp, vp, vp, vp, vp, sz, vp, sz]),

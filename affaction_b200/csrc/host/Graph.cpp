@@ -112,6 +112,44 @@ Graph Graph::load(const std::string& file, std::vector<std::string>* tail)
   return g;
 }
 
+Graph Graph::fromDesc(const aff_scene_desc& d, const std::vector<std::string>& bodyNames,
+                      const std::vector<std::string>& jointNames, const std::string& graphName)
+{
+  if ((int)bodyNames.size() != d.n_bodies || (int)jointNames.size() != d.n_joints) throw std::runtime_error("fromDesc: name lists do not match the description");
+  Graph g;
+  g.name = graphName;
+  auto get12 = [](const double* p) { HTr A; for (int k = 0; k < 3; ++k) A.org[k] = p[k]; for (int i = 0; i < 3; ++i) for (int k = 0; k < 3; ++k) A.rot[i][k] = p[3 + 3 * i + k]; return A; };
+  g.bodies.resize((size_t)d.n_bodies); g.joints.resize((size_t)d.n_joints); g.shapes.resize((size_t)d.n_shapes);
+  for (int b = 0; b < d.n_bodies; ++b) {
+    Body& B = g.bodies[(size_t)b];
+    B.name = bodyNames[(size_t)b]; B.parent = d.body_parent[b]; B.rigid_body_joints = d.body_rbj[b] != 0;
+    B.A_BP = get12(d.body_A_BP + 12 * (size_t)b); B.A_BI = HTr::identity();
+    B.firstJoint = d.body_first_joint[b]; B.nJoints = d.body_n_joints[b]; B.firstShape = d.body_first_shape[b]; B.nShapes = d.body_n_shapes[b];
+    g.bodyIndex_[B.name] = b;
+    for (int k = 0; k < B.nJoints; ++k) g.joints.at((size_t)(B.firstJoint + k)).body = b;
+    for (int k = 0; k < B.nShapes; ++k) g.shapes.at((size_t)(B.firstShape + k)).body = b;
+  }
+  for (int j = 0; j < d.n_joints; ++j) {
+    Joint& J = g.joints[(size_t)j];
+    J.name = jointNames[(size_t)j]; J.type = d.joint_type[j]; J.constrained = d.joint_constrained[j] != 0;
+    J.q_init = d.joint_q_init[j]; J.q0 = d.joint_q0[j]; J.q_min = d.joint_q_min[j]; J.q_max = d.joint_q_max[j];
+    J.speedLimit = d.joint_speed_limit[j]; J.accLimit = d.joint_acc_limit[j]; J.weightJL = d.joint_weight_jl[j]; J.weightMetric = d.joint_weight_metric[j];
+    J.A_JP = get12(d.joint_A_JP + 12 * (size_t)j);
+    J.jacobiIndex = J.constrained ? -1 : g.nJ++;
+    g.jointIndex_[J.name] = j;
+  }
+  for (int s = 0; s < d.n_shapes; ++s) {
+    Shape& S = g.shapes[(size_t)s];
+    S.type = d.shape_type[s]; S.distance = d.shape_distance[s] != 0; S.A_CB = get12(d.shape_A_CB + 12 * (size_t)s);
+    for (int k = 0; k < 3; ++k) S.extents[k] = d.shape_extents[3 * (size_t)s + k];
+  }
+  g.bpThreshold = d.bp_threshold;
+  g.bpTrees.assign(d.bp_tree_root, d.bp_tree_root + d.n_bp_trees);
+  g.bpBodies.assign(d.bp_body, d.bp_body + d.n_bp_bodies);
+  g.computeForwardKinematics();
+  return g;
+}
+
 int Graph::getBodyByName(const std::string& n) const
 {
   auto it = bodyIndex_.find(n);

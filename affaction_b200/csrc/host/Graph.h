@@ -64,6 +64,11 @@ class Graph
 public:
   // Throws std::runtime_error on malformed input.
   static Graph load(const std::string& affsceneFile, std::vector<std::string>* tail = nullptr);
+  // The inverse of toDesc(): a Graph from a plain-C scene description plus the names the description does
+  // not carry.  This is how the shim gets its graph in the REFERENCE tree, where the description comes from
+  // the live RcsGraph (integration/rcs_graph_adapter.h) instead of an .affscene file.
+  static Graph fromDesc(const aff_scene_desc& d, const std::vector<std::string>& bodyNames,
+                        const std::vector<std::string>& jointNames, const std::string& graphName = "");
 
   int getBodyByName(const std::string& name) const;        // -1 if absent
   int getBodyByNameNoCase(const std::string& name) const;  // RcsGraph_getBodyByNameNoCase

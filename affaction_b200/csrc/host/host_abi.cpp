@@ -126,6 +126,30 @@ int aff_host_rollout_transforms(aff_host_scene* s, const aff_host_batch* b, size
   } catch (const std::exception& e) { g_hostError = e.what(); return AFF_ERR_INVALID; }
 }
 
+int aff_host_scene_desc_roundtrip(aff_host_scene* s)
+{
+  try {
+    const aff_scene_desc* d = s->graph.toDesc();
+    std::vector<std::string> bn, jn;
+    for (const Body& b : s->graph.bodies) bn.push_back(b.name);
+    for (const Joint& j : s->graph.joints) jn.push_back(j.name);
+    Graph g2 = Graph::fromDesc(*d, bn, jn, s->graph.name);
+    const aff_scene_desc* e = g2.toDesc();
+    auto same = [](const void* a, const void* b, size_t n) { return n == 0 || std::memcmp(a, b, n) == 0; };
+    const size_t nb = (size_t)d->n_bodies, nj = (size_t)d->n_joints, ns = (size_t)d->n_shapes;
+    bool ok = d->n_bodies == e->n_bodies && d->n_joints == e->n_joints && d->n_shapes == e->n_shapes &&
+              d->n_bp_trees == e->n_bp_trees && d->n_bp_bodies == e->n_bp_bodies && d->bp_threshold == e->bp_threshold;
+    ok = ok && same(d->body_parent, e->body_parent, 4 * nb) && same(d->body_A_BP, e->body_A_BP, 96 * nb) && same(d->body_rbj, e->body_rbj, nb) &&
+         same(d->body_first_joint, e->body_first_joint, 4 * nb) && same(d->body_first_shape, e->body_first_shape, 4 * nb) &&
+         same(d->joint_type, e->joint_type, 4 * nj) && same(d->joint_A_JP, e->joint_A_JP, 96 * nj) && same(d->joint_q_init, e->joint_q_init, 8 * nj) &&
+         same(d->joint_q_min, e->joint_q_min, 8 * nj) && same(d->joint_q_max, e->joint_q_max, 8 * nj) && same(d->joint_speed_limit, e->joint_speed_limit, 8 * nj) &&
+         same(d->shape_type, e->shape_type, 4 * ns) && same(d->shape_A_CB, e->shape_A_CB, 96 * ns) && same(d->shape_extents, e->shape_extents, 24 * ns) &&
+         same(d->bp_tree_root, e->bp_tree_root, 4 * (size_t)d->n_bp_trees) && same(d->bp_body, e->bp_body, 4 * (size_t)d->n_bp_bodies) &&
+         d->ns_base == e->ns_base && d->ns_hand[0] == e->ns_hand[0] && d->ns_hand[1] == e->ns_hand[1];
+    return ok ? 1 : 0;
+  } catch (const std::exception& e) { g_hostError = e.what(); return AFF_ERR_INVALID; }
+}
+
 aff_scene* aff_host_scene_device(aff_host_scene* s, int device)
 {
   // one cached device scene per host scene; asking for another device replaces it

@@ -51,8 +51,8 @@ L2_FLUSH_BYTES = 256 << 20
 # candidate tables read once (tasks, via points, activations, graph constraints, candidate record) + 88-byte verdict
 ALGORITHMIC_BYTES_PER_ROLLOUT = 2300 + 88
 # dram__bytes_read.sum + dram__bytes_write.sum of one aff_sweep_kernel launch / rollouts in it (profiles/r2_summary.md:
-# 5.33 TB for 151 552 rollouts): the per-thread rollout state does not fit on chip and streams through HBM
-NCU_DRAM_BYTES_PER_ROLLOUT = 35150000
+# 4.47 TB for 151 552 rollouts, gpurun_out/prof_r2c.ncu-rep): the per-thread rollout state does not fit on chip and streams through HBM
+NCU_DRAM_BYTES_PER_ROLLOUT = 29480000
 
 
 def algorithmic_flops_per_rollout():

@@ -26,6 +26,10 @@ const char* aff_host_last_error(void);
  * (tools/flatten_scene.py output of the reference's XML scene). NULL on error. */
 aff_host_scene* aff_host_scene_load(const char* path);
 void aff_host_scene_destroy(aff_host_scene* s);
+/* Round trip used by the tests of the reference-tree path: rebuild the scene's graph from its own plain-C
+ * description + names (Graph::fromDesc, what integration/rcs_graph_adapter.h feeds in the reference tree)
+ * and report whether the rebuilt graph yields a byte-identical description.  1 = identical, 0 = not, <0 error. */
+int aff_host_scene_desc_roundtrip(aff_host_scene* s);
 const aff_scene_desc* aff_host_scene_desc(aff_host_scene* s);
 int aff_host_num_bodies(const aff_host_scene* s);
 int aff_host_num_ik_joints(const aff_host_scene* s);

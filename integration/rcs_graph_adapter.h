@@ -68,6 +68,7 @@ public:
         speed_.push_back(JNT->speedLimit); acc_.push_back(JNT->accLimit);
         wjl_.push_back(JNT->weightJL); wmetric_.push_back(JNT->weightMetric);
         jointIndex_.push_back(JNT->jointIndex);
+        jointNames_.push_back(JNT->name);
       }
       nJoints_.push_back(nj);
       // shapes: primitives that take part in distance computation now, or can be switched on by a
@@ -117,6 +118,10 @@ public:
     for (size_t j = 0; j < jointIndex_.size(); ++j) qinit_[j] = graph->q->ele[jointIndex_[j]];
   }
 
+  const aff_scene_desc* desc() const { return &desc_; }
+  const std::vector<std::string>& bodyNames() const { return names_; }
+  const std::vector<std::string>& jointNames() const { return jointNames_; }
+
   int indexOf(const char* name) const
   {
     for (size_t i = 0; i < names_.size(); ++i) if (names_[i] == name) return (int)i;
@@ -149,7 +154,7 @@ private:
     parent_.clear(); firstJoint_.clear(); nJoints_.clear(); firstShape_.clear(); nShapes_.clear(); rbj_.clear(); abp_.clear();
     jtype_.clear(); jcon_.clear(); ajp_.clear(); qinit_.clear(); q0_.clear(); qmin_.clear(); qmax_.clear(); speed_.clear();
     acc_.clear(); wjl_.clear(); wmetric_.clear(); jointIndex_.clear(); stype_.clear(); sdist_.clear(); acb_.clear(); ext_.clear();
-    trees_.clear(); bpBodies_.clear(); names_.clear();
+    trees_.clear(); bpBodies_.clear(); names_.clear(); jointNames_.clear();
     std::memset(&desc_, 0, sizeof(desc_));
   }
 
@@ -158,7 +163,7 @@ private:
   std::vector<uint8_t> rbj_, jcon_, sdist_;
   std::vector<double> abp_, ajp_, qinit_, q0_, qmin_, qmax_, speed_, acc_, wjl_, wmetric_, acb_, ext_;
   std::vector<unsigned int> jointIndex_;
-  std::vector<std::string> names_;
+  std::vector<std::string> names_, jointNames_;
 };
 
 }   // namespace affgpu

@@ -364,3 +364,12 @@ def test_joint_limit_message_lists_the_joints(built):
             assert long.startswith(short) and long.count(" outside [") == r.fail_id0 >= 1
             return
     pytest.skip("no joint-limit verdict among the first 64 perturbed candidates")
+
+
+def test_graph_from_desc_roundtrip(built):
+    """Graph::fromDesc (the reference-tree entry: description from the live RcsGraph via
+    integration/rcs_graph_adapter.h) inverts Graph::toDesc on both committed scenes."""
+    import os
+    for f in ("pizza.affscene", "unittest_predict_many.affscene"):
+        s = ab.HostScene(os.path.join(ab.DATA_DIR, f))
+        assert ab.lib().aff_host_scene_desc_roundtrip(s.h) == 1
