@@ -468,7 +468,9 @@ int aff_predict_batch(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, 
   const char* mnEnv = getenv("AFF_SWEEP_MIN");
   const char* kEnv = getenv("AFF_KERNEL");
   const bool sweepLikely = !(kEnv && !strcmp(kEnv, "warp")) && n_cands >= (mnEnv ? (size_t)atoll(mnEnv) : (size_t)AFF_SWEEP_MIN_DEFAULT);
-  size_t wave = sweepLikely ? (size_t)s->smCount * 1024 : (size_t)s->smCount * AFF_BLOCKS_PER_SM * AFF_WARPS_PER_BLOCK;
+  // thread-per-candidate kernel: chunks of HALF a resident wave on two alternating kernel streams - two chunks are
+  // co-resident (full occupancy), and the first kernel starts after half the plan-compile time of a full wave
+  size_t wave = sweepLikely ? (size_t)s->smCount * 512 : (size_t)s->smCount * AFF_BLOCKS_PER_SM * AFF_WARPS_PER_BLOCK;
   // chunks in flight: at most three (running, queued, being compiled); the oldest is collected and freed
   struct Part { aff_batch* b; size_t first; cudaEvent_t done; };
   std::vector<Part> parts;
@@ -497,7 +499,9 @@ int aff_predict_batch(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, 
     if (ks) cudaStreamDestroy(ks);
     ks = cs = nullptr; wave = n_cands;
   }
+  if (ks && sweepLikely && cudaStreamCreateWithFlags(&ks2, cudaStreamNonBlocking) != cudaSuccess) ks2 = nullptr;
   if (n_cands <= wave + wave / 2) wave = n_cands;
+  const size_t maxInFlight = ks2 ? 3 : 2;
   for (size_t off = 0; off < n_cands && rc == AFF_OK;) {
     size_t cnt = std::min(wave, n_cands - off);
     if (n_cands - off - cnt < wave / 2) cnt = n_cands - off;        // no short last chunk
@@ -522,22 +526,24 @@ int aff_predict_batch(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, 
     Part part{b, off, nullptr};
     if (nParts == 0 && ks) {
       // the first chunk tells how many rollouts are resident at once with this batch's shared-memory footprint
-      const size_t resident = b->useSweep ? (size_t)s->smCount * 1024 : (size_t)b->grid * AFF_WARPS_PER_BLOCK;
+      const size_t resident = b->useSweep ? (size_t)s->smCount * 512 : (size_t)b->grid * AFF_WARPS_PER_BLOCK;
       if (resident > 0 && (resident < wave || !b->useSweep)) wave = std::min(wave, resident);
     }
-    rc = aff_batch_launch(b, ks);
-    if (rc == AFF_OK && ks && (cudaEventCreateWithFlags(&part.done, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(part.done, ks) != cudaSuccess))
+    cudaStream_t kst = (ks2 && (nParts & 1)) ? ks2 : ks;
+    rc = aff_batch_launch(b, kst);
+    if (rc == AFF_OK && ks && (cudaEventCreateWithFlags(&part.done, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(part.done, kst) != cudaSuccess))
       rc = fail(AFF_ERR_CUDA, "aff_predict_batch: cannot record an event");
     parts.push_back(part);
     ++nParts;
     off += cnt;
-    if (rc == AFF_OK && parts.size() > 2) { rc = retire(parts.front()); parts.erase(parts.begin()); }
+    if (rc == AFF_OK && parts.size() > maxInFlight) { rc = retire(parts.front()); parts.erase(parts.begin()); }
   }
   const auto t1 = now();
   for (Part& p : parts) { const int r = retire(p); if (rc == AFF_OK) rc = r; }
   parts.clear();
   const auto t2 = now();
   if (ks) cudaStreamDestroy(ks);
+  if (ks2) cudaStreamDestroy(ks2);
   if (cs) cudaStreamDestroy(cs);
   const auto t3 = now();
   if (timing) std::fprintf(stderr, "aff_predict_batch: %zu candidates in %zu chunk(s): plan + H2D %.1f ms (overlapped after the first chunk), "

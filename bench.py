@@ -43,6 +43,8 @@ VARIANTS = ["get tomato_sauce_bottle", "get fresh_tomatoes", "get italian_season
 PER_VARIANT = 151552                     # one resident wave of the thread-per-candidate kernel: 148 SMs x 2 blocks x 512 rollouts
 ROLLOUTS_PER_GPU = PER_VARIANT * len(VARIANTS)
 STEPS_PER_ROLLOUT = 1555
+WORKLOAD = ("synthetic sweep of perturbed-goal get candidates (BASELINE.json configs[4]), pizza scene, "
+            "PowerGrasp/BallGrasp/TopGrasp in equal parts, 1555 steps per rollout, no early exit")
 METRIC = "candidate IK rollouts/sec"
 UNIT = "rollouts/s"
 L2_FLUSH_BYTES = 256 << 20
@@ -144,8 +146,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic sweep of perturbed-goal get candidates, pizza scene, 3 grasp variants, 1555 steps each",
-                   "rollouts_per_step": sample, "note": "CPU oracle (restated reference; Rcs/Tropic are not vendored so the "
+        "config": {"workload": WORKLOAD, "rollouts_per_step": sample, "steps_per_rollout": STEPS_PER_ROLLOUT, "note": "CPU oracle (restated reference; Rcs/Tropic are not vendored so the "
                    "reference itself cannot be built), ConcurrentExecutor-style pool on all host threads"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d rollouts per step x %d steps" % (sample, args.steps)},
@@ -303,9 +304,7 @@ def run_cuda(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic sweep of perturbed-goal get candidates (BASELINE.json configs[4]), pizza scene, "
-                                   "PowerGrasp/BallGrasp/TopGrasp in equal parts, 1555 steps per rollout, no early exit",
-                       "rollouts_per_gpu_per_step": n_local, "steps_per_rollout": STEPS_PER_ROLLOUT,
+            "config": {"workload": WORKLOAD, "rollouts_per_gpu_per_step": n_local, "steps_per_rollout": STEPS_PER_ROLLOUT,
                        "kernel": kname + (" (one rollout per thread, 32 per warp)" if sweep else " (one rollout per warp)"),
                        "l2": "flushed between timed iterations (256 MiB fill)",
                        "parallelism": "candidates sharded statically over %d GPU(s); NCCL gather of verdicts to rank 0" % world,
