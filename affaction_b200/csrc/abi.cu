@@ -474,7 +474,7 @@ int aff_predict_batch(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, 
   // chunks in flight: at most three (running, queued, being compiled); the oldest is collected and freed
   struct Part { aff_batch* b; size_t first; cudaEvent_t done; };
   std::vector<Part> parts;
-  cudaStream_t ks = nullptr, cs = nullptr;
+  cudaStream_t ks = nullptr, ks2 = nullptr, cs = nullptr;
   int rc = AFF_OK;
   double planMs = 0.0;
   size_t nParts = 0;
