@@ -468,9 +468,9 @@ int aff_predict_batch(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, 
   const char* mnEnv = getenv("AFF_SWEEP_MIN");
   const char* kEnv = getenv("AFF_KERNEL");
   const bool sweepLikely = !(kEnv && !strcmp(kEnv, "warp")) && n_cands >= (mnEnv ? (size_t)atoll(mnEnv) : (size_t)AFF_SWEEP_MIN_DEFAULT);
-  // thread-per-candidate kernel: chunks of HALF a resident wave on two alternating kernel streams - two chunks are
-  // co-resident (full occupancy), and the first kernel starts after half the plan-compile time of a full wave
-  size_t wave = sweepLikely ? (size_t)s->smCount * 512 : (size_t)s->smCount * AFF_BLOCKS_PER_SM * AFF_WARPS_PER_BLOCK;
+  // (measured round 2: half-wave chunks on two alternating kernel streams, to start the first kernel earlier, lose
+  // more in the kernels than they gain: e2e 99 k -> 88 k rollouts/s)
+  size_t wave = sweepLikely ? (size_t)s->smCount * 1024 : (size_t)s->smCount * AFF_BLOCKS_PER_SM * AFF_WARPS_PER_BLOCK;
   // chunks in flight: at most three (running, queued, being compiled); the oldest is collected and freed
   struct Part { aff_batch* b; size_t first; cudaEvent_t done; };
   std::vector<Part> parts;
@@ -499,7 +499,6 @@ int aff_predict_batch(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, 
     if (ks) cudaStreamDestroy(ks);
     ks = cs = nullptr; wave = n_cands;
   }
-  if (ks && sweepLikely && cudaStreamCreateWithFlags(&ks2, cudaStreamNonBlocking) != cudaSuccess) ks2 = nullptr;
   if (n_cands <= wave + wave / 2) wave = n_cands;
   const size_t maxInFlight = ks2 ? 3 : 2;
   for (size_t off = 0; off < n_cands && rc == AFF_OK;) {
@@ -526,7 +525,7 @@ int aff_predict_batch(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, 
     Part part{b, off, nullptr};
     if (nParts == 0 && ks) {
       // the first chunk tells how many rollouts are resident at once with this batch's shared-memory footprint
-      const size_t resident = b->useSweep ? (size_t)s->smCount * 512 : (size_t)b->grid * AFF_WARPS_PER_BLOCK;
+      const size_t resident = b->useSweep ? (size_t)s->smCount * 1024 : (size_t)b->grid * AFF_WARPS_PER_BLOCK;
       if (resident > 0 && (resident < wave || !b->useSweep)) wave = std::min(wave, resident);
     }
     cudaStream_t kst = (ks2 && (nParts & 1)) ? ks2 : ks;
