@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 #include <numeric>
+#include <thread>
 #include <unordered_map>
 
 namespace affk
@@ -500,121 +501,176 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   for (int b : objBodies) { const int pr = H.dyn[bodyRef[b]].parent; if (pr >= 0 && H.roundOf[pr] >= H.roundOf[bodyRef[b]]) P.warp_ok = 0; }
   H.cands.resize(nCands);
   H.vias.reserve(nConsIn); H.acts.reserve(nConsIn);
-  std::vector<std::pair<int, int>> order;   // (sort key, constraint index)
   int maxViaUnk = 0;
-  for (size_t i = 0; i < nCands; ++i) {
-    const aff_candidate& c = candsIn[i];
-    KCand& kc = H.cands[i];
-    std::memset(&kc, 0, sizeof(kc));
-    if (c.n_tasks > AFFK_MAX_TASKS) { err = "too many tasks in one candidate"; return AFF_ERR_CAPACITY; }
-    kc.first_task = taskBaseOf[i]; kc.n_tasks = c.n_tasks;
-    int xdim = 0;
-    int toff[AFFK_MAX_TASKS + 1];
-    for (int t = 0; t < c.n_tasks; ++t) {
-      KTask& k = H.tasks[kc.first_task + t];
-      k.xoff = xdim; toff[t] = xdim;
-      xdim += (k.kind == AFF_TASK_XYZ) ? 3 : (k.kind == AFF_TASK_POLAR ? 2 : (k.kind == AFF_TASK_JOINTS ? k.n_joints : 1));
-    }
-    toff[c.n_tasks] = xdim;
-    if (xdim > AFFK_MAX_XDIM) { err = "candidate has more than AFFK_MAX_XDIM task dimensions"; return AFF_ERR_CAPACITY; }
-    kc.xdim = xdim;
-    H.maxXdim = std::max(H.maxXdim, xdim);
-    const aff_constraint* cc = consIn + c.first_constraint;
-    double endT = 0.0, startT = 1.0e308;
-    for (int k = 0; k < c.n_constraints; ++k) { if (cc[k].t > endT) endT = cc[k].t; if (cc[k].t < startT) startT = cc[k].t; }
-    kc.end_abs = endT;
-    kc.start_abs = (c.n_constraints == 0) ? 0.0 : (startT < 0.0 ? 0.0 : startT);
-    kc.n_steps = (int)std::lround(endT / opts.dt) + opts.n_after_steps;
-    H.maxSteps = std::max(H.maxSteps, kc.n_steps);
-    // vias by (dimension, time), stable in insertion order
-    kc.first_via = (int)H.vias.size();
-    int unknowns[AFFK_MAX_XDIM];   // per dimension, whole trajectory
-    for (int d = 0; d < xdim; ++d) unknowns[d] = 0;
-    order.clear();
-    for (int k = 0; k < c.n_constraints; ++k) {
-      if (cc[k].kind != AFF_CON_VIA) continue;
-      if (cc[k].task < 0 || cc[k].task >= c.n_tasks || cc[k].dim < 0 || toff[cc[k].task] + cc[k].dim >= toff[cc[k].task + 1]) {
-        err = "via point outside its task"; return AFF_ERR_INVALID;
+  // task row offsets once per shared task slice (the candidates only read them)
+  {
+    std::vector<char> done(H.tasks.size() + 1, 0);
+    for (size_t i = 0; i < nCands; ++i) {
+      const int base = taskBaseOf[i];
+      if (candsIn[i].n_tasks > AFFK_MAX_TASKS) { err = "too many tasks in one candidate"; return AFF_ERR_CAPACITY; }
+      if (candsIn[i].n_tasks == 0 || done[(size_t)base]) continue;
+      done[(size_t)base] = 1;
+      int xdim = 0;
+      for (int t = 0; t < candsIn[i].n_tasks; ++t) {
+        KTask& k = H.tasks[(size_t)base + t];
+        k.xoff = xdim;
+        xdim += (k.kind == AFF_TASK_XYZ) ? 3 : (k.kind == AFF_TASK_POLAR ? 2 : (k.kind == AFF_TASK_JOINTS ? k.n_joints : 1));
       }
-      order.emplace_back(toff[cc[k].task] + cc[k].dim, k);
     }
-    std::stable_sort(order.begin(), order.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
-      if (a.first != b.first) return a.first < b.first;
-      return cc[a.second].t < cc[b.second].t;
-    });
-    {
-      size_t oi = 0;
-      for (int d = 0; d <= xdim; ++d) {
-        kc.via_off[d] = (int)(H.vias.size() - kc.first_via);
-        while (d < xdim && oi < order.size() && order[oi].first == d) {
-          const aff_constraint& v = cc[order[oi].second];
-          KVia kv; kv.t = v.t; kv.x = v.x; kv.xd = v.xd; kv.xdd = v.xdd; kv.flag = v.flag & 7; kv.pad = 0;
-          unknowns[d] += popcount3(kv.flag);
-          H.vias.push_back(kv);
-          ++oi;
+  }
+  // static frames a connect can name get their slot now (slotOfRef appends on first sight: not for the workers)
+  for (size_t k = 0; k < nConsIn; ++k) if (consIn[k].kind == AFF_CON_CONNECT && consIn[k].body_b >= 0 && consIn[k].body_b < nB) (void)slotOfRef(bodyRef[consIn[k].body_b]);
+  // The per-candidate tables are built by a few host threads over contiguous candidate ranges (each into its own
+  // vectors, merged in order afterwards: the result does not depend on the number of threads).
+  struct Local
+  {
+    std::vector<KVia> vias; std::vector<KAct> acts; std::vector<KGraphCon> gcons;
+    std::vector<std::pair<int, int>> order;
+    int maxXdim = 0, maxSteps = 0, maxViaUnk = 0, warpOk = 1, rc = AFF_OK;
+    std::string err;
+  };
+  auto work = [&](size_t lo, size_t hi, Local& L) -> int {
+    for (size_t i = lo; i < hi; ++i) {
+      const aff_candidate& c = candsIn[i];
+      KCand& kc = H.cands[i];
+      std::memset(&kc, 0, sizeof(kc));
+      if (c.n_tasks > AFFK_MAX_TASKS) { L.err = "too many tasks in one candidate"; return AFF_ERR_CAPACITY; }
+      kc.first_task = taskBaseOf[i]; kc.n_tasks = c.n_tasks;
+      int xdim = 0;
+      int toff[AFFK_MAX_TASKS + 1];
+      for (int t = 0; t < c.n_tasks; ++t) {
+        const KTask& k = H.tasks[kc.first_task + t];
+        toff[t] = xdim;      // = k.xoff, set once per shared slice before the workers start
+        xdim += (k.kind == AFF_TASK_XYZ) ? 3 : (k.kind == AFF_TASK_POLAR ? 2 : (k.kind == AFF_TASK_JOINTS ? k.n_joints : 1));
+      }
+      toff[c.n_tasks] = xdim;
+      if (xdim > AFFK_MAX_XDIM) { L.err = "candidate has more than AFFK_MAX_XDIM task dimensions"; return AFF_ERR_CAPACITY; }
+      kc.xdim = xdim;
+      L.maxXdim = std::max(L.maxXdim, xdim);
+      const aff_constraint* cc = consIn + c.first_constraint;
+      double endT = 0.0, startT = 1.0e308;
+      for (int k = 0; k < c.n_constraints; ++k) { if (cc[k].t > endT) endT = cc[k].t; if (cc[k].t < startT) startT = cc[k].t; }
+      kc.end_abs = endT;
+      kc.start_abs = (c.n_constraints == 0) ? 0.0 : (startT < 0.0 ? 0.0 : startT);
+      kc.n_steps = (int)std::lround(endT / opts.dt) + opts.n_after_steps;
+      L.maxSteps = std::max(L.maxSteps, kc.n_steps);
+      // vias by (dimension, time), stable in insertion order
+      kc.first_via = (int)L.vias.size();
+      int unknowns[AFFK_MAX_XDIM];   // per dimension, whole trajectory
+      for (int d = 0; d < xdim; ++d) unknowns[d] = 0;
+      L.order.clear();
+      for (int k = 0; k < c.n_constraints; ++k) {
+        if (cc[k].kind != AFF_CON_VIA) continue;
+        if (cc[k].task < 0 || cc[k].task >= c.n_tasks || cc[k].dim < 0 || toff[cc[k].task] + cc[k].dim >= toff[cc[k].task + 1]) {
+          L.err = "via point outside its task"; return AFF_ERR_INVALID;
+        }
+        L.order.emplace_back(toff[cc[k].task] + cc[k].dim, k);
+      }
+      std::stable_sort(L.order.begin(), L.order.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+        if (a.first != b.first) return a.first < b.first;
+        return cc[a.second].t < cc[b.second].t;
+      });
+      {
+        size_t oi = 0;
+        for (int d = 0; d <= xdim; ++d) {
+          kc.via_off[d] = (int)(L.vias.size() - kc.first_via);
+          while (d < xdim && oi < L.order.size() && L.order[oi].first == d) {
+            const aff_constraint& v = cc[L.order[oi].second];
+            KVia kv; kv.t = v.t; kv.x = v.x; kv.xd = v.xd; kv.xdd = v.xdd; kv.flag = v.flag & 7; kv.pad = 0;
+            unknowns[d] += popcount3(kv.flag);
+            L.vias.push_back(kv);
+            ++oi;
+          }
         }
       }
-    }
-    // Largest window any step can see: with constraint i the next one to come (tnow <= t_i), the
-    // window ends at the first full constraint at least one horizon later (k_via_step).
-    for (int d = 0; d < xdim; ++d) {
-      const KVia* v = H.vias.data() + kc.first_via + kc.via_off[d];
-      const int n = kc.via_off[d + 1] - kc.via_off[d];
-      for (int i = 0; i < n; ++i) {
-        int G = -1, lastFull = -1;
-        for (int j = i; j < n; ++j) if (v[j].flag == 7) { lastFull = j; if (v[j].t - v[i].t >= AFFK_HORIZON) { G = j; break; } }
-        if (G < 0) G = lastFull >= 0 ? lastFull : n - 1;
-        int K = 0;
-        for (int j = i; j <= G; ++j) K += popcount3(v[j].flag);
-        maxViaUnk = std::max(maxViaUnk, K);
-      }
-    }
-    if (maxViaUnk > AFFK_MAX_VIA_UNK) { err = "a trajectory window has more than 12 constrained values"; return AFF_ERR_CAPACITY; }
-    // activations by (task, time)
-    kc.first_act = (int)H.acts.size();
-    order.clear();
-    for (int k = 0; k < c.n_constraints; ++k) {
-      if (cc[k].kind != AFF_CON_ACTIVATION) continue;
-      if (cc[k].task < 0 || cc[k].task >= c.n_tasks) { err = "activation outside the task list"; return AFF_ERR_INVALID; }
-      order.emplace_back(cc[k].task, k);
-    }
-    std::stable_sort(order.begin(), order.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
-      if (a.first != b.first) return a.first < b.first;
-      return cc[a.second].t < cc[b.second].t;
-    });
-    {
-      size_t oi = 0;
-      for (int t = 0; t <= c.n_tasks; ++t) {
-        kc.act_off[t] = (int)(H.acts.size() - kc.first_act);
-        while (t < c.n_tasks && oi < order.size() && order[oi].first == t) {
-          const aff_constraint& a = cc[order[oi].second];
-          KAct ka; ka.t = a.t; ka.horizon = a.horizon; ka.on = a.flag ? 1 : 0; ka.pad = 0;
-          H.acts.push_back(ka);
-          ++oi;
+      // Largest window any step can see: with constraint i the next one to come (tnow <= t_i), the
+      // window ends at the first full constraint at least one horizon later (k_via_step).
+      for (int d = 0; d < xdim; ++d) {
+        const KVia* v = L.vias.data() + kc.first_via + kc.via_off[d];
+        const int n = kc.via_off[d + 1] - kc.via_off[d];
+        for (int i = 0; i < n; ++i) {
+          int G = -1, lastFull = -1;
+          for (int j = i; j < n; ++j) if (v[j].flag == 7) { lastFull = j; if (v[j].t - v[i].t >= AFFK_HORIZON) { G = j; break; } }
+          if (G < 0) G = lastFull >= 0 ? lastFull : n - 1;
+          int K = 0;
+          for (int j = i; j <= G; ++j) K += popcount3(v[j].flag);
+          L.maxViaUnk = std::max(L.maxViaUnk, K);
         }
       }
+      if (L.maxViaUnk > AFFK_MAX_VIA_UNK) { L.err = "a trajectory window has more than 12 constrained values"; return AFF_ERR_CAPACITY; }
+      // activations by (task, time)
+      kc.first_act = (int)L.acts.size();
+      L.order.clear();
+      for (int k = 0; k < c.n_constraints; ++k) {
+        if (cc[k].kind != AFF_CON_ACTIVATION) continue;
+        if (cc[k].task < 0 || cc[k].task >= c.n_tasks) { L.err = "activation outside the task list"; return AFF_ERR_INVALID; }
+        L.order.emplace_back(cc[k].task, k);
+      }
+      std::stable_sort(L.order.begin(), L.order.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+        if (a.first != b.first) return a.first < b.first;
+        return cc[a.second].t < cc[b.second].t;
+      });
+      {
+        size_t oi = 0;
+        for (int t = 0; t <= c.n_tasks; ++t) {
+          kc.act_off[t] = (int)(L.acts.size() - kc.first_act);
+          while (t < c.n_tasks && oi < L.order.size() && L.order[oi].first == t) {
+            const aff_constraint& a = cc[L.order[oi].second];
+            KAct ka; ka.t = a.t; ka.horizon = a.horizon; ka.on = a.flag ? 1 : 0; ka.pad = 0;
+            L.acts.push_back(ka);
+            ++oi;
+          }
+        }
+      }
+      // graph constraints in list order
+      kc.first_gcon = (int)L.gcons.size();
+      for (int k = 0; k < c.n_constraints; ++k) {
+        if (cc[k].kind != AFF_CON_CONNECT && cc[k].kind != AFF_CON_COLLISION) continue;
+        KGraphCon g; g.t = cc[k].t; g.kind = cc[k].kind; g.on = (cc[k].kind == AFF_CON_CONNECT) ? (cc[k].dim == 1 ? 1 : 0) : (cc[k].flag ? 1 : 0); g.slot = objSlotOfBody[cc[k].body_a];
+        g.parent = (cc[k].kind == AFF_CON_CONNECT) ? bodyRef[cc[k].body_b] : AFFK_WORLD;
+        g.parent_slot = (cc[k].kind == AFF_CON_CONNECT) ? slotOfRef(g.parent) : 0;
+        g.parent_tree = -1;
+        if (cc[k].kind == AFF_CON_CONNECT) g.parent_tree = underObj[cc[k].body_b] ? -2 - (underObj[cc[k].body_b] - 1) : treeB[cc[k].body_b];
+        if (cc[k].kind == AFF_CON_CONNECT && cc[k].body_b >= 0 && underObj[cc[k].body_b] == g.slot + 1) { L.err = "connect onto the object's own subtree"; return AFF_ERR_INVALID; }
+        // The warp-per-candidate FK composes an object with its parent's pose of the same step only if the
+        // parent sits in an earlier round of the schedule; a parent in a later round (an object listed before
+        // the robot, or put onto another object's subtree) would be read one step late.  Such batches run on
+        // the thread-per-candidate kernel, whose FK walks objects after everything else.
+        if (cc[k].kind == AFF_CON_CONNECT && g.parent >= 0 && H.roundOf[g.parent] >= H.roundOf[bodyRef[cc[k].body_a]]) L.warpOk = 0;
+        L.gcons.push_back(g);
+      }
+      kc.n_gcon = (int)L.gcons.size() - kc.first_gcon;
+      if (kc.n_gcon > 32) { L.err = "more than 32 graph constraints in one candidate"; return AFF_ERR_CAPACITY; }
+      kc.pose_slot = c.pose_body >= 0 ? objSlotOfBody[c.pose_body] : -1;
+      for (int k = 0; k < 6; ++k) kc.pose_q6[k] = c.pose_q6[k];
     }
-    // graph constraints in list order
-    kc.first_gcon = (int)H.gcons.size();
-    for (int k = 0; k < c.n_constraints; ++k) {
-      if (cc[k].kind != AFF_CON_CONNECT && cc[k].kind != AFF_CON_COLLISION) continue;
-      KGraphCon g; g.t = cc[k].t; g.kind = cc[k].kind; g.on = (cc[k].kind == AFF_CON_CONNECT) ? (cc[k].dim == 1 ? 1 : 0) : (cc[k].flag ? 1 : 0); g.slot = objSlotOfBody[cc[k].body_a];
-      g.parent = (cc[k].kind == AFF_CON_CONNECT) ? bodyRef[cc[k].body_b] : AFFK_WORLD;
-      g.parent_slot = (cc[k].kind == AFF_CON_CONNECT) ? slotOfRef(g.parent) : 0;
-      g.parent_tree = -1;
-      if (cc[k].kind == AFF_CON_CONNECT) g.parent_tree = underObj[cc[k].body_b] ? -2 - (underObj[cc[k].body_b] - 1) : treeB[cc[k].body_b];
-      if (cc[k].kind == AFF_CON_CONNECT && cc[k].body_b >= 0 && underObj[cc[k].body_b] == g.slot + 1) { err = "connect onto the object's own subtree"; return AFF_ERR_INVALID; }
-      // The warp-per-candidate FK composes an object with its parent's pose of the same step only if the
-      // parent sits in an earlier round of the schedule; a parent in a later round (an object listed before
-      // the robot, or put onto another object's subtree) would be read one step late.  Such batches run on
-      // the thread-per-candidate kernel, whose FK walks objects after everything else.
-      if (cc[k].kind == AFF_CON_CONNECT && g.parent >= 0 && H.roundOf[g.parent] >= H.roundOf[bodyRef[cc[k].body_a]]) P.warp_ok = 0;
-      H.gcons.push_back(g);
+    return AFF_OK;
+  };
+  {
+    unsigned nThreads = 1;
+    if (const char* e = getenv("AFF_PLAN_THREADS")) nThreads = (unsigned)std::max(1, atoi(e));
+    else if (nCands >= 8192) nThreads = std::min(4u, std::max(1u, std::thread::hardware_concurrency() / 4));
+    nThreads = (unsigned)std::min<size_t>(nThreads, std::max<size_t>(1, nCands / 1024));
+    std::vector<Local> locals(nThreads);
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nThreads; ++t) {
+      const size_t lo = nCands * t / nThreads, hi = nCands * (t + 1) / nThreads;
+      if (nThreads == 1) locals[0].rc = work(lo, hi, locals[0]);
+      else pool.emplace_back([&, t, lo, hi]() { locals[t].rc = work(lo, hi, locals[t]); });
     }
-    kc.n_gcon = (int)H.gcons.size() - kc.first_gcon;
-    if (kc.n_gcon > 32) { err = "more than 32 graph constraints in one candidate"; return AFF_ERR_CAPACITY; }
-    kc.pose_slot = c.pose_body >= 0 ? objSlotOfBody[c.pose_body] : -1;
-    for (int k = 0; k < 6; ++k) kc.pose_q6[k] = c.pose_q6[k];
+    for (std::thread& th : pool) th.join();
+    for (unsigned t = 0; t < nThreads; ++t) if (locals[t].rc != AFF_OK) { err = locals[t].err; return locals[t].rc; }
+    for (unsigned t = 0; t < nThreads; ++t) {
+      const size_t lo = nCands * t / nThreads, hi = nCands * (t + 1) / nThreads;
+      const int bv = (int)H.vias.size(), ba = (int)H.acts.size(), bg = (int)H.gcons.size();
+      for (size_t i = lo; i < hi; ++i) { H.cands[i].first_via += bv; H.cands[i].first_act += ba; H.cands[i].first_gcon += bg; }
+      H.vias.insert(H.vias.end(), locals[t].vias.begin(), locals[t].vias.end());
+      H.acts.insert(H.acts.end(), locals[t].acts.begin(), locals[t].acts.end());
+      H.gcons.insert(H.gcons.end(), locals[t].gcons.begin(), locals[t].gcons.end());
+      H.maxXdim = std::max(H.maxXdim, locals[t].maxXdim); H.maxSteps = std::max(H.maxSteps, locals[t].maxSteps);
+      maxViaUnk = std::max(maxViaUnk, locals[t].maxViaUnk);
+      if (!locals[t].warpOk) P.warp_ok = 0;
+    }
   }
 
   // ---- scalars

@@ -103,3 +103,19 @@ def test_put_on_the_120_supportable_table(built, sweep):
         ref, _ = ob.predict(scene, b, i, opts)
         (emu,), _ = eb.predict(scene, b, opts, first=i, count=1, sweep=sweep)
         assert emu.as_tuple() == ref.as_tuple()
+
+
+def test_plan_compiler_threads_do_not_change_the_plan(scene, monkeypatch):
+    """The per-candidate tables are built by several host threads over candidate ranges and merged in order:
+    2 100 candidates (two ranges) give the same records as the single-threaded plan."""
+    b = ab.HostBatch(scene)
+    b.add_perturbed("get italian_seasoning_bowl", 2100, seed0=99)
+    opts = ab.default_opts(early_exit=True)      # early exit keeps the 2 x 2 100 CPU rollouts short
+    out = []
+    for th in ("1", "2"):
+        monkeypatch.setenv("AFF_PLAN_THREADS", th)
+        res, _ = eb.predict(scene, b, opts, sweep=True)
+        out.append([r.as_tuple() for r in res])
+    assert out[0] == out[1]
+    ref, _ = ob.predict(scene, b, 2099, opts)
+    assert out[1][2099] == ref.as_tuple()
