@@ -519,7 +519,11 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     }
   }
   // static frames a connect can name get their slot now (slotOfRef appends on first sight: not for the workers)
-  for (size_t k = 0; k < nConsIn; ++k) if (consIn[k].kind == AFF_CON_CONNECT && consIn[k].body_b >= 0 && consIn[k].body_b < nB) (void)slotOfRef(bodyRef[consIn[k].body_b]);
+  for (size_t i = 0; i < nCands; ++i)
+    for (int k = 0; k < candsIn[i].n_constraints; ++k) {
+      const aff_constraint& cc = consIn[candsIn[i].first_constraint + k];
+      if (cc.kind == AFF_CON_CONNECT && cc.body_b >= 0 && cc.body_b < nB) (void)slotOfRef(bodyRef[cc.body_b]);
+    }
   // The per-candidate tables are built by a few host threads over contiguous candidate ranges (each into its own
   // vectors, merged in order afterwards: the result does not depend on the number of threads).
   struct Local
