@@ -79,3 +79,22 @@ def test_compiled_c_client(built):
     out = subprocess.run([exe, ab.PIZZA_SCENE, "get fresh_tomatoes"], check=True, capture_output=True, text=True).stdout
     assert "bodies 455 ik_joints 23 candidates 2" in out
     assert "device present" in out or "no device: status %d" % -2 in out
+
+
+def _build_cpp_client():
+    import subprocess
+    libdir = os.path.join(ab.REPO_ROOT, "affaction_b200")
+    exe = os.path.join(ab.REPO_ROOT, "tests", "cpp_client", "shim_client")
+    inc = ["-I" + os.path.join(ab.REPO_ROOT, d) for d in ("include", "affaction_b200/csrc", "affaction_b200/csrc/host")]
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror"] + inc + [exe + ".cpp", "-o", exe, "-L" + libdir, "-laffhost", "-laffpredict",
+                    "-Wl,-rpath," + libdir], check=True)
+    return exe
+
+
+def test_shim_links_beside_classes_named_like_the_reference(built):
+    """The C++ shim (namespace affgpu) in one binary with classes named aff::ActionBase / aff::ActionScene /
+    aff::TrajectoryPredictor (the reference's names): INTEGRATION.md section 2 as a compiled program."""
+    import subprocess
+    exe = _build_cpp_client()
+    out = subprocess.run([exe, ab.PIZZA_SCENE, "get fresh_tomatoes"], check=True, capture_output=True, text=True).stdout
+    assert out.startswith("solutions 2 tasks ")

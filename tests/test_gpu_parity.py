@@ -541,3 +541,21 @@ def test_compiled_c_client_predicts(scene):
         f = line.split("|")[0].split()
         assert (int(f[0]), int(f[1]), int(f[2]), int(f[3])) == (r.idx, r.success, r.code, r.first_fail_step)
         assert float(f[4]) == r.jl_cost + r.coll_cost
+
+
+def test_cpp_shim_client_predicts(scene):
+    """tests/cpp_client/shim_client.cpp (INTEGRATION.md section 2 as a program, next to classes named like the
+    reference's) through affgpu::TrajectoryPredictor::predictBatch."""
+    import subprocess
+    from test_abi import _build_cpp_client
+    exe = _build_cpp_client()
+    out = subprocess.run([exe, ab.PIZZA_SCENE, "get fresh_tomatoes", "--predict"], check=True, capture_output=True, text=True).stdout
+    rows = [l for l in out.splitlines() if "|" in l]
+    batch = ab.HostBatch(scene)
+    batch.add_action("get fresh_tomatoes")
+    ref = ob.predict_batch(scene, batch, ab.default_opts(), n_threads=2)
+    ranked = [ref[i] for i in ab.rank(ref)]
+    assert len(rows) == 2
+    for line, r in zip(rows, ranked):
+        f = line.split("|")[0].split()
+        assert (int(f[0]), int(f[1])) == (r.idx, r.success) and float(f[2]) == r.jl_cost + r.coll_cost
