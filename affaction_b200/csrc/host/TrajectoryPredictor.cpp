@@ -86,6 +86,8 @@ TrajectoryPredictor::PredictionResult TrajectoryPredictor::convert(const aff_res
     default:
       p.message = "ERROR: unknown predictor code " + std::to_string(r.code);
   }
+  if (r.reserved & AFF_FLAG_LIST_OVERFLOW)
+    p.message += " DEVELOPER: a collision scratch list overflowed during this rollout (more than 32 pairs in contact or 64 AABB-found pairs in one step); collision cost / minimum distance may be incomplete";
   return p;
 }
 

@@ -701,7 +701,7 @@ AFF_DEV bool k_aabb_overlap(const double* A, const double* B, double thr)
 }
 
 // ------------------------------------------------------- collision model
-struct KCollResult { double minDist; int minB1, minB2; double cost; };
+struct KCollResult { double minDist; int minB1, minB2; double cost; int overflow; };
 
 // toggleSlotPlus1: slot+1 if the shape's body IS a re-parentable object (the
 // body a CollisionModelConstraint names), else 0.
@@ -923,6 +923,7 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
       nLive += w_popc(m);
     }
   }
+  const int nearOverflow = nLive > AFFK_MAX_NEAR;
   if (nLive > AFFK_MAX_NEAR) nLive = AFFK_MAX_NEAR;
   // 5. narrow phase over the precompiled, type-sorted shape-pair lists
   KPairAcc acc;
@@ -1022,6 +1023,7 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
   // cost: one term per BODY pair (its closest shape pair), added in ascending (b1, b2) order.
   // Only pairs closer than the threshold contribute, so this loop almost never runs.
   res.cost = 0.0;
+  res.overflow = (nearOverflow || acc.nCostly > 32) ? 1 : 0;
   if (acc.nCostly > 0) {
     w_sync();
     const int n = acc.nCostly < 32 ? acc.nCostly : 32;
@@ -1144,6 +1146,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
 
   KCollResult cm = k_collision(c, DBL_MAX);
   r_minDist = cm.minDist; r_b1 = cm.minB1; r_b2 = cm.minB2;
+  unsigned r_flags = cm.overflow ? AFF_FLAG_LIST_OVERFLOW : 0u;
 
   // check(): checkLimits(jl, coll, speed, 0, 0, 0.01)  (src/TrajectoryPredictor.cpp:426-441)
   {
@@ -1155,7 +1158,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
         aff_result res;
         res.idx = cand; res.success = 0; res.code = AFF_CODE_INITIAL_STATE; res.first_code = AFF_CODE_INITIAL_STATE;
         res.first_fail_step = 0; res.fail_step = 0; res.fail_id0 = -1; res.fail_id1 = -1;
-        res.min_dist_b1 = r_b1; res.min_dist_b2 = r_b2; res.n_steps = 0; res.reserved = 0; res.jmask_bits = 0ull;
+        res.min_dist_b1 = r_b1; res.min_dist_b2 = r_b2; res.n_steps = 0; res.reserved = r_flags; res.jmask_bits = 0ull;
         res.min_dist = r_minDist; res.jl_cost = 0.0; res.coll_cost = 0.0; res.track_err = 0.0;
         P.results[cand] = res;
       }
@@ -1465,6 +1468,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
       // integration, FK, collision model, checkState (:730-752)
       k_fk(c, false);
       cm = k_collision(c, r_minDist > 0.001 ? r_minDist : 0.001);
+      if (cm.overflow) r_flags |= AFF_FLAG_LIST_OVERFLOW;
       const unsigned fast = w_ballot(lane < nJ && jspeed < AFFK_NO_LIMIT && fabs(qd) > jspeed * 1.0);
       const unsigned viol = w_ballot(lane < nJ && (q[lane] < jqmin || q[lane] > jqmax));
       if (fast) ikRes = AFF_CODE_SPEED;
@@ -1517,7 +1521,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
     aff_result res;
     res.idx = cand; res.success = success; res.code = r_code; res.first_code = r_first_code;
     res.first_fail_step = r_first_fail; res.fail_step = r_fail_step; res.fail_id0 = r_id0; res.fail_id1 = r_id1;
-    res.min_dist_b1 = r_b1; res.min_dist_b2 = r_b2; res.n_steps = rows; res.reserved = 0;
+    res.min_dist_b1 = r_b1; res.min_dist_b2 = r_b2; res.n_steps = rows; res.reserved = r_flags;
     res.jmask_bits = (uint64_t)jmaskBits; res.min_dist = r_minDist;
     res.jl_cost = jlSum / (double)rows; res.coll_cost = collSum / (double)rows; res.track_err = err;
     P.results[cand] = res;

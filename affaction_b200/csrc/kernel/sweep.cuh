@@ -288,6 +288,7 @@ AFFT_PHASE void t_collision(TCtx& c, double need, KCollResult* out)
       ++nLive;
     }
   }
+  const int nearOverflow = nLive > AFFK_MAX_NEAR;
   if (nLive > AFFK_MAX_NEAR) nLive = AFFK_MAX_NEAR;
   T_SUBMARK(11);
   // 5. narrow phase
@@ -394,6 +395,7 @@ AFFT_PHASE void t_collision(TCtx& c, double need, KCollResult* out)
   } else { res.minDist = DBL_MAX; res.minB1 = -1; res.minB2 = -1; }
   // cost: one term per body pair (its closest shape pair), in ascending (b1, b2) order
   res.cost = 0.0;
+  res.overflow = (nearOverflow || nCostly > AFFT_MAX_COSTLY) ? 1 : 0;
   if (nCostly > 0) {
     const int n = nCostly < AFFT_MAX_COSTLY ? nCostly : AFFT_MAX_COSTLY;
     for (;;) {
@@ -496,6 +498,7 @@ AFF_DEV void t_rollout(const KPlan& P, int cand, TState& S, bool alive)
   KCollResult cm;
   t_collision(c, DBL_MAX, &cm);
   r_minDist = cm.minDist; r_b1 = cm.minB1; r_b2 = cm.minB2;
+  unsigned r_flags = cm.overflow ? AFF_FLAG_LIST_OVERFLOW : 0u;
 
   // check(): checkLimits(jl, coll, speed, 0, 0, 0.01)  (src/TrajectoryPredictor.cpp:426-441)
   {
@@ -506,7 +509,7 @@ AFF_DEV void t_rollout(const KPlan& P, int cand, TState& S, bool alive)
       aff_result res;
       res.idx = cand; res.success = 0; res.code = AFF_CODE_INITIAL_STATE; res.first_code = AFF_CODE_INITIAL_STATE;
       res.first_fail_step = 0; res.fail_step = 0; res.fail_id0 = -1; res.fail_id1 = -1;
-      res.min_dist_b1 = r_b1; res.min_dist_b2 = r_b2; res.n_steps = 0; res.reserved = 0; res.jmask_bits = 0ull;
+      res.min_dist_b1 = r_b1; res.min_dist_b2 = r_b2; res.n_steps = 0; res.reserved = r_flags; res.jmask_bits = 0ull;
       res.min_dist = r_minDist; res.jl_cost = 0.0; res.coll_cost = 0.0; res.track_err = 0.0;
       if (alive) P.results[cand] = res;
       alive = false;
@@ -856,6 +859,7 @@ AFF_DEV void t_rollout(const KPlan& P, int cand, TState& S, bool alive)
     if (act && !singular) t_collision(c, r_minDist > 0.001 ? r_minDist : 0.001, &cm);           // ======== phase E
     T_SYNCI(5);
     T_MARK(4);
+    if (act && !singular && cm.overflow) r_flags |= AFF_FLAG_LIST_OVERFLOW;
     if (act) {   // ======== phase F: checkState, costs, tracking error
     if (!singular) {
       int viol = 0;
@@ -919,7 +923,7 @@ AFF_DEV void t_rollout(const KPlan& P, int cand, TState& S, bool alive)
   aff_result res;
   res.idx = cand; res.success = success; res.code = r_code; res.first_code = r_first_code;
   res.first_fail_step = r_first_fail; res.fail_step = r_fail_step; res.fail_id0 = r_id0; res.fail_id1 = r_id1;
-  res.min_dist_b1 = r_b1; res.min_dist_b2 = r_b2; res.n_steps = rows; res.reserved = 0;
+  res.min_dist_b1 = r_b1; res.min_dist_b2 = r_b2; res.n_steps = rows; res.reserved = r_flags;
   res.jmask_bits = (uint64_t)jmaskBits; res.min_dist = r_minDist;
   res.jl_cost = jlSum / (double)rows; res.coll_cost = collSum / (double)rows; res.track_err = err;
   P.results[cand] = res;

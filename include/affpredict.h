@@ -138,7 +138,7 @@ typedef struct aff_task_desc {
   int32_t kind;       /* AFF_TASK_*                                              */
   int32_t effector;   /* body id                                                 */
   int32_t ref_body;   /* body id or -1 (world)                                   */
-  int32_t ref_frame;  /* body id or -1 (= ref_body)                              */
+  int32_t ref_frame;  /* body id, -1 (= ref_body), or -2 (= world frame whatever ref_body is) */
   int32_t axis;       /* POLAR / INCLINATION axisDirection: 0,1,2 (default 2)    */
   int32_t n_joints;   /* JOINTS only                                             */
   int32_t joints[AFF_MAX_TASK_JOINTS]; /* joint ids                              */
@@ -189,13 +189,19 @@ typedef struct aff_result {
   int32_t min_dist_b1; /* bodies of the closest pair over the rollout, -1 = NULL */
   int32_t min_dist_b2;
   int32_t n_steps;     /* rows accumulated = nSteps+1 (0 if initial check failed)*/
-  uint32_t reserved;
+  uint32_t reserved;        /* flags: AFF_FLAG_LIST_OVERFLOW */
   uint64_t jmask_bits; /* binarised jMask, bit = jacobi index                    */
   double min_dist;     /* DBL_MAX if no pair was ever tested                     */
   double jl_cost;      /* mean over rows                                         */
   double coll_cost;    /* mean over rows                                         */
   double track_err;    /* running max tracking error while successful            */
 } aff_result;
+
+/* aff_result.reserved, bit 0: in some step a scratch list of the collision model overflowed (more than 32
+ * body pairs closer than DistanceThreshold, or more than 64 body pairs found by the AABB test): the entries
+ * beyond the capacity were dropped, so coll_cost / min_dist of this candidate may be incomplete.  Never seen
+ * in the shipped scenes; reported instead of truncating silently. */
+#define AFF_FLAG_LIST_OVERFLOW 1u
 
 typedef struct aff_opts {
   double dt;            /* 0.01 in every reference call site                     */
