@@ -451,8 +451,9 @@ class DeviceBatch:
 
     @property
     def kernel(self):
-        """'sweep' (one rollout per thread) or 'warp' (one rollout per warp)."""
-        return "sweep" if lib().aff_batch_kernel_kind(self.h) else "warp"
+        """'cta' (one rollout per block: a handful of candidates), 'warp' (one rollout per warp) or
+        'sweep' (one rollout per thread)."""
+        return ("warp", "sweep", "cta")[lib().aff_batch_kernel_kind(self.h)]
 
 
 def predict_batch(scene, batch, opts=None, device=0):

@@ -80,6 +80,38 @@ __global__ void __launch_bounds__(32) aff_prologue_kernel(const KPlan P)
 AFF_ROLLOUT_KERNEL(aff_rollout_kernel, kfixed)            // batches in the fixed layout (KPlan::fixed_layout)
 AFF_ROLLOUT_KERNEL(aff_rollout_kernel_generic, kgeneric)  // anything larger
 
+// Block-per-candidate kernel for batches far below one wave (the call sites that check a handful of
+// candidates, or one trajectory): warp 0 walks the step loop, AFFC_WORKERS warps evaluate the collision
+// model of the finished steps on private copies of the frames, a few steps behind (k_rollout_t<1>,
+// k_cta_worker in rollout.cuh).  One warp per scheduler; the rollout is a dependent chain, so the time
+// of a step is what counts here, not the work per SM.
+#ifndef AFF_CTA_BLOCKS_PER_SM
+#define AFF_CTA_BLOCKS_PER_SM 2     // 255 registers per thread: the step loop without spills
+#endif
+#define AFF_CTA_THREADS (32 * (1 + AFFC_WORKERS))
+#define AFF_CTA_KERNEL(NAME, NS)                                                                                         \
+  __global__ void __launch_bounds__(AFF_CTA_THREADS, AFF_CTA_BLOCKS_PER_SM) NAME(const KPlan P)                          \
+  {                                                                                                                      \
+    extern __shared__ double smem[];                                                                                     \
+    const int warp = threadIdx.x >> 5;                                                                                   \
+    unsigned smAddr = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)warp * (unsigned)P.warp_doubles * 8u;        \
+    asm volatile("" : "+r"(smAddr));                                                                                    \
+    double* sm = (double*)__cvta_shared_to_generic((size_t)smAddr);                                                      \
+    NS::KCtaShared* X = (NS::KCtaShared*)(smem + (size_t)(1 + AFFC_WORKERS) * P.warp_doubles);                           \
+    for (int cand = blockIdx.x; cand < P.nCands; cand += gridDim.x) {                                                    \
+      if (threadIdx.x == 0) {                                                                                            \
+        X->fkSeq = 0; X->stop = 0;                                                                                       \
+        for (int w = 0; w < AFFC_WORKERS; ++w) { X->copied[w] = 0; X->done[w] = 0; }                                     \
+      }                                                                                                                  \
+      __syncthreads();                                                                                                   \
+      if (warp == 0) NS::template k_rollout_t<1>(P, cand, sm, X);                                                        \
+      else NS::k_cta_worker(P, cand, sm, smem + P.o_node, X, warp);                                                      \
+      __syncthreads();                                                                                                   \
+    }                                                                                                                    \
+  }
+AFF_CTA_KERNEL(aff_rollout_cta_kernel, kfixed)
+AFF_CTA_KERNEL(aff_rollout_cta_kernel_generic, kgeneric)
+
 // Thread-per-candidate kernel (sweep.cuh): 32 rollouts per warp.  Persistent blocks: block b takes the
 // chunks b, b + gridDim, ... of THREADS consecutive entries of sweep_order (candidates grouped by
 // structure), and its warps walk the step loop in lock-step phases (T_SYNC in sweep.cuh).  THREADS x
@@ -159,7 +191,8 @@ struct aff_batch
   DevBuf<aff_result> results;
   int grid = 0; size_t smemBytes = 0; int launches = 0;
   size_t h2dBytes = 0;
-  bool prologueDone = false, useFixed = false, useSweep = false;
+  bool prologueDone = false, useFixed = false, useSweep = false, useCta = false;
+  int ctaGrid = 0; size_t ctaSmemBytes = 0;
   int sweepGrid = 0, sweepThreads = 512;
   cudaStream_t lastStream = nullptr; bool launched = false;
   void release()
@@ -334,6 +367,35 @@ int aff_batch_create(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, c
   if (perSM < 1) perSM = 1;
   const int blocksNeeded = (int)((n_cands + AFF_WARPS_PER_BLOCK - 1) / AFF_WARPS_PER_BLOCK);
   b->grid = std::max(1, std::min(blocksNeeded, perSM * s->smCount));
+  // block-per-candidate kernel: batches of at most AFF_CTA_MAX candidates (default: what one wave of
+  // its blocks holds); AFF_KERNEL=cta forces it, AFF_KERNEL=warp / sweep rule it out
+  {
+    const char* force = getenv("AFF_KERNEL");
+    b->ctaSmemBytes = b->host.smemBytesPerWarp * (1 + AFFC_WORKERS) + sizeof(kgeneric::KCtaShared);
+    const void* cfn = b->useFixed ? (const void*)aff_rollout_cta_kernel : (const void*)aff_rollout_cta_kernel_generic;
+    const bool fits = b->plan.warp_ok && b->ctaSmemBytes <= (size_t)s->smemOptin;
+    int perSMc = 0;
+    if (fits) {
+      static std::mutex mtx;
+      static size_t raised[64][2] = {};
+      std::lock_guard<std::mutex> lock(mtx);
+      size_t& cur = raised[s->device & 63][b->useFixed ? 0 : 1];
+      if (b->ctaSmemBytes > cur) {
+        CUDA_TRY(cudaFuncSetAttribute(cfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->ctaSmemBytes));
+        cur = b->ctaSmemBytes;
+      }
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSMc, cfn, AFF_CTA_THREADS, b->ctaSmemBytes));
+    }
+    const char* mx = getenv("AFF_CTA_MAX");
+    const size_t ctaMax = mx ? (size_t)atoll(mx) : (size_t)std::max(perSMc, 0) * (size_t)s->smCount;
+    b->useCta = fits && perSMc >= 1 && !b->useSweep && n_cands <= ctaMax;
+    if (force && !strcmp(force, "warp")) b->useCta = false;
+    if (force && !strcmp(force, "cta")) {
+      if (!fits || perSMc < 1) return fail(AFF_ERR_CAPACITY, "aff_batch_create: AFF_KERNEL=cta but the batch does not fit the block-per-candidate kernel");
+      b->useCta = true; b->useSweep = false;
+    }
+    b->ctaGrid = (int)std::max<size_t>(1, std::min(n_cands, (size_t)std::max(perSMc, 1) * (size_t)s->smCount));
+  }
   CUDA_TRY(cudaStreamSynchronize(0));
   *out = owner.release();
   return AFF_OK;
@@ -361,7 +423,11 @@ int aff_batch_launch(aff_batch* b, void* stream)
     b->prologueDone = true;
     b->launches++;
   }
-  if (b->useSweep) {
+  if (b->useCta) {
+    if (b->useFixed) aff_rollout_cta_kernel<<<b->ctaGrid, AFF_CTA_THREADS, b->ctaSmemBytes, st>>>(b->plan);
+    else aff_rollout_cta_kernel_generic<<<b->ctaGrid, AFF_CTA_THREADS, b->ctaSmemBytes, st>>>(b->plan);
+  }
+  else if (b->useSweep) {
     if (b->sweepThreads == 512) aff_sweep_kernel<512><<<b->sweepGrid, 512, 0, st>>>(b->plan);
     else if (b->sweepThreads == 256) aff_sweep_kernel<256><<<b->sweepGrid, 256, 0, st>>>(b->plan);
     else aff_sweep_kernel<128><<<b->sweepGrid, 128, 0, st>>>(b->plan);
@@ -396,8 +462,8 @@ int aff_batch_last_launch_count(const aff_batch* b) { return b ? b->launches : 0
 int aff_batch_num_steps(const aff_batch* b, size_t cand) { return (b && cand < b->host.cands.size()) ? b->host.cands[cand].n_steps : -1; }
 size_t aff_batch_h2d_bytes(const aff_batch* b) { return b ? b->h2dBytes : 0; }
 size_t aff_batch_smem_bytes_per_warp(const aff_batch* b) { return b ? b->host.smemBytesPerWarp : 0; }
-int aff_batch_grid_blocks(const aff_batch* b) { return b ? (b->useSweep ? b->sweepGrid : b->grid) : 0; }
-int aff_batch_kernel_kind(const aff_batch* b) { return (b && b->useSweep) ? 1 : 0; }
+int aff_batch_grid_blocks(const aff_batch* b) { return b ? (b->useCta ? b->ctaGrid : (b->useSweep ? b->sweepGrid : b->grid)) : 0; }
+int aff_batch_kernel_kind(const aff_batch* b) { return !b ? 0 : (b->useCta ? 2 : (b->useSweep ? 1 : 0)); }
 
 int aff_batch_fetch_q(aff_batch* b, size_t cand, double* out, size_t max_rows)
 {

@@ -1042,7 +1042,28 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
 }
 
 // ----------------------------------------------------------- the rollout
-AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
+// Control block of the block-per-candidate kernel (cta.cuh), in shared memory: warp 0 walks the step
+// loop, the other warps evaluate the collision model of the steps it has finished, a few steps behind.
+#define AFFC_WORKERS 3
+#define AFFC_RING 4
+struct KCtaShared
+{
+  int fkSeq;                 // number of steps whose frames are final in warp 0's node array
+  int stop;                  // warp 0 has left the step loop
+  int copied[AFFC_WORKERS];  // per worker: steps whose frames it has taken over
+  int done[AFFC_WORKERS];    // per worker: steps whose result is posted
+  int objState[4];           // objMode0, objMode1, objTree0, objTree1 of the posted step
+  double need;               // running minimum distance (a stale, larger value only costs work)
+  KCollResult res[AFFC_RING];
+  // bookkeeping of steps whose collision result has not arrived yet
+  int pendIk[AFFC_RING], pendId0[AFFC_RING], pendEk[AFFC_RING];
+  double pendEv[AFFC_RING];
+};
+
+// CTA = 0: the warp does everything (one rollout per warp).  CTA = 1: warp 0 of a block-per-candidate
+// launch; the collision model of step k is evaluated by a worker warp and folded into the verdict
+// `lag` steps later.  The rollout itself never reads a collision result, so both orders give the same record.
+template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm, KCtaShared* X)
 {
   KCtx c;
   c.P = &P; c.C = P.cands + cand; c.sm = sm; c.lane = w_lane();
@@ -1162,6 +1183,7 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
         res.min_dist = r_minDist; res.jl_cost = 0.0; res.coll_cost = 0.0; res.track_err = 0.0;
         P.results[cand] = res;
       }
+      if (CTA) w_post(&X->stop, 1);
       return;
     }
   }
@@ -1178,6 +1200,32 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
   const double motionDuration = endAbs - ldg(&C.start_abs);
   const double alpha = P.opts.alpha, lambda = P.opts.lambda, qFiltDecay = P.opts.q_filt_decay;
   int success = 1, rows = 1;
+  double errOpt = 0.0;     // running maximum of the tracking error over all steps (err: over the steps before the first failure)
+  const int lag = CTA ? (P.opts.early_exit ? 0 : AFFC_WORKERS - 1) : 0;
+  if (CTA) { if (lane == 0) X->need = r_minDist; }
+
+  // checkState + bookkeeping of step j (:730-752, :297-337), once its collision result is known.  pIk / pId0: the
+  // failure the step found before looking at collisions; pEv / pEk: its tracking error if that grew, else -1.
+  auto fold = [&](int j, const KCollResult& cmv, int pIk, int pId0, double pEv, int pEk) {
+    int ikRes = pIk, id0 = pId0, id1 = -1;
+    if (ikRes == 0 && cmv.minB1 >= 0 && cmv.minDist < 0.001) { ikRes = AFF_CODE_COLLISION; id0 = cmv.minB1; id1 = cmv.minB2; }
+    if (ikRes != 0) {
+      if (success) { r_first_code = ikRes; r_first_fail = j; }
+      success = 0; r_code = ikRes; r_fail_step = j; r_id0 = id0; r_id1 = id1;
+    }
+    if (cmv.overflow) r_flags |= AFF_FLAG_LIST_OVERFLOW;
+    collSum = collSum + cmv.cost;
+    if (success && pEv > err) {
+      err = pEv;
+      if (err > AFFK_TRACK_MAX) {
+        int etask = -1, edim = -1;
+        for (int t = 0; t < nTasks; ++t) if (pEk >= c.tdesc[8 * t + TD_XOFF]) { etask = t; edim = pEk - c.tdesc[8 * t + TD_XOFF]; }
+        success = 0; r_code = AFF_CODE_TRACKING; r_first_code = AFF_CODE_TRACKING;
+        r_first_fail = j; r_fail_step = j; r_id0 = etask; r_id1 = edim;
+      }
+    }
+    if (cmv.minDist < r_minDist) { r_minDist = cmv.minDist; r_b1 = cmv.minB1; r_b2 = cmv.minB2; }
+  };
 
   for (int iter = 0; iter < nSteps; ++iter) {
     const int successPrev = success;
@@ -1418,7 +1466,9 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
       else if (lane > j && lane < m) L[lane * LS + j] = t * inv;
       w_sync();
     }
-    int ikRes = 0, id0 = -1, id1 = -1;
+    int ikRes = 0, id0 = -1;      // failure of this step, collisions aside
+    // block-per-candidate: the worker of the previous step has taken that step's frames and object state
+    if (CTA) { if (iter > 0) w_wait_ge(&X->copied[(iter - 1) % AFFC_WORKERS], iter); }
     if (singular) {
       ikRes = AFF_CODE_SINGULAR;
     } else {
@@ -1467,17 +1517,17 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
       w_sync();
       // integration, FK, collision model, checkState (:730-752)
       k_fk(c, false);
-      cm = k_collision(c, r_minDist > 0.001 ? r_minDist : 0.001);
-      if (cm.overflow) r_flags |= AFF_FLAG_LIST_OVERFLOW;
+      if (!CTA) cm = k_collision(c, r_minDist > 0.001 ? r_minDist : 0.001);
       const unsigned fast = w_ballot(lane < nJ && jspeed < AFFK_NO_LIMIT && fabs(qd) > jspeed * 1.0);
       const unsigned viol = w_ballot(lane < nJ && (q[lane] < jqmin || q[lane] > jqmax));
       if (fast) ikRes = AFF_CODE_SPEED;
       else if (viol) { ikRes = AFF_CODE_JOINT_LIMIT; id0 = w_popc(viol); }
-      else if (cm.minB1 >= 0 && cm.minDist < 0.001) { ikRes = AFF_CODE_COLLISION; id0 = cm.minB1; id1 = cm.minB2; }
     }
-    if (ikRes != 0) {
-      if (success) { r_first_code = ikRes; r_first_fail = iter; }
-      success = 0; r_code = ikRes; r_fail_step = iter; r_id0 = id0; r_id1 = id1;
+    if (CTA) {
+      // hand the step to its worker (a singular step leaves the frames as they were: the worker finds what
+      // the single-warp kernel keeps from the step before)
+      if (lane == 0) { X->objState[0] = c.objMode0; X->objState[1] = c.objMode1; X->objState[2] = c.objTree0; X->objState[3] = c.objTree1; }
+      w_post(&X->fkSeq, iter + 1);
     }
     // ---- costs (:226-227)
     {
@@ -1489,33 +1539,51 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
         term = (0.5 * jwjl) * (u * u);
       }
       jlSum = jlSum + w_tree_sum(term);
-      collSum = collSum + cm.cost;
     }
     // ---- geometry of the new state; tracking error (:297-337)
     if (lane < nTasks) k_task_geo(c, c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur);
     w_sync();
-    if (success) {
+    double pEv = -1.0; int pEk = 0;
+    if (success && ikRes == 0) {       // (a step that has failed already does not look at the tracking error)
       double* dxe = dxv;   // stacked over all dims here
       if (lane < nTasks && ((activeMask >> lane) & 1u)) k_task_dx(c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur, xdes, dxe + c.tdesc[8 * lane + TD_XOFF]);
       w_sync();
       double ev = -1.0; int ek = 0x7fffffff;
       if (lane < xdim && ((activeMask >> myTask) & 1u)) { ev = fabs(dxe[lane]); ek = lane; }
-      if (w_ballot(ev > err)) {        // the running maximum grows
+      if (w_ballot(ev > errOpt)) {        // the running maximum grows
         w_max_keyed(ev, ek);
-        err = ev;
-        if (err > AFFK_TRACK_MAX) {
-          int etask = -1, edim = -1;
-          for (int t = 0; t < nTasks; ++t) if (ek >= c.tdesc[8 * t + TD_XOFF]) { etask = t; edim = ek - c.tdesc[8 * t + TD_XOFF]; }
-          success = 0; r_code = AFF_CODE_TRACKING; r_first_code = AFF_CODE_TRACKING;
-          r_first_fail = iter; r_fail_step = iter; r_id0 = etask; r_id1 = edim;
-        }
+        errOpt = ev; pEv = ev; pEk = ek;
       }
       w_sync();
     }
-    if (cm.minDist < r_minDist) { r_minDist = cm.minDist; r_b1 = cm.minB1; r_b2 = cm.minB2; }
+    if (!CTA) fold(iter, cm, ikRes, id0, pEv, pEk);
+    else {
+      const int slot = iter & (AFFC_RING - 1);
+      if (lane == 0) { X->pendIk[slot] = ikRes; X->pendId0[slot] = id0; X->pendEv[slot] = pEv; X->pendEk[slot] = pEk; }
+      w_sync();
+      const int j = iter - lag;
+      if (j >= 0) {
+        w_wait_ge(&X->done[j % AFFC_WORKERS], j + 1);
+        const int sj = j & (AFFC_RING - 1);
+        const KCollResult cj = X->res[sj];
+        fold(j, cj, X->pendIk[sj], X->pendId0[sj], X->pendEv[sj], X->pendEk[sj]);
+        if (lane == 0) X->need = r_minDist;
+      }
+    }
     if (qlog && lane < nJ && rows < qrows) qlog[(size_t)rows * nJ + lane] = q[lane];
     rows++;
     if (P.opts.early_exit && !success && successPrev) break;     // opt-in: the reference's commented-out break (:368-373)
+  }
+  if (CTA) {
+    // the steps still in flight
+    const int stepsDone = rows - 1;
+    for (int j = (stepsDone > lag ? stepsDone - lag : 0); j < stepsDone; ++j) {
+      w_wait_ge(&X->done[j % AFFC_WORKERS], j + 1);
+      const int sj = j & (AFFC_RING - 1);
+      const KCollResult cj = X->res[sj];
+      fold(j, cj, X->pendIk[sj], X->pendId0[sj], X->pendEv[sj], X->pendEk[sj]);
+    }
+    w_post(&X->stop, 1);
   }
   if (lane == 0) {
     aff_result res;
@@ -1525,6 +1593,35 @@ AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm)
     res.jmask_bits = (uint64_t)jmaskBits; res.min_dist = r_minDist;
     res.jl_cost = jlSum / (double)rows; res.coll_cost = collSum / (double)rows; res.track_err = err;
     P.results[cand] = res;
+  }
+}
+
+AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm) { k_rollout_t<0>(P, cand, sm, nullptr); }
+
+// Worker warp w (1 .. AFFC_WORKERS) of a block-per-candidate launch: the collision model of the steps
+// k = w - 1, w - 1 + AFFC_WORKERS, ... on a private copy of the frames (its own slab: same layout as warp 0's).
+AFF_DEV void k_cta_worker(const KPlan& P, int cand, double* sm, const double* nodes0, KCtaShared* X, int w)
+{
+  KCtx c;
+  c.P = &P; c.C = P.cands + cand; c.sm = sm; c.lane = w_lane();
+  c.nodes = sm + P.o_node;
+  c.chain = (unsigned*)(sm + AFFK_O(P, chain));
+  c.tdesc = (int*)(sm + AFFK_O(P, tdesc));
+  c.objHasRel = 0u;
+  c.objParentSlot0 = c.objParentSlot1 = 0; c.objParentDynamic0 = c.objParentDynamic1 = 0; c.objChain0 = c.objChain1 = 0u;
+  c.objTree0 = c.objTree1 = -1; c.objMode0 = c.objMode1 = 0;
+  const int lane = c.lane;
+  const int nEl = 12 * (P.nDyn + P.nStatPar);
+  const int nSteps = ldg(&c.C->n_steps);
+  for (int k = w - 1; k < nSteps; k += AFFC_WORKERS) {
+    if (w_wait_ge_or(&X->fkSeq, k + 1, &X->stop)) return;
+    for (int i = lane; i < nEl; i += 32) c.nodes[i] = nodes0[i];
+    c.objMode0 = X->objState[0]; c.objMode1 = X->objState[1]; c.objTree0 = X->objState[2]; c.objTree1 = X->objState[3];
+    w_post(&X->copied[w - 1], k + 1);
+    const double run = c_ld(&X->need);
+    const KCollResult cm = k_collision(c, run > 0.001 ? run : 0.001);
+    if (lane == 0) X->res[k & (AFFC_RING - 1)] = cm;
+    w_post(&X->done[w - 1], k + 1);
   }
 }
 #undef viaEnd

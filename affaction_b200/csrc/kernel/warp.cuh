@@ -25,6 +25,19 @@ template <class T> static inline T ldg_fk(const T* p) { return *p; }
 static inline double ldg_here(const double* p) { return *p; }
 static inline int w_popc(unsigned v) { return __builtin_popcount(v); }
 static inline int w_ffs(unsigned v) { return __builtin_ffs((int)v); }
+// between the warps of a block (the emulator runs every lane of every warp as a fiber): the waits leave
+// the loop for all lanes of a warp in the same scheduler round, so its barriers stay aligned
+static inline double c_ld(const double* p) { return *p; }   // fibers switch only at yields
+static inline void w_wait_ge(const int* flag, int v) { while (w_ballot(*(const volatile int*)flag >= v) != 0xffffffffu) {} }
+static inline bool w_wait_ge_or(const int* flag, int v, const int* stop)
+{
+  for (;;) {
+    const int s = *(const volatile int*)stop;
+    if (w_ballot(*(const volatile int*)flag >= v) == 0xffffffffu) return false;
+    if (w_ballot(s) == 0xffffffffu) return true;
+  }
+}
+static inline void w_post(int* flag, int v) { w_sync(); if (w_lane() == 0) *(volatile int*)flag = v; }
 
 #else
 
@@ -65,6 +78,28 @@ template <class T> AFF_DEV T ldg_fk(const T* p)
 }
 AFF_DEV int w_popc(unsigned v) { return __popc(v); }
 AFF_DEV int w_ffs(unsigned v) { return __ffs((int)v); }
+// Flags between the warps of one block (shared memory).  w_post: everything the warp wrote before is
+// visible to a warp that has seen the flag.  The lanes of a waiting warp read the same word, so they
+// leave the loop together.
+AFF_DEV double c_ld(const double* p) { return *(const volatile double*)p; }
+AFF_DEV void w_wait_ge(const int* flag, int v)
+{
+  while (!__all_sync(0xffffffffu, *(const volatile int*)flag >= v)) {}
+  __threadfence_block();
+}
+AFF_DEV bool w_wait_ge_or(const int* flag, int v, const int* stop)
+{
+  for (;;) {
+    const int s = *(const volatile int*)stop;      // read first: a posted step is served even if stop follows it
+    if (__all_sync(0xffffffffu, *(const volatile int*)flag >= v)) { __threadfence_block(); return false; }
+    if (__all_sync(0xffffffffu, s != 0)) return true;
+  }
+}
+AFF_DEV void w_post(int* flag, int v)
+{
+  __syncwarp();
+  if ((threadIdx.x & 31u) == 0u) { __threadfence_block(); *(volatile int*)flag = v; }
+}
 
 #endif
 

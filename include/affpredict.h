@@ -297,8 +297,10 @@ int aff_predict_batch_multi(const aff_scene_desc* scene, const int* devices, int
                             const aff_candidate* cands, size_t n_cands,
                             const aff_opts* opts, aff_result* out);
 
-/* Which kernel a batch runs on: 0 = one rollout per warp (small batches),
- * 1 = one rollout per thread (sweeps). */
+/* Which kernel a batch runs on: 0 = one rollout per warp (mid-size batches),
+ * 1 = one rollout per thread (sweeps), 2 = one rollout per block (a handful of
+ * candidates, one trajectory re-check); see DESIGN.md section 4.  The records
+ * are the same bit for bit whichever runs. */
 int aff_batch_kernel_kind(const aff_batch* b);
 
 /* Argsort of results with PredictionResult::lesser (success first, then

@@ -21,26 +21,32 @@
 
 #include "kernel/plan_build.h"
 
-static ucontext_t g_main, g_ctx[32];
+// up to EMU_WARPS warps of one block: fiber f = 32 * warp + lane.  Every fiber advances to its next
+// yield once per scheduler round, so the lanes of a warp stay aligned at their barriers, and flags
+// written by another warp are seen a round later at the latest.
+#define EMU_WARPS 4
+static ucontext_t g_main, g_ctx[32 * EMU_WARPS];
 static int g_cur = 0;
-static bool g_done[32];
+static bool g_done[32 * EMU_WARPS];
 static std::function<void()>* g_body = nullptr;
-static double g_xd[32];
-static int g_xi[32];
+static double g_xd[32 * EMU_WARPS];
+static int g_xi[32 * EMU_WARPS];
 static std::vector<char> g_stacks;
 
-int w_lane() { return g_cur; }
+int w_lane() { return g_cur & 31; }
+static int emu_warp() { return g_cur >> 5; }
 void w_sync() { swapcontext(&g_ctx[g_cur], &g_main); }
-double w_shfl(double v, int src) { g_xd[g_cur] = v; w_sync(); const double r = g_xd[src & 31]; w_sync(); return r; }
-int w_shfl(int v, int src) { g_xi[g_cur] = v; w_sync(); const int r = g_xi[src & 31]; w_sync(); return r; }
-double w_shfl_xor(double v, int mask) { return w_shfl(v, g_cur ^ mask); }
-int w_shfl_xor(int v, int mask) { return w_shfl(v, g_cur ^ mask); }
+double w_shfl(double v, int src) { g_xd[g_cur] = v; w_sync(); const double r = g_xd[(g_cur & ~31) | (src & 31)]; w_sync(); return r; }
+int w_shfl(int v, int src) { g_xi[g_cur] = v; w_sync(); const int r = g_xi[(g_cur & ~31) | (src & 31)]; w_sync(); return r; }
+double w_shfl_xor(double v, int mask) { return w_shfl(v, (g_cur & 31) ^ mask); }
+int w_shfl_xor(int v, int mask) { return w_shfl(v, (g_cur & 31) ^ mask); }
 unsigned w_ballot(int pred)
 {
   g_xi[g_cur] = pred ? 1 : 0;
   w_sync();
   unsigned m = 0u;
-  for (int i = 0; i < 32; ++i) if (g_xi[i]) m |= 1u << i;
+  const int base = g_cur & ~31;
+  for (int i = 0; i < 32; ++i) if (g_xi[base + i]) m |= 1u << i;
   w_sync();
   return m;
 }
@@ -55,12 +61,16 @@ static void fiberEntry()
   swapcontext(&g_ctx[g_cur], &g_main);
 }
 
-static void runWarp(std::function<void()> body)
+static void runBlock(int nWarps, std::function<void()> body);
+static void runWarp(std::function<void()> body) { runBlock(1, body); }
+
+static void runBlock(int nWarps, std::function<void()> body)
 {
   const size_t stackSize = 512 * 1024;
-  if (g_stacks.size() < 32 * stackSize) g_stacks.resize(32 * stackSize);
+  const int nFib = 32 * nWarps;
+  if (g_stacks.size() < nFib * stackSize) g_stacks.resize(nFib * stackSize);
   g_body = &body;
-  for (int l = 0; l < 32; ++l) {
+  for (int l = 0; l < nFib; ++l) {
     g_done[l] = false;
     getcontext(&g_ctx[l]);
     g_ctx[l].uc_stack.ss_sp = g_stacks.data() + l * stackSize;
@@ -71,7 +81,7 @@ static void runWarp(std::function<void()> body)
   bool any = true;
   while (any) {
     any = false;
-    for (int l = 0; l < 32; ++l) {
+    for (int l = 0; l < nFib; ++l) {
       if (g_done[l]) continue;
       g_cur = l;
       swapcontext(&g_main, &g_ctx[l]);
@@ -126,6 +136,23 @@ static int emu_run(int sweep, const aff_scene_desc* scene, const aff_task_desc* 
     for (size_t i = 0; i < nCands; ++i) out[i] = results[i];
     return AFF_OK;
   }
+  if (sweep == 3) {
+    // block-per-candidate kernel: warp 0 = step loop, warps 1 .. AFFC_WORKERS = collision model
+    std::vector<double> sm((size_t)P.warp_doubles * (1 + AFFC_WORKERS) + 64);
+    for (size_t i = 0; i < nCands; ++i) {
+      std::fill(sm.begin(), sm.end(), 0.0);
+      KCtaShared X;
+      std::memset(&X, 0, sizeof(X));
+      runBlock(1 + AFFC_WORKERS, [&]() {
+        const int w = emu_warp();
+        double* slab = sm.data() + (size_t)w * P.warp_doubles;
+        if (w == 0) k_rollout_t<1>(P, (int)i, slab, &X);
+        else k_cta_worker(P, (int)i, slab, sm.data() + P.o_node, &X, w);
+      });
+      out[i] = results[i];
+    }
+    return AFF_OK;
+  }
   std::vector<double> sm((size_t)P.warp_doubles + 64);
   for (size_t i = 0; i < nCands; ++i) {
     std::fill(sm.begin(), sm.end(), 0.0);
@@ -143,6 +170,14 @@ extern "C" int emu_predict_batch(const aff_scene_desc* scene, const aff_task_des
                                  const aff_opts* opts, aff_result* out, double* qlog, size_t qlogRows, char* errbuf, size_t errlen)
 {
   return emu_run(0, scene, tasks, nTasks, cons, nCons, cands, nCands, opts, out, qlog, qlogRows, errbuf, errlen);
+}
+
+// the block-per-candidate arrangement (warp 0 + collision workers) on the CPU
+extern "C" int emu_predict_batch_cta(const aff_scene_desc* scene, const aff_task_desc* tasks, size_t nTasks,
+                                     const aff_constraint* cons, size_t nCons, const aff_candidate* cands, size_t nCands,
+                                     const aff_opts* opts, aff_result* out, double* qlog, size_t qlogRows, char* errbuf, size_t errlen)
+{
+  return emu_run(3, scene, tasks, nTasks, cons, nCons, cands, nCands, opts, out, qlog, qlogRows, errbuf, errlen);
 }
 
 // the thread-per-candidate kernel source (sweep.cuh) on the CPU

@@ -23,6 +23,8 @@ def emu_lib():
         _lib.emu_predict_batch.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, vp, vp, sz, vp, sz]
         _lib.emu_predict_batch_sweep.restype = C.c_int
         _lib.emu_predict_batch_sweep.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, vp, vp, sz, vp, sz]
+        _lib.emu_predict_batch_cta.restype = C.c_int
+        _lib.emu_predict_batch_cta.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, vp, vp, sz, vp, sz]
         _lib.emu_count_flops.restype = C.c_int
         _lib.emu_count_flops.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp, sz]
     return _lib
@@ -30,7 +32,8 @@ def emu_lib():
 
 def predict(scene, batch, opts, first=0, count=None, log_q=False, n_steps=None, sweep=False):
     """Run candidates [first, first+count) through the emulated kernel (sweep=True: the
-    thread-per-candidate kernel source, sweep.cuh; else the warp-per-candidate one)."""
+    thread-per-candidate kernel source, sweep.cuh; sweep="cta": the block-per-candidate arrangement,
+    warp 0 + collision worker warps; else the warp-per-candidate one)."""
     n = batch.n_candidates - first if count is None else count
     res = (Result * n)()
     q = None
@@ -39,7 +42,8 @@ def predict(scene, batch, opts, first=0, count=None, log_q=False, n_steps=None, 
         rows = n_steps + 1
         q = np.zeros((n, rows, scene.nJ))
     err = C.create_string_buffer(512)
-    fn = emu_lib().emu_predict_batch_sweep if sweep else emu_lib().emu_predict_batch
+    fn = (emu_lib().emu_predict_batch_cta if sweep == "cta"
+          else emu_lib().emu_predict_batch_sweep if sweep else emu_lib().emu_predict_batch)
     rc = fn(scene.desc, batch.tasks_ptr, batch.n_tasks, batch.constraints_ptr, batch.n_constraints,
                                      batch.candidate_ptr(first), n, C.byref(opts), res,
                                      q.ctypes.data_as(C.c_void_p) if q is not None else None, rows, err, 512)

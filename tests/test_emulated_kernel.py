@@ -15,9 +15,10 @@ def scene(built):
     return ab.HostScene()
 
 
-@pytest.fixture(params=[False, True], ids=["warp", "sweep"])
+@pytest.fixture(params=[False, True, "cta"], ids=["warp", "sweep", "cta"])
 def sweep(request):
-    """False: rollout.cuh (one rollout per warp); True: sweep.cuh (one rollout per thread)."""
+    """False: rollout.cuh (one rollout per warp); True: sweep.cuh (one rollout per thread); "cta": rollout.cuh
+    in the block-per-candidate arrangement (warp 0 walks the steps, three warps evaluate the collision model)."""
     return request.param
 
 

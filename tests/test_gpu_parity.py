@@ -23,16 +23,20 @@ def scene(built):
     return ab.HostScene()
 
 
-@pytest.fixture(autouse=True, params=["warp", "sweep"])
+@pytest.fixture(autouse=True, params=["warp", "sweep", "cta"])
 def kernel(request, monkeypatch):
-    """Every parity test runs on both kernels: one rollout per warp (small batches) and one rollout per
+    """Every parity test runs on the three kernels: one rollout per warp (mid-size batches), one rollout per
     thread (sweeps; AFF_SWEEP_MIN=1 selects it for every batch within its per-thread caps, anything larger
-    still runs on the warp kernel)."""
+    still runs on the warp kernel) and one rollout per block (a handful of candidates)."""
+    monkeypatch.delenv("AFF_CTA_MAX", raising=False)
     if request.param == "warp":
         monkeypatch.setenv("AFF_KERNEL", "warp")
+    elif request.param == "cta":
+        monkeypatch.setenv("AFF_KERNEL", "cta")
     else:
         monkeypatch.delenv("AFF_KERNEL", raising=False)
         monkeypatch.setenv("AFF_SWEEP_MIN", "1")
+        monkeypatch.setenv("AFF_CTA_MAX", "0")
     return request.param
 
 
@@ -478,6 +482,22 @@ def test_predict_batch_multi_splits_statically(scene):
     assert [r.as_tuple() for r in multi] == [r.as_tuple() for r in one]
     with pytest.raises(ab.AffError, match="device"):
         ab.predict_batch_multi(scene, batch, [0, 99], opts)
+
+
+def test_kernel_is_chosen_by_batch_size(scene, kernel, monkeypatch):
+    """No AFF_KERNEL in the environment: a handful of candidates run one per block, a few hundred and more one
+    per warp, sweeps one per thread."""
+    if kernel != "sweep":
+        pytest.skip("kernel selection is only exercised once")
+    monkeypatch.delenv("AFF_SWEEP_MIN", raising=False)
+    monkeypatch.delenv("AFF_CTA_MAX", raising=False)
+    opts = ab.default_opts()
+    kinds = []
+    for n in (2, 600, 30000):
+        batch = ab.HostBatch(scene)
+        batch.add_perturbed("get fresh_tomatoes", n, seed0=5)
+        kinds.append(ab.DeviceBatch(scene, batch, opts).kernel)
+    assert kinds == ["cta", "warp", "sweep"]
 
 
 def test_large_batch_runs_on_the_sweep_kernel_and_matches(scene, kernel, monkeypatch):
