@@ -82,13 +82,14 @@ AFF_ROLLOUT_KERNEL(aff_rollout_kernel_generic, kgeneric)  // anything larger
 
 // Block-per-candidate kernel for batches far below one wave (the call sites that check a handful of
 // candidates, or one trajectory): warp 0 walks the step loop, AFFC_WORKERS warps evaluate the collision
-// model of the finished steps on private copies of the frames, a few steps behind (k_rollout_t<1>,
-// k_cta_worker in rollout.cuh).  One warp per scheduler; the rollout is a dependent chain, so the time
+// model of the finished steps on private copies of the frames, a step or two behind, and one warp runs
+// the time-driven part (trajectories, activation points, blending) ahead of it (k_rollout_t<1>,
+// k_cta_worker, k_cta_traj in rollout.cuh).  One warp per scheduler; the rollout is a dependent chain, so the time
 // of a step is what counts here, not the work per SM.
 #ifndef AFF_CTA_BLOCKS_PER_SM
 #define AFF_CTA_BLOCKS_PER_SM 2     // 255 registers per thread: the step loop without spills
 #endif
-#define AFF_CTA_THREADS (32 * (1 + AFFC_WORKERS))
+#define AFF_CTA_THREADS (32 * AFFC_WARPS)
 #define AFF_CTA_KERNEL(NAME, NS)                                                                                         \
   __global__ void __launch_bounds__(AFF_CTA_THREADS, AFF_CTA_BLOCKS_PER_SM) NAME(const KPlan P)                          \
   {                                                                                                                      \
@@ -97,15 +98,16 @@ AFF_ROLLOUT_KERNEL(aff_rollout_kernel_generic, kgeneric)  // anything larger
     unsigned smAddr = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)warp * (unsigned)P.warp_doubles * 8u;        \
     asm volatile("" : "+r"(smAddr));                                                                                    \
     double* sm = (double*)__cvta_shared_to_generic((size_t)smAddr);                                                      \
-    NS::KCtaShared* X = (NS::KCtaShared*)(smem + (size_t)(1 + AFFC_WORKERS) * P.warp_doubles);                           \
+    NS::KCtaShared* X = (NS::KCtaShared*)(smem + (size_t)AFFC_WARPS * P.warp_doubles);                           \
     for (int cand = blockIdx.x; cand < P.nCands; cand += gridDim.x) {                                                    \
       if (threadIdx.x == 0) {                                                                                            \
-        X->fkSeq = 0; X->stop = 0;                                                                                       \
+        X->fkSeq = 0; X->stop = 0; X->trajSeq = 0; X->geoSeq = 0;                                                        \
         for (int w = 0; w < AFFC_WORKERS; ++w) { X->copied[w] = 0; X->done[w] = 0; }                                     \
       }                                                                                                                  \
       __syncthreads();                                                                                                   \
       if (warp == 0) NS::template k_rollout_t<1>(P, cand, sm, X);                                                        \
-      else NS::k_cta_worker(P, cand, sm, smem + P.o_node, X, warp);                                                      \
+      else if (warp <= AFFC_WORKERS) NS::k_cta_worker(P, cand, sm, smem + P.o_node, X, warp);                            \
+      else NS::k_cta_traj(P, cand, sm, smem + NS::k_xcur_offset(P), X);                                                  \
       __syncthreads();                                                                                                   \
     }                                                                                                                    \
   }
@@ -371,7 +373,7 @@ int aff_batch_create(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, c
   // its blocks holds); AFF_KERNEL=cta forces it, AFF_KERNEL=warp / sweep rule it out
   {
     const char* force = getenv("AFF_KERNEL");
-    b->ctaSmemBytes = b->host.smemBytesPerWarp * (1 + AFFC_WORKERS) + sizeof(kgeneric::KCtaShared);
+    b->ctaSmemBytes = b->host.smemBytesPerWarp * AFFC_WARPS + sizeof(kgeneric::KCtaShared);
     const void* cfn = b->useFixed ? (const void*)aff_rollout_cta_kernel : (const void*)aff_rollout_cta_kernel_generic;
     const bool fits = b->plan.warp_ok && b->ctaSmemBytes <= (size_t)s->smemOptin;
     int perSMc = 0;
@@ -662,6 +664,19 @@ int aff_debug_phase_clocks(unsigned long long out[16], int reset)
 {
   if (cudaMemcpyFromSymbol(out, kgeneric::g_phaseClocks, sizeof(unsigned long long) * 16) != cudaSuccess) return AFF_ERR_CUDA;
   if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(kgeneric::g_phaseClocks, z, sizeof(z)); }
+  return AFF_OK;
+}
+#endif
+
+#ifdef AFFK_PROFILE
+// tuning builds only: cycles lane 0 of warp 0 of block 0 spent in the parts of a step (K_MARK in rollout.cuh)
+extern "C" int aff_debug_step_clocks(unsigned long long out[16], int reset)
+{
+  unsigned long long a[16], b[16];
+  if (cudaMemcpyFromSymbol(a, kgeneric::g_kClocks, sizeof(a)) != cudaSuccess) return AFF_ERR_CUDA;
+  if (cudaMemcpyFromSymbol(b, kfixed::g_kClocks, sizeof(b)) != cudaSuccess) return AFF_ERR_CUDA;
+  for (int i = 0; i < 16; ++i) out[i] = a[i] + b[i];
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(kgeneric::g_kClocks, z, sizeof(z)); cudaMemcpyToSymbol(kfixed::g_kClocks, z, sizeof(z)); }
   return AFF_OK;
 }
 #endif

@@ -252,7 +252,7 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     // per-lane FK table
     const int nR = (int)H.rounds.size() / 2;
     KFkEntry idle; std::memset(&idle, 0, sizeof(idle));
-    H.fktab.assign((size_t)nR * 32, idle);   // idle lanes get their destination (the spare element) in patchFkAux
+    H.fktab.assign((size_t)(nR + 1) * 32, idle);   // idle lanes get their destination (the spare element) in patchFkAux; one spare round: the prefetch of k_fk_t<1> reads one round ahead
     P.fk_obj_rounds[0] = P.fk_obj_rounds[1] = P.fk_const_rounds[0] = P.fk_const_rounds[1] = 0u;
     for (int r = 0; r < nR; ++r)
       for (int grp = 0; grp < 2; ++grp) {

@@ -41,6 +41,22 @@
 #define AFFK_LS(P) ((P).LS)
 #endif
 
+// -DAFFK_PROFILE (tuning builds only): lane 0 of warp 0 of block 0 adds up the clock cycles of the parts of a step
+#if defined(AFFK_PROFILE) && !defined(AFF_EMULATE)
+__device__ unsigned long long g_kClocks[16];
+#define K_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now_ = clock64(); g_kClocks[i] += (unsigned long long)(now_ - kmark_); kmark_ = now_; } } while (0)
+#define K_MARK_INIT long long kmark_ = clock64()
+#define K_SUB(i, t0_) do { if (blockIdx.x == 0 && threadIdx.x == 0) { g_kClocks[i] += (unsigned long long)(clock64() - (t0_)); } } while (0)
+#define K_NOW() clock64()
+#else
+#define K_MARK(i) do { } while (0)
+#define K_MARK_INIT do { } while (0)
+#define K_SUB(i, t0_) do { } while (0)
+#define K_NOW() 0ll
+#endif
+#ifndef AFFK_ABL
+#define AFFK_ABL 0
+#endif
 #define AFFK_TRACK_MAX 0.05      // MAX_TRACKING_ERROR, src/TrajectoryPredictor.cpp:50
 #define AFFK_TRAJ_EPS 1.0e-8
 #define AFFK_NO_LIMIT 1.0e300
@@ -177,22 +193,37 @@ AFF_DEV void k_object_from_q6(const KCtx& c, int n, int slot)
 
 // RcsGraph_setState for the dynamic nodes: 12 lanes per node (one per HTr element), two nodes
 // per round on the host-built schedule; all parents are shared-memory slots.
-AFF_DEV void k_fk(const KCtx& c, bool init)
+template <int PREFETCH> AFF_DEV void k_fk_t(const KCtx& c, bool init)
 {
   const KPlan& P = *c.P;
   double* sn = c.sm + AFFK_O(P, sn); double* cs = c.sm + AFFK_O(P, cs);
   const double* q = c.sm + AFFK_O(P, q);
   double* nodes = c.nodes;
   const int lane = c.lane;
+  const long long tfk_ = K_NOW();
   if (lane < P.nJ) { double s, co; aff_sincos(q[lane], &s, &co); sn[lane] = s; cs[lane] = co; }
   w_sync();
+  K_SUB(11, tfk_);
   const int e = lane % 12;
   const int col = (e < 3) ? e : (e - 3) % 3, eo = (e < 3) ? e : 0;
   const KFkEntry* tab = P.fktab + lane;
   unsigned constRounds = P.fk_const_rounds[0], objRounds = P.fk_obj_rounds[0];   // bit 0 = this round
   const int scratchDst = 12 * (P.nDyn + P.nStatPar);      // one spare element behind the node array
+  // PREFETCH (block-per-candidate kernel: registers to spare): the entry of the next round is in flight
+  // while this round computes (the table has one spare round behind its end)
+  KFkEntry nxt;
+  if (PREFETCH) nxt = ldg_fk(tab);
   for (int r = 0; r < P.nRounds; ++r, tab += 32) {
-    const KFkEntry en = ldg_fk(tab);
+    KFkEntry en;
+#if defined(AFFK_PROFILE) && !defined(AFF_EMULATE)
+    const long long tld_ = K_NOW();
+#endif
+    if (PREFETCH) { en = nxt; nxt = ldg_fk(tab + 32); }
+    else en = ldg_fk(tab);
+#if defined(AFFK_PROFILE) && !defined(AFF_EMULATE)
+    asm volatile("" :: "r"(en.w0), "r"(en.w1));
+    K_SUB(13, tld_);
+#endif
     const int op = (int)((en.w0 >> 24) & 7u);
     const int pbase = (int)(en.w0 & 4095u);               // parent node (0 for lanes that do not compose)
     int dst = (int)((en.w0 >> 12) & 4095u);                // idle lanes: the spare element
@@ -211,6 +242,7 @@ AFF_DEV void k_fk(const KCtx& c, bool init)
     double val = (op == FKOP_COPY) ? x : (compose ? comp : 0.0);
     double s = x, co = cs[qi];
     if (r == 32) { constRounds = P.fk_const_rounds[1]; objRounds = P.fk_obj_rounds[1]; }
+#if AFFK_ABL != 1
     if (constRounds & 1u) {
       if (op > FKOP_FIXED && op <= FKOP_TRANS && (en.w1 & 0x80u)) {
         const int n = (int)((en.w1 >> 8) & 255u);
@@ -218,6 +250,8 @@ AFF_DEV void k_fk(const KCtx& c, bool init)
         co = ldg(&P.dynSC[2 * n + 1]);
       }
     }
+#endif
+#if AFFK_ABL != 2
     if (objRounds & 1u) {
       if (op == FKOP_OBJECT) {
         const int slot = (int)(en.w1 & 3u), n = (int)((en.w1 >> 8) & 255u);
@@ -233,14 +267,23 @@ AFF_DEV void k_fk(const KCtx& c, bool init)
         }
       }
     }
+#endif
+#if AFFK_ABL == 3
+    const double other = val;
+#else
     const double other = w_shfl(val, partner);
+#endif
     const double rotA = fma(s, other, co * val), rotB = fma(co, val, -(s * other)), trn = fma(s, other, val);
     val = (op == FKOP_ROT_A) ? rotA : ((op == FKOP_ROT_B) ? rotB : ((op == FKOP_TRANS) ? trn : val));
     nodes[dst] = val;
     constRounds >>= 1; objRounds >>= 1;
+#if AFFK_ABL != 4
     w_sync();
+#endif
   }
 }
+
+AFF_DEV void k_fk(const KCtx& c, bool init) { k_fk_t<0>(c, init); }
 
 // ------------------------------------------------------------ via-point step
 // One receding-horizon step of a 1-D via-point trajectory (the oracle's
@@ -1044,10 +1087,24 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
 // ----------------------------------------------------------- the rollout
 // Control block of the block-per-candidate kernel (cta.cuh), in shared memory: warp 0 walks the step
 // loop, the other warps evaluate the collision model of the steps it has finished, a few steps behind.
-#define AFFC_WORKERS 3
+#define AFFC_WORKERS 2
 #define AFFC_RING 4
+#define AFFC_TRING 8       // steps the trajectory warp may run ahead
+#define AFFC_WARPS (2 + AFFC_WORKERS)
+// What the step loop needs from the time-driven part of a step (trajectories, activation points, blending):
+// produced by the trajectory warp, which depends on the rollout only where a task switches on (its
+// trajectory then starts from the current task value).
+struct KCtaStep
+{
+  double xdes[32];
+  double alphaEff, phaseScale, qFilt;
+  unsigned activeMask; int pad;
+};
 struct KCtaShared
 {
+  int trajSeq;               // steps whose KCtaStep record is posted
+  int geoSeq;                // 1 + number of steps whose task values (xcur) are final in warp 0's slab
+  KCtaStep ring[AFFC_TRING];
   int fkSeq;                 // number of steps whose frames are final in warp 0's node array
   int stop;                  // warp 0 has left the step loop
   int copied[AFFC_WORKERS];  // per worker: steps whose frames it has taken over
@@ -1191,6 +1248,7 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
   // geometry of the initial state (for the first re-initialisation of the trajectories)
   if (lane < nTasks) k_task_geo(c, c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur);
   w_sync();
+  if (CTA) w_post(&X->geoSeq, 1);
 
   unsigned activeMask = 0u, prevMask = 0u, jmaskBits = 0u;
   unsigned emask = ~(P.rbj_static_chain);
@@ -1227,36 +1285,40 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
     if (cmv.minDist < r_minDist) { r_minDist = cmv.minDist; r_b1 = cmv.minB1; r_b2 = cmv.minB2; }
   };
 
+  K_MARK_INIT;
   for (int iter = 0; iter < nSteps; ++iter) {
     const int successPrev = success;
-    // ---- task switch / qFilt (:166-180)
-    if (prevMask != activeMask) qFilt = 1.0;
-    if (qFiltDecay <= 0.0) qFilt = 0.0;
-    else qFilt = k_clip(qFilt - (1.0 / qFiltDecay) * dt, 0.0, 1.0);
-
-    // ---- tc->step(dt): trajectories.  The state of an inactive task's trajectory is overwritten at
-    // the start of the next step unless the task switches on in this one, so only then is it computed.
     const double tnext = tnow + dt;
-    const int ah = w_shfl(actHead, myTask < 0 ? 0 : myTask), ae = actEndOf(myTask < 0 ? 0 : myTask);
-    // eight dimensions at a time: the solver scratch (via_stride doubles per lane) is the largest
-    // user of the shared union region
-    for (int batch = 0; batch < xdim; batch += AFFK_VIA_LANES) {
-      if (lane >= batch && lane < batch + AFFK_VIA_LANES && lane < xdim) {
-        const bool active = (activeMask >> myTask) & 1u;
-        // does an activation point of my task fire in this step and switch it on?
-        bool switchesOn = false;
-        for (int k = ah; k < ae; ++k) { if (!(ldg(&acts[k].t) - tnext < AFFK_TRAJ_EPS)) break; switchesOn = ldg(&acts[k].on) != 0; }
-        if (active || switchesOn) {
-          double s3[3];
-          if (!active) { s3[0] = xcur[lane]; s3[1] = 0.0; s3[2] = 0.0; }
-          else { s3[0] = st[3 * lane]; s3[1] = st[3 * lane + 1]; s3[2] = st[3 * lane + 2]; }
-          k_via_step(s3, vias + viaHead, viaEnd - viaHead, tnow, dt, sm + AFFK_O(P, scratch) + P.via_stride * (lane - batch), P.via_unk);
-          st[3 * lane] = s3[0]; st[3 * lane + 1] = s3[1]; st[3 * lane + 2] = s3[2];
-          xdes[lane] = s3[0];
+    if (!CTA) {
+      // ---- task switch / qFilt (:166-180)
+      if (prevMask != activeMask) qFilt = 1.0;
+      if (qFiltDecay <= 0.0) qFilt = 0.0;
+      else qFilt = k_clip(qFilt - (1.0 / qFiltDecay) * dt, 0.0, 1.0);
+
+      // ---- tc->step(dt): trajectories.  The state of an inactive task's trajectory is overwritten at
+      // the start of the next step unless the task switches on in this one, so only then is it computed.
+      const int ah = w_shfl(actHead, myTask < 0 ? 0 : myTask), ae = actEndOf(myTask < 0 ? 0 : myTask);
+      // eight dimensions at a time: the solver scratch (via_stride doubles per lane) is the largest
+      // user of the shared union region
+      for (int batch = 0; batch < xdim; batch += AFFK_VIA_LANES) {
+        if (lane >= batch && lane < batch + AFFK_VIA_LANES && lane < xdim) {
+          const bool active = (activeMask >> myTask) & 1u;
+          // does an activation point of my task fire in this step and switch it on?
+          bool switchesOn = false;
+          for (int k = ah; k < ae; ++k) { if (!(ldg(&acts[k].t) - tnext < AFFK_TRAJ_EPS)) break; switchesOn = ldg(&acts[k].on) != 0; }
+          if (active || switchesOn) {
+            double s3[3];
+            if (!active) { s3[0] = xcur[lane]; s3[1] = 0.0; s3[2] = 0.0; }
+            else { s3[0] = st[3 * lane]; s3[1] = st[3 * lane + 1]; s3[2] = st[3 * lane + 2]; }
+            k_via_step(s3, vias + viaHead, viaEnd - viaHead, tnow, dt, sm + AFFK_O(P, scratch) + P.via_stride * (lane - batch), P.via_unk);
+            st[3 * lane] = s3[0]; st[3 * lane + 1] = s3[1]; st[3 * lane + 2] = s3[2];
+            xdes[lane] = s3[0];
+          }
         }
+        w_sync();
       }
-      w_sync();
     }
+    K_MARK(0);
     tnow = tnext;
     // graph constraints
     for (int k = 0; k < nGcon; ++k) {
@@ -1299,35 +1361,46 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
         if (tc - tnow < 0.0) { const int md = ldg(&gcons[k].on) ? 1 : 2; OBJ_SET(c, objMode, slot, md); gfired |= 1u << k; }
       }
     }
-    // activation points
-    int myActive = (activeMask >> lane) & 1u;
-    if (lane < nTasks) {
-      const int actEnd = actEndOf(lane);
-      while (actHead < actEnd && ldg(&acts[actHead].t) - tnow < AFFK_TRAJ_EPS) { myActive = ldg(&acts[actHead].on); ++actHead; }
-    }
-    if (lane < xdim) { const int ve = viaEnd; while (viaHead < ve && ldg(&vias[viaHead].t) - tnow < AFFK_TRAJ_EPS) ++viaHead; }
-    prevMask = activeMask;
-    activeMask = w_ballot(lane < nTasks && myActive);
-    {
-      const double rem = endAbs - tnow;
-      endTime = rem > 0.0 ? rem : 0.0;
-    }
-    // blending
-    double bl = 1.0;
-    if (lane < nTasks) {
-      if (actHead < actEndOf(lane)) { const double h = ldg(&acts[actHead].horizon); if (h > 0.0) bl = k_clip((ldg(&acts[actHead].t) - tnow) / h, 0.0, 1.0); }
-      if (actHead > actBeginOf(lane)) {
-        const double lastSwitchT = ldg(&acts[actHead - 1].t), lastSwitchH = ldg(&acts[actHead - 1].horizon);
-        if (lastSwitchH > 0.0) { const double up = k_clip((tnow - lastSwitchT) / lastSwitchH, 0.0, 1.0); if (up < bl) bl = up; }
+    double alphaEff, phaseScale;
+    const double* xdesNow = xdes;
+    if (!CTA) {
+      // activation points
+      int myActive = (activeMask >> lane) & 1u;
+      if (lane < nTasks) {
+        const int actEnd = actEndOf(lane);
+        while (actHead < actEnd && ldg(&acts[actHead].t) - tnow < AFFK_TRAJ_EPS) { myActive = ldg(&acts[actHead].on); ++actHead; }
       }
-    }
-    double blending = w_ballot(bl < 1.0) ? w_min(bl) : 1.0;
-    if (activeMask == 0u) blending = 0.0;
-    const double phase = (motionDuration > 0.0) ? 1.0 - (endTime / motionDuration) : 0.0;
-    const double phaseScale = aff_sin(AFF_PI * phase);
-    const double alphaEff = blending * alpha;
-    w_sync();
+      if (lane < xdim) { const int ve = viaEnd; while (viaHead < ve && ldg(&vias[viaHead].t) - tnow < AFFK_TRAJ_EPS) ++viaHead; }
+      prevMask = activeMask;
+      activeMask = w_ballot(lane < nTasks && myActive);
+      {
+        const double rem = endAbs - tnow;
+        endTime = rem > 0.0 ? rem : 0.0;
+      }
+      // blending
+      double bl = 1.0;
+      if (lane < nTasks) {
+        if (actHead < actEndOf(lane)) { const double h = ldg(&acts[actHead].horizon); if (h > 0.0) bl = k_clip((ldg(&acts[actHead].t) - tnow) / h, 0.0, 1.0); }
+        if (actHead > actBeginOf(lane)) {
+          const double lastSwitchT = ldg(&acts[actHead - 1].t), lastSwitchH = ldg(&acts[actHead - 1].horizon);
+          if (lastSwitchH > 0.0) { const double up = k_clip((tnow - lastSwitchT) / lastSwitchH, 0.0, 1.0); if (up < bl) bl = up; }
+        }
+      }
+      double blending = w_ballot(bl < 1.0) ? w_min(bl) : 1.0;
+      if (activeMask == 0u) blending = 0.0;
+      const double phase = (motionDuration > 0.0) ? 1.0 - (endTime / motionDuration) : 0.0;
+      phaseScale = aff_sin(AFF_PI * phase);
+      alphaEff = blending * alpha;
+      w_sync();
 
+    } else {
+      // the record of this step from the trajectory warp
+      w_wait_ge(&X->trajSeq, iter + 1);
+      const KCtaStep* rec = &X->ring[iter & (AFFC_TRING - 1)];
+      activeMask = rec->activeMask; alphaEff = rec->alphaEff; phaseScale = rec->phaseScale; qFilt = rec->qFilt;
+      xdesNow = rec->xdes;
+    }
+    K_MARK(1);
     // ================= computeIK =================
     // row offsets of the active tasks
     int m = 0, myRow = 0;
@@ -1335,7 +1408,7 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
       if (t == lane) myRow = m;
       if ((activeMask >> t) & 1u) m += c.tdesc[8 * t + TD_DIM];
     }
-    if (lane < nTasks && ((activeMask >> lane) & 1u)) k_task_dx(c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur, xdes, dxv + myRow);
+    if (lane < nTasks && ((activeMask >> lane) & 1u)) k_task_dx(c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur, xdesNow, dxv + myRow);
     // joint frame of this lane's IK joint
     KJointFrame jf;
     jf.valid = (lane < nJ); jf.type = jtype;
@@ -1354,6 +1427,7 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
         row += c.tdesc[8 * t + TD_DIM];
       }
     }
+    K_MARK(2);
     // dH: joint limit gradient + elbow / wrist terms (:589-625)
     double dHv = 0.0;
     if (lane < nJ) {
@@ -1381,10 +1455,14 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
             double f;
             if (side == 0) f = k_clip((yE - yS) - boundary, -0.5, 0.0) * 5.0;
             else f = -k_clip((-yE + yS) - boundary, -0.5, 0.0) * 5.0;
-            double te[3], re[3], tr[3], rr[3];
-            k_jac_cols(c, jf, lane, el, Ae, te, re);
-            k_jac_cols(c, jf, lane, base, Ab, tr, rr);
-            tmp = tmp + (te[1] - tr[1]) * f;
+            // f == +-0 (the usual case: elbow / hand clear of its boundary): the term is +-0 and leaves the
+            // sum, which is never -0, as it is; f is the same on every lane
+            if (f != 0.0) {
+              double te[3], re[3], tr[3], rr[3];
+              k_jac_cols(c, jf, lane, el, Ae, te, re);
+              k_jac_cols(c, jf, lane, base, Ab, tr, rr);
+              tmp = tmp + (te[1] - tr[1]) * f;
+            }
           }
         }
         ex = ex + tmp;
@@ -1399,10 +1477,12 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
           const double z = fma(Ab[3 + 6 + 2], dW[2], fma(Ab[3 + 6 + 1], dW[1], Ab[3 + 6] * dW[0]));
           const double dBound = (z > 1.0) ? 0.4 * (z - 1.0) : 0.0;
           const double f = k_clip(x - (0.25 + dBound), -0.5, 0.0) * 5.0;
-          double te[3], re[3], tr[3], rr[3];
-          k_jac_cols(c, jf, lane, wr, Aw, te, re);
-          k_jac_cols(c, jf, lane, base, Ab, tr, rr);
-          tmp = tmp + (te[0] - tr[0]) * f;
+          if (f != 0.0) {
+            double te[3], re[3], tr[3], rr[3];
+            k_jac_cols(c, jf, lane, wr, Aw, te, re);
+            k_jac_cols(c, jf, lane, base, Ab, tr, rr);
+            tmp = tmp + (te[0] - tr[0]) * f;
+          }
         }
         ex = (ex + tmp) * alphaEff;
       }
@@ -1419,6 +1499,7 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
       if (lane < nJ && !(((aMask | emask) >> lane) & 1u)) dHv = dHv * 0.0;
       for (int r = 0; r < m; ++r) { const unsigned rm = w_ballot((nz >> r) & 1u); if (lane == r) rmask[r] = rm; }
     }
+    K_MARK(3);
     // ---- solveRightInverse
     const double vv = (lane < nJ) ? jw * dHv : 0.0;
     if (lane < nJ) vbuf[lane] = vv;          // v = W^-1 dH
@@ -1448,6 +1529,7 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
       }
     }
     w_sync();
+    K_MARK(4);
     // Cholesky, one lane per row, reciprocal pivots
     int singular = 0;
     double myInv = 1.0;     // lane i keeps 1 / L[i][i]
@@ -1466,6 +1548,7 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
       else if (lane > j && lane < m) L[lane * LS + j] = t * inv;
       w_sync();
     }
+    K_MARK(5);
     int ikRes = 0, id0 = -1;      // failure of this step, collisions aside
     // block-per-candidate: the worker of the previous step has taken that step's frames and object state
     if (CTA) { if (iter > 0) w_wait_ge(&X->copied[(iter - 1) % AFFC_WORKERS], iter); }
@@ -1515,8 +1598,10 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
         qdot[lane] = qd; q[lane] = q[lane] + dqv;     // own elements only: no hazard
       }
       w_sync();
+      K_MARK(6);
       // integration, FK, collision model, checkState (:730-752)
-      k_fk(c, false);
+      k_fk_t<CTA>(c, false);
+      K_MARK(7);
       if (!CTA) cm = k_collision(c, r_minDist > 0.001 ? r_minDist : 0.001);
       const unsigned fast = w_ballot(lane < nJ && jspeed < AFFK_NO_LIMIT && fabs(qd) > jspeed * 1.0);
       const unsigned viol = w_ballot(lane < nJ && (q[lane] < jqmin || q[lane] > jqmax));
@@ -1540,13 +1625,16 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
       }
       jlSum = jlSum + w_tree_sum(term);
     }
+    K_MARK(8);
     // ---- geometry of the new state; tracking error (:297-337)
+    const long long tgeo_ = K_NOW();
     if (lane < nTasks) k_task_geo(c, c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur);
     w_sync();
+    K_SUB(12, tgeo_);
     double pEv = -1.0; int pEk = 0;
     if (success && ikRes == 0) {       // (a step that has failed already does not look at the tracking error)
       double* dxe = dxv;   // stacked over all dims here
-      if (lane < nTasks && ((activeMask >> lane) & 1u)) k_task_dx(c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur, xdes, dxe + c.tdesc[8 * lane + TD_XOFF]);
+      if (lane < nTasks && ((activeMask >> lane) & 1u)) k_task_dx(c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur, xdesNow, dxe + c.tdesc[8 * lane + TD_XOFF]);
       w_sync();
       double ev = -1.0; int ek = 0x7fffffff;
       if (lane < xdim && ((activeMask >> myTask) & 1u)) { ev = fabs(dxe[lane]); ek = lane; }
@@ -1556,8 +1644,10 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
       }
       w_sync();
     }
+    K_MARK(9);
     if (!CTA) fold(iter, cm, ikRes, id0, pEv, pEk);
     else {
+      w_post(&X->geoSeq, iter + 2);      // task values of this state are final, the record of the step is no longer read
       const int slot = iter & (AFFC_RING - 1);
       if (lane == 0) { X->pendIk[slot] = ikRes; X->pendId0[slot] = id0; X->pendEv[slot] = pEv; X->pendEk[slot] = pEk; }
       w_sync();
@@ -1570,6 +1660,7 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
         if (lane == 0) X->need = r_minDist;
       }
     }
+    K_MARK(10);
     if (qlog && lane < nJ && rows < qrows) qlog[(size_t)rows * nJ + lane] = q[lane];
     rows++;
     if (P.opts.early_exit && !success && successPrev) break;     // opt-in: the reference's commented-out break (:368-373)
@@ -1597,6 +1688,7 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
 }
 
 AFF_DEV void k_rollout(const KPlan& P, int cand, double* sm) { k_rollout_t<0>(P, cand, sm, nullptr); }
+AFF_DEV int k_xcur_offset(const KPlan& P) { return AFFK_O(P, xcur); }
 
 // Worker warp w (1 .. AFFC_WORKERS) of a block-per-candidate launch: the collision model of the steps
 // k = w - 1, w - 1 + AFFC_WORKERS, ... on a private copy of the frames (its own slab: same layout as warp 0's).
@@ -1624,6 +1716,90 @@ AFF_DEV void k_cta_worker(const KPlan& P, int cand, double* sm, const double* no
     w_post(&X->done[w - 1], k + 1);
   }
 }
+// Trajectory warp of a block-per-candidate launch: everything of a step that is driven by time alone
+// (:166-180 qFilt, tc->step, activation points, blending), up to AFFC_TRING steps ahead of the step loop.
+// It waits for the rollout only where a task switches on: that trajectory starts from the task value of
+// the state before the step (xcur0: warp 0's slab).
+AFF_DEV void k_cta_traj(const KPlan& P, int cand, double* sm, const double* xcur0, KCtaShared* X)
+{
+  const KCand& C = P.cands[cand];
+  const int lane = w_lane();
+  const double dt = P.opts.dt;
+  const int nTasks = ldg(&C.n_tasks), xdim = ldg(&C.xdim);
+  const int taskBase = ldg(&C.first_task);
+  double* st = sm + AFFK_O(P, st); double* xdes = sm + AFFK_O(P, xdes);
+  int myTask = -1;
+  if (lane < xdim) for (int t = 0; t < nTasks; ++t) if (lane >= ldg(&tasks[t].xoff)) myTask = t;
+  int viaHead = 0;
+  if (lane < xdim) viaHead = ldg(&C.first_via) + ldg(&C.via_off[lane]);
+  int actHead = 0;
+  if (lane < nTasks) actHead = ldg(&C.first_act) + ldg(&C.act_off[lane]);
+  if (lane < xdim) { st[3 * lane] = 0.0; st[3 * lane + 1] = 0.0; st[3 * lane + 2] = 0.0; xdes[lane] = 0.0; }
+  w_sync();
+  unsigned activeMask = 0u, prevMask = 0u;
+  double tnow = 0.0, qFilt = 0.0, endTime = ldg(&C.end_abs);
+  const double endAbs = ldg(&C.end_abs);
+  const double motionDuration = endAbs - ldg(&C.start_abs);
+  const double alpha = P.opts.alpha, qFiltDecay = P.opts.q_filt_decay;
+  const int nSteps = ldg(&C.n_steps);
+  for (int iter = 0; iter < nSteps; ++iter) {
+    // the ring slot of this step is free once the step loop has finished step iter - AFFC_TRING
+    if (iter >= AFFC_TRING) { if (w_wait_ge_or(&X->geoSeq, iter - AFFC_TRING + 2, &X->stop)) return; }
+    if (prevMask != activeMask) qFilt = 1.0;
+    if (qFiltDecay <= 0.0) qFilt = 0.0;
+    else qFilt = k_clip(qFilt - (1.0 / qFiltDecay) * dt, 0.0, 1.0);
+    const double tnext = tnow + dt;
+    const int ah = w_shfl(actHead, myTask < 0 ? 0 : myTask), ae = actEndOf(myTask < 0 ? 0 : myTask);
+    bool active = false, switchesOn = false;
+    if (lane < xdim) {
+      active = (activeMask >> myTask) & 1u;
+      for (int k = ah; k < ae; ++k) { if (!(ldg(&acts[k].t) - tnext < AFFK_TRAJ_EPS)) break; switchesOn = ldg(&acts[k].on) != 0; }
+    }
+    if (w_ballot(!active && switchesOn)) { if (w_wait_ge_or(&X->geoSeq, iter + 1, &X->stop)) return; }
+    for (int batch = 0; batch < xdim; batch += AFFK_VIA_LANES) {
+      if (lane >= batch && lane < batch + AFFK_VIA_LANES && lane < xdim) {
+        if (active || switchesOn) {
+          double s3[3];
+          if (!active) { s3[0] = xcur0[lane]; s3[1] = 0.0; s3[2] = 0.0; }
+          else { s3[0] = st[3 * lane]; s3[1] = st[3 * lane + 1]; s3[2] = st[3 * lane + 2]; }
+          k_via_step(s3, vias + viaHead, viaEnd - viaHead, tnow, dt, sm + AFFK_O(P, scratch) + P.via_stride * (lane - batch), P.via_unk);
+          st[3 * lane] = s3[0]; st[3 * lane + 1] = s3[1]; st[3 * lane + 2] = s3[2];
+          xdes[lane] = s3[0];
+        }
+      }
+      w_sync();
+    }
+    tnow = tnext;
+    int myActive = (activeMask >> lane) & 1u;
+    if (lane < nTasks) {
+      const int actEnd = actEndOf(lane);
+      while (actHead < actEnd && ldg(&acts[actHead].t) - tnow < AFFK_TRAJ_EPS) { myActive = ldg(&acts[actHead].on); ++actHead; }
+    }
+    if (lane < xdim) { const int ve = viaEnd; while (viaHead < ve && ldg(&vias[viaHead].t) - tnow < AFFK_TRAJ_EPS) ++viaHead; }
+    prevMask = activeMask;
+    activeMask = w_ballot(lane < nTasks && myActive);
+    {
+      const double rem = endAbs - tnow;
+      endTime = rem > 0.0 ? rem : 0.0;
+    }
+    double bl = 1.0;
+    if (lane < nTasks) {
+      if (actHead < actEndOf(lane)) { const double h = ldg(&acts[actHead].horizon); if (h > 0.0) bl = k_clip((ldg(&acts[actHead].t) - tnow) / h, 0.0, 1.0); }
+      if (actHead > actBeginOf(lane)) {
+        const double lastSwitchT = ldg(&acts[actHead - 1].t), lastSwitchH = ldg(&acts[actHead - 1].horizon);
+        if (lastSwitchH > 0.0) { const double up = k_clip((tnow - lastSwitchT) / lastSwitchH, 0.0, 1.0); if (up < bl) bl = up; }
+      }
+    }
+    double blending = w_ballot(bl < 1.0) ? w_min(bl) : 1.0;
+    if (activeMask == 0u) blending = 0.0;
+    const double phase = (motionDuration > 0.0) ? 1.0 - (endTime / motionDuration) : 0.0;
+    KCtaStep* rec = &X->ring[iter & (AFFC_TRING - 1)];
+    if (lane < xdim) rec->xdes[lane] = xdes[lane];
+    if (lane == 0) { rec->activeMask = activeMask; rec->alphaEff = blending * alpha; rec->phaseScale = aff_sin(AFF_PI * phase); rec->qFilt = qFilt; }
+    w_post(&X->trajSeq, iter + 1);
+  }
+}
+
 #undef viaEnd
 #undef actBeginOf
 #undef actEndOf

@@ -137,17 +137,18 @@ static int emu_run(int sweep, const aff_scene_desc* scene, const aff_task_desc* 
     return AFF_OK;
   }
   if (sweep == 3) {
-    // block-per-candidate kernel: warp 0 = step loop, warps 1 .. AFFC_WORKERS = collision model
-    std::vector<double> sm((size_t)P.warp_doubles * (1 + AFFC_WORKERS) + 64);
+    // block-per-candidate kernel: warp 0 = step loop, warps 1 .. AFFC_WORKERS = collision model, last warp = trajectories
+    std::vector<double> sm((size_t)P.warp_doubles * AFFC_WARPS + 64);
     for (size_t i = 0; i < nCands; ++i) {
       std::fill(sm.begin(), sm.end(), 0.0);
       KCtaShared X;
       std::memset(&X, 0, sizeof(X));
-      runBlock(1 + AFFC_WORKERS, [&]() {
+      runBlock(AFFC_WARPS, [&]() {
         const int w = emu_warp();
         double* slab = sm.data() + (size_t)w * P.warp_doubles;
         if (w == 0) k_rollout_t<1>(P, (int)i, slab, &X);
-        else k_cta_worker(P, (int)i, slab, sm.data() + P.o_node, &X, w);
+        else if (w <= AFFC_WORKERS) k_cta_worker(P, (int)i, slab, sm.data() + P.o_node, &X, w);
+        else k_cta_traj(P, (int)i, slab, sm.data() + k_xcur_offset(P), &X);
       });
       out[i] = results[i];
     }
