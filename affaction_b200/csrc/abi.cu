@@ -87,7 +87,7 @@ AFF_ROLLOUT_KERNEL(aff_rollout_kernel_generic, kgeneric)  // anything larger
 // k_cta_worker, k_cta_traj in rollout.cuh).  One warp per scheduler; the rollout is a dependent chain, so the time
 // of a step is what counts here, not the work per SM.
 #ifndef AFF_CTA_BLOCKS_PER_SM
-#define AFF_CTA_BLOCKS_PER_SM 2     // 255 registers per thread: the step loop without spills
+#define AFF_CTA_BLOCKS_PER_SM 1     // 255 registers per thread: the step loop without spills
 #endif
 #define AFF_CTA_THREADS (32 * AFFC_WARPS)
 #define AFF_CTA_KERNEL(NAME, NS)                                                                                         \
@@ -98,16 +98,17 @@ AFF_ROLLOUT_KERNEL(aff_rollout_kernel_generic, kgeneric)  // anything larger
     unsigned smAddr = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)warp * (unsigned)P.warp_doubles * 8u;        \
     asm volatile("" : "+r"(smAddr));                                                                                    \
     double* sm = (double*)__cvta_shared_to_generic((size_t)smAddr);                                                      \
-    NS::KCtaShared* X = (NS::KCtaShared*)(smem + (size_t)AFFC_WARPS * P.warp_doubles);                           \
+    NS::KCtaShared* X = (NS::KCtaShared*)(smem + (size_t)(AFFC_WORKERS + 2) * P.warp_doubles);                           \
     for (int cand = blockIdx.x; cand < P.nCands; cand += gridDim.x) {                                                    \
       if (threadIdx.x == 0) {                                                                                            \
-        X->fkSeq = 0; X->stop = 0; X->trajSeq = 0; X->geoSeq = 0;                                                        \
+        X->fkSeq = 0; X->stop = 0; X->trajSeq = 0; X->geoSeq = 0; X->consSeq = 0; X->nsSeq = 0; X->trkSeq = 0;              \
         for (int w = 0; w < AFFC_WORKERS; ++w) { X->copied[w] = 0; X->done[w] = 0; }                                     \
       }                                                                                                                  \
       __syncthreads();                                                                                                   \
       if (warp == 0) NS::template k_rollout_t<1>(P, cand, sm, X);                                                        \
       else if (warp <= AFFC_WORKERS) NS::k_cta_worker(P, cand, sm, smem + P.o_node, X, warp);                            \
-      else NS::k_cta_traj(P, cand, sm, smem + NS::k_xcur_offset(P), X);                                                  \
+      else if (warp == AFFC_WORKERS + 1) NS::k_cta_traj(P, cand, sm, smem + NS::k_xcur_offset(P), X);                    \
+      else if (warp == AFFC_NS_WARP) NS::k_cta_nullspace(P, cand, smem, X);                                              \
       __syncthreads();                                                                                                   \
     }                                                                                                                    \
   }
@@ -373,7 +374,7 @@ int aff_batch_create(aff_scene* s, const aff_task_desc* tasks, size_t n_tasks, c
   // its blocks holds); AFF_KERNEL=cta forces it, AFF_KERNEL=warp / sweep rule it out
   {
     const char* force = getenv("AFF_KERNEL");
-    b->ctaSmemBytes = b->host.smemBytesPerWarp * AFFC_WARPS + sizeof(kgeneric::KCtaShared);
+    b->ctaSmemBytes = b->host.smemBytesPerWarp * (AFFC_WORKERS + 2) + sizeof(kgeneric::KCtaShared);     // slabs: step loop, workers, trajectories
     const void* cfn = b->useFixed ? (const void*)aff_rollout_cta_kernel : (const void*)aff_rollout_cta_kernel_generic;
     const bool fits = b->plan.warp_ok && b->ctaSmemBytes <= (size_t)s->smemOptin;
     int perSMc = 0;

@@ -1084,13 +1084,93 @@ AFF_DEV KCollResult k_collision(const KCtx& c, double need)
   return res;
 }
 
+// dH of one step (:589-625): joint-limit gradient + elbow / wrist null-space terms, scaled and speed-limited;
+// lane = IK joint.  Reads the frames, the chains and q of the state before the step.
+template <class Ctx> AFF_DEV double k_null_space_dH(const Ctx& c, const KJointFrame& jf, const double* q, double alphaEff, double phaseScale)
+{
+  const KPlan& P = *c.P;
+  const int lane = c.lane, nJ = P.nJ;
+  const double dt = P.opts.dt;
+  const int jl = (lane < nJ) ? lane : 0;
+  const double jq0 = ldg_here(&P.jq0[jl]), jqmin = ldg_here(&P.jq_min[jl]), jqmax = ldg_here(&P.jq_max[jl]);
+  const double jwjl = ldg_here(&P.jwjl[jl]), jspeed = ldg_here(&P.jspeed[jl]);
+  double dHv = 0.0;
+  if (lane < nJ) {
+    const double dqc = q[lane] - jq0;
+    const double r = (dqc > 0.0) ? jqmax - jq0 : jq0 - jqmin;
+    dHv = ((jwjl * dqc) / (r * r)) * alphaEff;
+  }
+  {
+    double ex = 0.0, tmp = 0.0;
+    if (P.ns_base >= 0) {   // -1: base_footprint absent, no extra null space
+      const int base = P.ns_base;
+      const double* Ab = k_slot(c, base);
+      // elbows, then hands (boundary 0.15 / 0.0)
+      for (int pass = 0; pass < 2; ++pass) {
+        const double boundary = pass ? 0.0 : 0.15;
+        for (int side = 0; side < 2; ++side) {
+          const int el = pass ? P.ns_hand[side] : P.ns_forearm[side];
+          const int sh = P.ns_upperarm[side];
+          if (el < 0 || sh < 0) continue;
+          const double* Ae = k_slot(c, el); const double* As = k_slot(c, sh);
+          double dS[3], dE[3];
+          for (int k = 0; k < 3; ++k) { dS[k] = As[k] - Ab[k]; dE[k] = Ae[k] - Ab[k]; }
+          const double yS = fma(Ab[3 + 3 + 2], dS[2], fma(Ab[3 + 3 + 1], dS[1], Ab[3 + 3] * dS[0]));
+          const double yE = fma(Ab[3 + 3 + 2], dE[2], fma(Ab[3 + 3 + 1], dE[1], Ab[3 + 3] * dE[0]));
+          double f;
+          if (side == 0) f = k_clip((yE - yS) - boundary, -0.5, 0.0) * 5.0;
+          else f = -k_clip((-yE + yS) - boundary, -0.5, 0.0) * 5.0;
+          // f == +-0 (the usual case: elbow / hand clear of its boundary): the term is +-0 and leaves the
+          // sum, which is never -0, as it is; f is the same on every lane
+          if (f != 0.0) {
+            double te[3], re[3], tr[3], rr[3];
+            k_jac_cols(c, jf, lane, el, Ae, te, re);
+            k_jac_cols(c, jf, lane, base, Ab, tr, rr);
+            tmp = tmp + (te[1] - tr[1]) * f;
+          }
+        }
+      }
+      ex = ex + tmp;
+      tmp = 0.0;
+      for (int side = 0; side < 2; ++side) {
+        const int wr = P.ns_hand[side];
+        if (wr < 0) continue;
+        const double* Aw = k_slot(c, wr);
+        double dW[3];
+        for (int k = 0; k < 3; ++k) dW[k] = Aw[k] - Ab[k];
+        const double x = fma(Ab[3 + 2], dW[2], fma(Ab[3 + 1], dW[1], Ab[3] * dW[0]));
+        const double z = fma(Ab[3 + 6 + 2], dW[2], fma(Ab[3 + 6 + 1], dW[1], Ab[3 + 6] * dW[0]));
+        const double dBound = (z > 1.0) ? 0.4 * (z - 1.0) : 0.0;
+        const double f = k_clip(x - (0.25 + dBound), -0.5, 0.0) * 5.0;
+        if (f != 0.0) {
+          double te[3], re[3], tr[3], rr[3];
+          k_jac_cols(c, jf, lane, wr, Aw, te, re);
+          k_jac_cols(c, jf, lane, base, Ab, tr, rr);
+          tmp = tmp + (te[0] - tr[0]) * f;
+        }
+      }
+      ex = (ex + tmp) * alphaEff;
+    }
+    // RcsGraph_checkJointSpeeds(dH_extra, dt, IK)
+    double sc = 1.0;
+    if (lane < nJ && jspeed < AFFK_NO_LIMIT) { const double a = fabs(ex), mx = jspeed * dt; if (a > mx) sc = mx / a; }
+    if (w_ballot(sc < 1.0)) { const double scale = w_min(sc); ex = ex * (0.99999 * scale); }
+    dHv = dHv + ex * phaseScale;
+  }
+  return dHv;
+}
+
 // ----------------------------------------------------------- the rollout
 // Control block of the block-per-candidate kernel (cta.cuh), in shared memory: warp 0 walks the step
 // loop, the other warps evaluate the collision model of the steps it has finished, a few steps behind.
 #define AFFC_WORKERS 2
 #define AFFC_RING 4
 #define AFFC_TRING 8       // steps the trajectory warp may run ahead
-#define AFFC_WARPS (2 + AFFC_WORKERS)
+// warp roles: 0 step loop | 1 .. AFFC_WORKERS collision | AFFC_WORKERS + 1 trajectories | 4 idle | 5 null space.
+// Warps w and w + 4 share a scheduler: the step loop keeps its scheduler to itself (the null-space warp, which
+// also spins on flags, sits beside a collision worker instead).
+#define AFFC_NS_WARP 5
+#define AFFC_WARPS 6
 // What the step loop needs from the time-driven part of a step (trajectories, activation points, blending):
 // produced by the trajectory warp, which depends on the rollout only where a task switches on (its
 // trajectory then starts from the current task value).
@@ -1104,6 +1184,11 @@ struct KCtaShared
 {
   int trajSeq;               // steps whose KCtaStep record is posted
   int geoSeq;                // 1 + number of steps whose task values (xcur) are final in warp 0's slab
+  int consSeq;               // steps whose graph constraints are applied (chains, object state) and whose start state is final
+  int nsSeq;                 // steps whose dH is posted by the null-space warp
+  int trkSeq;                // steps whose tracking error is posted by the null-space warp
+  double dH[32];
+  double trkDx[32];          // scratch of the tracking error
   KCtaStep ring[AFFC_TRING];
   int fkSeq;                 // number of steps whose frames are final in warp 0's node array
   int stop;                  // warp 0 has left the step loop
@@ -1285,6 +1370,51 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
     if (cmv.minDist < r_minDist) { r_minDist = cmv.minDist; r_b1 = cmv.minB1; r_b2 = cmv.minB2; }
   };
 
+  // graph constraints due at time tAt (the start of a step): ConnectBodyConstraint, CollisionModelConstraint
+  auto applyConstraints = [&](double tAt) {
+  for (int k = 0; k < nGcon; ++k) {
+    if ((gfired >> k) & 1u) continue;
+    const double tc = ldg(&gcons[k].t);
+    const int kind = ldg(&gcons[k].kind), slot = ldg(&gcons[k].slot);
+    if (kind == AFF_CON_CONNECT) {
+      if (tc - tAt < AFFK_TRAJ_EPS) {
+        const int ps = ldg(&gcons[k].parent_slot);
+        const int on = ldg(&P.obj_node[slot]);
+        w_sync();
+        if (lane < 12) {
+          // HTr_invTransform: child relative to the new parent; or the identity the constraint
+          // was given (setConnectTransform): the child then sits on the parent frame
+          const double* Cc = k_slot(c, on); const double* Pp = k_slot(c, ps);
+          double v;
+          if (ldg(&gcons[k].on)) v = (lane == 3 || lane == 7 || lane == 11) ? 1.0 : 0.0;
+          else if (lane < 3) {
+            const double d0 = Cc[0] - Pp[0], d1 = Cc[1] - Pp[1], d2 = Cc[2] - Pp[2];
+            v = fma(Pp[3 + 3 * lane + 2], d2, fma(Pp[3 + 3 * lane + 1], d1, Pp[3 + 3 * lane] * d0));
+          } else {
+            const int i = (lane - 3) / 3, j = (lane - 3) % 3;
+            v = fma(Cc[3 + 3 * i + 2], Pp[3 + 3 * j + 2], fma(Cc[3 + 3 * i + 1], Pp[3 + 3 * j + 1], Cc[3 + 3 * i] * Pp[3 + 3 * j]));
+          }
+          sm[AFFK_O(P, objrel) + 12 * slot + lane] = v;
+        }
+        c.objHasRel |= 1u << slot;
+        OBJ_SET(c, objParentSlot, slot, ps);
+        OBJ_SET(c, objParentDynamic, slot, ps < P.nDyn);
+        { const unsigned ch = c.chain[ps]; OBJ_SET(c, objChain, slot, ch); }
+        const int pt = ldg(&gcons[k].parent_tree);
+        { const int tr = (pt <= -2) ? OBJ_GET(c, objTree, -2 - pt) : pt; OBJ_SET(c, objTree, slot, tr); }
+        w_sync();
+        for (int i = lane; i < P.nDyn; i += 32) if (ldg(&P.dyn_under[i]) == slot + 1) c.chain[i] = ldg(&P.dyn_chain[i]) | OBJ_GET(c, objChain, slot);
+        emask = ~(P.rbj_static_chain);
+        emask &= ~(c.objChain0 | c.objChain1);
+        gfired |= 1u << k;
+      }
+    } else {
+      if (tc - tAt < 0.0) { const int md = ldg(&gcons[k].on) ? 1 : 2; OBJ_SET(c, objMode, slot, md); gfired |= 1u << k; }
+    }
+  }
+  };
+  if (CTA) { applyConstraints(0.0 + dt); w_post(&X->consSeq, 1); }
+
   K_MARK_INIT;
   for (int iter = 0; iter < nSteps; ++iter) {
     const int successPrev = success;
@@ -1320,47 +1450,9 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
     }
     K_MARK(0);
     tnow = tnext;
-    // graph constraints
-    for (int k = 0; k < nGcon; ++k) {
-      if ((gfired >> k) & 1u) continue;
-      const double tc = ldg(&gcons[k].t);
-      const int kind = ldg(&gcons[k].kind), slot = ldg(&gcons[k].slot);
-      if (kind == AFF_CON_CONNECT) {
-        if (tc - tnow < AFFK_TRAJ_EPS) {
-          const int ps = ldg(&gcons[k].parent_slot);
-          const int on = ldg(&P.obj_node[slot]);
-          w_sync();
-          if (lane < 12) {
-            // HTr_invTransform: child relative to the new parent; or the identity the constraint
-            // was given (setConnectTransform): the child then sits on the parent frame
-            const double* Cc = k_slot(c, on); const double* Pp = k_slot(c, ps);
-            double v;
-            if (ldg(&gcons[k].on)) v = (lane == 3 || lane == 7 || lane == 11) ? 1.0 : 0.0;
-            else if (lane < 3) {
-              const double d0 = Cc[0] - Pp[0], d1 = Cc[1] - Pp[1], d2 = Cc[2] - Pp[2];
-              v = fma(Pp[3 + 3 * lane + 2], d2, fma(Pp[3 + 3 * lane + 1], d1, Pp[3 + 3 * lane] * d0));
-            } else {
-              const int i = (lane - 3) / 3, j = (lane - 3) % 3;
-              v = fma(Cc[3 + 3 * i + 2], Pp[3 + 3 * j + 2], fma(Cc[3 + 3 * i + 1], Pp[3 + 3 * j + 1], Cc[3 + 3 * i] * Pp[3 + 3 * j]));
-            }
-            sm[AFFK_O(P, objrel) + 12 * slot + lane] = v;
-          }
-          c.objHasRel |= 1u << slot;
-          OBJ_SET(c, objParentSlot, slot, ps);
-          OBJ_SET(c, objParentDynamic, slot, ps < P.nDyn);
-          { const unsigned ch = c.chain[ps]; OBJ_SET(c, objChain, slot, ch); }
-          const int pt = ldg(&gcons[k].parent_tree);
-          { const int tr = (pt <= -2) ? OBJ_GET(c, objTree, -2 - pt) : pt; OBJ_SET(c, objTree, slot, tr); }
-          w_sync();
-          for (int i = lane; i < P.nDyn; i += 32) if (ldg(&P.dyn_under[i]) == slot + 1) c.chain[i] = ldg(&P.dyn_chain[i]) | OBJ_GET(c, objChain, slot);
-          emask = ~(P.rbj_static_chain);
-          emask &= ~(c.objChain0 | c.objChain1);
-          gfired |= 1u << k;
-        }
-      } else {
-        if (tc - tnow < 0.0) { const int md = ldg(&gcons[k].on) ? 1 : 2; OBJ_SET(c, objMode, slot, md); gfired |= 1u << k; }
-      }
-    }
+    // graph constraints (block-per-candidate: applied at the end of the step before, so that the null-space
+    // warp can start on the state they leave)
+    if (!CTA) applyConstraints(tnow);
     double alphaEff, phaseScale;
     const double* xdesNow = xdes;
     if (!CTA) {
@@ -1428,70 +1520,10 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
       }
     }
     K_MARK(2);
-    // dH: joint limit gradient + elbow / wrist terms (:589-625)
-    double dHv = 0.0;
-    if (lane < nJ) {
-      const double dqc = q[lane] - jq0;
-      const double r = (dqc > 0.0) ? jqmax - jq0 : jq0 - jqmin;
-      dHv = ((jwjl * dqc) / (r * r)) * alphaEff;
-    }
-    {
-      double ex = 0.0, tmp = 0.0;
-      if (P.ns_base >= 0) {   // -1: base_footprint absent, no extra null space
-        const int base = P.ns_base;
-        const double* Ab = k_slot(c, base);
-        // elbows, then hands (boundary 0.15 / 0.0)
-        for (int pass = 0; pass < 2; ++pass) {
-          const double boundary = pass ? 0.0 : 0.15;
-          for (int side = 0; side < 2; ++side) {
-            const int el = pass ? P.ns_hand[side] : P.ns_forearm[side];
-            const int sh = P.ns_upperarm[side];
-            if (el < 0 || sh < 0) continue;
-            const double* Ae = k_slot(c, el); const double* As = k_slot(c, sh);
-            double dS[3], dE[3];
-            for (int k = 0; k < 3; ++k) { dS[k] = As[k] - Ab[k]; dE[k] = Ae[k] - Ab[k]; }
-            const double yS = fma(Ab[3 + 3 + 2], dS[2], fma(Ab[3 + 3 + 1], dS[1], Ab[3 + 3] * dS[0]));
-            const double yE = fma(Ab[3 + 3 + 2], dE[2], fma(Ab[3 + 3 + 1], dE[1], Ab[3 + 3] * dE[0]));
-            double f;
-            if (side == 0) f = k_clip((yE - yS) - boundary, -0.5, 0.0) * 5.0;
-            else f = -k_clip((-yE + yS) - boundary, -0.5, 0.0) * 5.0;
-            // f == +-0 (the usual case: elbow / hand clear of its boundary): the term is +-0 and leaves the
-            // sum, which is never -0, as it is; f is the same on every lane
-            if (f != 0.0) {
-              double te[3], re[3], tr[3], rr[3];
-              k_jac_cols(c, jf, lane, el, Ae, te, re);
-              k_jac_cols(c, jf, lane, base, Ab, tr, rr);
-              tmp = tmp + (te[1] - tr[1]) * f;
-            }
-          }
-        }
-        ex = ex + tmp;
-        tmp = 0.0;
-        for (int side = 0; side < 2; ++side) {
-          const int wr = P.ns_hand[side];
-          if (wr < 0) continue;
-          const double* Aw = k_slot(c, wr);
-          double dW[3];
-          for (int k = 0; k < 3; ++k) dW[k] = Aw[k] - Ab[k];
-          const double x = fma(Ab[3 + 2], dW[2], fma(Ab[3 + 1], dW[1], Ab[3] * dW[0]));
-          const double z = fma(Ab[3 + 6 + 2], dW[2], fma(Ab[3 + 6 + 1], dW[1], Ab[3 + 6] * dW[0]));
-          const double dBound = (z > 1.0) ? 0.4 * (z - 1.0) : 0.0;
-          const double f = k_clip(x - (0.25 + dBound), -0.5, 0.0) * 5.0;
-          if (f != 0.0) {
-            double te[3], re[3], tr[3], rr[3];
-            k_jac_cols(c, jf, lane, wr, Aw, te, re);
-            k_jac_cols(c, jf, lane, base, Ab, tr, rr);
-            tmp = tmp + (te[0] - tr[0]) * f;
-          }
-        }
-        ex = (ex + tmp) * alphaEff;
-      }
-      // RcsGraph_checkJointSpeeds(dH_extra, dt, IK)
-      double sc = 1.0;
-      if (lane < nJ && jspeed < AFFK_NO_LIMIT) { const double a = fabs(ex), mx = jspeed * dt; if (a > mx) sc = mx / a; }
-      if (w_ballot(sc < 1.0)) { const double scale = w_min(sc); ex = ex * (0.99999 * scale); }
-      dHv = dHv + ex * phaseScale;
-    }
+    // dH: joint limit gradient + elbow / wrist terms (:589-625); block-per-candidate: from the null-space warp
+    double dHv;
+    if (!CTA) dHv = k_null_space_dH(c, jf, q, alphaEff, phaseScale);
+    else { w_wait_ge(&X->nsSeq, iter + 1); dHv = X->dH[lane]; }
     // joint masks (:636-675); row masks of J for the sparse products below
     {
       const unsigned aMask = w_ballot(nz != 0u);
@@ -1599,6 +1631,9 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
       }
       w_sync();
       K_MARK(6);
+#if defined(AFFK_PROFILE) && !defined(AFF_EMULATE)
+      if (iter == 100) { const long long tr_ = K_NOW(); for (int rep = 0; rep < 64; ++rep) k_fk_t<CTA>(c, false); K_SUB(14, tr_); K_MARK(15); }
+#endif
       // integration, FK, collision model, checkState (:730-752)
       k_fk_t<CTA>(c, false);
       K_MARK(7);
@@ -1613,6 +1648,8 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
       // the single-warp kernel keeps from the step before)
       if (lane == 0) { X->objState[0] = c.objMode0; X->objState[1] = c.objMode1; X->objState[2] = c.objTree0; X->objState[3] = c.objTree1; }
       w_post(&X->fkSeq, iter + 1);
+      if (iter + 1 < nSteps) applyConstraints(tnow + dt);
+      w_post(&X->consSeq, iter + 2);
     }
     // ---- costs (:226-227)
     {
@@ -1628,11 +1665,13 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
     K_MARK(8);
     // ---- geometry of the new state; tracking error (:297-337)
     const long long tgeo_ = K_NOW();
+    if (CTA) { if (iter > 0) w_wait_ge(&X->trkSeq, iter); }      // the tracking error of the step before has been taken from geo / xcur
     if (lane < nTasks) k_task_geo(c, c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur);
     w_sync();
     K_SUB(12, tgeo_);
+    if (CTA) w_post(&X->geoSeq, iter + 2);      // task values of this state are final
     double pEv = -1.0; int pEk = 0;
-    if (success && ikRes == 0) {       // (a step that has failed already does not look at the tracking error)
+    if (!CTA && success && ikRes == 0) {       // (a step that has failed already does not look at the tracking error)
       double* dxe = dxv;   // stacked over all dims here
       if (lane < nTasks && ((activeMask >> lane) & 1u)) k_task_dx(c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur, xdesNow, dxe + c.tdesc[8 * lane + TD_XOFF]);
       w_sync();
@@ -1647,13 +1686,13 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
     K_MARK(9);
     if (!CTA) fold(iter, cm, ikRes, id0, pEv, pEk);
     else {
-      w_post(&X->geoSeq, iter + 2);      // task values of this state are final, the record of the step is no longer read
       const int slot = iter & (AFFC_RING - 1);
-      if (lane == 0) { X->pendIk[slot] = ikRes; X->pendId0[slot] = id0; X->pendEv[slot] = pEv; X->pendEk[slot] = pEk; }
+      if (lane == 0) { X->pendIk[slot] = ikRes; X->pendId0[slot] = id0; }     // (pendEv / pendEk: from the null-space warp)
       w_sync();
       const int j = iter - lag;
       if (j >= 0) {
         w_wait_ge(&X->done[j % AFFC_WORKERS], j + 1);
+        w_wait_ge(&X->trkSeq, j + 1);
         const int sj = j & (AFFC_RING - 1);
         const KCollResult cj = X->res[sj];
         fold(j, cj, X->pendIk[sj], X->pendId0[sj], X->pendEv[sj], X->pendEk[sj]);
@@ -1670,6 +1709,7 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
     const int stepsDone = rows - 1;
     for (int j = (stepsDone > lag ? stepsDone - lag : 0); j < stepsDone; ++j) {
       w_wait_ge(&X->done[j % AFFC_WORKERS], j + 1);
+      w_wait_ge(&X->trkSeq, j + 1);
       const int sj = j & (AFFC_RING - 1);
       const KCollResult cj = X->res[sj];
       fold(j, cj, X->pendIk[sj], X->pendId0[sj], X->pendEv[sj], X->pendEk[sj]);
@@ -1743,8 +1783,8 @@ AFF_DEV void k_cta_traj(const KPlan& P, int cand, double* sm, const double* xcur
   const double alpha = P.opts.alpha, qFiltDecay = P.opts.q_filt_decay;
   const int nSteps = ldg(&C.n_steps);
   for (int iter = 0; iter < nSteps; ++iter) {
-    // the ring slot of this step is free once the step loop has finished step iter - AFFC_TRING
-    if (iter >= AFFC_TRING) { if (w_wait_ge_or(&X->geoSeq, iter - AFFC_TRING + 2, &X->stop)) return; }
+    // the ring slot of this step is free once the last reader (tracking error) of step iter - AFFC_TRING is through
+    if (iter >= AFFC_TRING) { if (w_wait_ge_or(&X->trkSeq, iter - AFFC_TRING + 1, &X->stop)) return; }
     if (prevMask != activeMask) qFilt = 1.0;
     if (qFiltDecay <= 0.0) qFilt = 0.0;
     else qFilt = k_clip(qFilt - (1.0 / qFiltDecay) * dt, 0.0, 1.0);
@@ -1798,6 +1838,68 @@ AFF_DEV void k_cta_traj(const KPlan& P, int cand, double* sm, const double* xcur
     if (lane == 0) { rec->activeMask = activeMask; rec->alphaEff = blending * alpha; rec->phaseScale = aff_sin(AFF_PI * phase); rec->qFilt = qFilt; }
     w_post(&X->trajSeq, iter + 1);
   }
+}
+
+// Null-space warp of a block-per-candidate launch: the two per-step computations that sit beside the
+// critical chain FK -> Jacobian -> solve -> FK.  (1) dH of step k from the state before it (frames, chains,
+// q in warp 0's slab: final once consSeq > k) and the step's blending / phase factors; (2) the tracking
+// error of the state after step k (:297-337; geo / xcur final once geoSeq > k + 1), unconditionally: the
+// step loop decides at fold time whether it still counts.
+AFF_DEV void k_cta_nullspace(const KPlan& P, int cand, double* sm0, KCtaShared* X)
+{
+  KCtx c;
+  c.P = &P; c.C = P.cands + cand; c.sm = sm0; c.lane = w_lane();
+  c.nodes = sm0 + P.o_node;
+  c.chain = (unsigned*)(sm0 + AFFK_O(P, chain));
+  c.tdesc = (int*)(sm0 + AFFK_O(P, tdesc));
+  c.objHasRel = 0u;
+  c.objParentSlot0 = c.objParentSlot1 = 0; c.objParentDynamic0 = c.objParentDynamic1 = 0; c.objChain0 = c.objChain1 = 0u;
+  c.objTree0 = c.objTree1 = -1; c.objMode0 = c.objMode1 = 0;
+  const KCand& C = *c.C;
+  const int lane = c.lane, nJ = P.nJ;
+  const int nTasks = ldg(&C.n_tasks), xdim = ldg(&C.xdim);
+  const int taskBase = ldg(&C.first_task);
+  const double* q = sm0 + AFFK_O(P, q);
+  const double* geo = sm0 + AFFK_O(P, geo); const double* xcur = sm0 + AFFK_O(P, xcur);
+  double* dxe = X->trkDx;
+  int jnode = 0, jtype = 0;
+  if (lane < nJ) { jnode = ldg(&P.j_node[lane]); jtype = ldg(&P.j_type[lane]); }
+  int myTask = -1;
+  if (lane < xdim) for (int t = 0; t < nTasks; ++t) if (lane >= ldg(&tasks[t].xoff)) myTask = t;
+  const int nSteps = ldg(&C.n_steps);
+  // tracking error of the state after step j
+  auto tracking = [&](int j) -> bool {
+    if (w_wait_ge_or(&X->geoSeq, j + 2, &X->stop)) return true;
+    const KCtaStep* rec = &X->ring[j & (AFFC_TRING - 1)];
+    const unsigned activeMask = rec->activeMask;
+    if (lane < nTasks && ((activeMask >> lane) & 1u)) k_task_dx(c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur, rec->xdes, dxe + c.tdesc[8 * lane + TD_XOFF]);
+    w_sync();
+    double ev = -1.0; int ek = 0x7fffffff;
+    if (lane < xdim && ((activeMask >> myTask) & 1u)) { ev = fabs(dxe[lane]); ek = lane; }
+    w_max_keyed(ev, ek);
+    const int slot = j & (AFFC_RING - 1);
+    if (lane == 0) { X->pendEv[slot] = ev; X->pendEk[slot] = ek; }
+    w_post(&X->trkSeq, j + 1);
+    return false;
+  };
+  for (int iter = 0; iter < nSteps; ++iter) {
+    // dH of step iter first (the step loop needs it midway through the step), then the tracking error of the step before
+    if (w_wait_ge_or(&X->consSeq, iter + 1, &X->stop)) return;
+    if (w_wait_ge_or(&X->trajSeq, iter + 1, &X->stop)) return;
+    {
+      const KCtaStep* rec = &X->ring[iter & (AFFC_TRING - 1)];
+      KJointFrame jf;
+      jf.valid = (lane < nJ); jf.type = jtype;
+      const double* A = k_slot(c, jnode);
+      const int ar = (jtype < AFF_JNT_ROT_X) ? jtype : jtype - AFF_JNT_ROT_X;
+      for (int k = 0; k < 3; ++k) { jf.ax[k] = A[3 + 3 * ar + k]; jf.org[k] = A[k]; }
+      const double dHv = k_null_space_dH(c, jf, q, rec->alphaEff, rec->phaseScale);
+      X->dH[lane] = dHv;
+      w_post(&X->nsSeq, iter + 1);
+    }
+    if (iter > 0) { if (tracking(iter - 1)) return; }
+  }
+  if (nSteps > 0) tracking(nSteps - 1);
 }
 
 #undef viaEnd

@@ -24,7 +24,7 @@
 // up to EMU_WARPS warps of one block: fiber f = 32 * warp + lane.  Every fiber advances to its next
 // yield once per scheduler round, so the lanes of a warp stay aligned at their barriers, and flags
 // written by another warp are seen a round later at the latest.
-#define EMU_WARPS 4
+#define EMU_WARPS 8
 static ucontext_t g_main, g_ctx[32 * EMU_WARPS];
 static int g_cur = 0;
 static bool g_done[32 * EMU_WARPS];
@@ -148,7 +148,8 @@ static int emu_run(int sweep, const aff_scene_desc* scene, const aff_task_desc* 
         double* slab = sm.data() + (size_t)w * P.warp_doubles;
         if (w == 0) k_rollout_t<1>(P, (int)i, slab, &X);
         else if (w <= AFFC_WORKERS) k_cta_worker(P, (int)i, slab, sm.data() + P.o_node, &X, w);
-        else k_cta_traj(P, (int)i, slab, sm.data() + k_xcur_offset(P), &X);
+        else if (w == AFFC_WORKERS + 1) k_cta_traj(P, (int)i, slab, sm.data() + k_xcur_offset(P), &X);
+        else if (w == AFFC_NS_WARP) k_cta_nullspace(P, (int)i, sm.data(), &X);
       });
       out[i] = results[i];
     }
