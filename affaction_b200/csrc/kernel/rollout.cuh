@@ -1200,6 +1200,8 @@ struct KCtaShared
   // bookkeeping of steps whose collision result has not arrived yet
   int pendIk[AFFC_RING], pendId0[AFFC_RING], pendEk[AFFC_RING];
   double pendEv[AFFC_RING];
+  int pendChk[AFFC_RING], pendChkId0[AFFC_RING];     // speed / joint-limit check of the state after the step (null-space warp)
+  double pendJl[AFFC_RING];                            // joint-limit cost summed over the steps up to it
 };
 
 // CTA = 0: the warp does everything (one rollout per warp).  CTA = 1: warp 0 of a block-per-candidate
@@ -1638,10 +1640,12 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
       k_fk_t<CTA>(c, false);
       K_MARK(7);
       if (!CTA) cm = k_collision(c, r_minDist > 0.001 ? r_minDist : 0.001);
-      const unsigned fast = w_ballot(lane < nJ && jspeed < AFFK_NO_LIMIT && fabs(qd) > jspeed * 1.0);
-      const unsigned viol = w_ballot(lane < nJ && (q[lane] < jqmin || q[lane] > jqmax));
-      if (fast) ikRes = AFF_CODE_SPEED;
-      else if (viol) { ikRes = AFF_CODE_JOINT_LIMIT; id0 = w_popc(viol); }
+      if (!CTA) {     // (block-per-candidate: the null-space warp checks the new state and adds up its joint-limit cost)
+        const unsigned fast = w_ballot(lane < nJ && jspeed < AFFK_NO_LIMIT && fabs(qd) > jspeed * 1.0);
+        const unsigned viol = w_ballot(lane < nJ && (q[lane] < jqmin || q[lane] > jqmax));
+        if (fast) ikRes = AFF_CODE_SPEED;
+        else if (viol) { ikRes = AFF_CODE_JOINT_LIMIT; id0 = w_popc(viol); }
+      }
     }
     if (CTA) {
       // hand the step to its worker (a singular step leaves the frames as they were: the worker finds what
@@ -1652,7 +1656,7 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
       w_post(&X->consSeq, iter + 2);
     }
     // ---- costs (:226-227)
-    {
+    if (!CTA) {
       double term = 0.0;
       if (lane < nJ) {
         const double dqc = q[lane] - jq0;
@@ -1695,7 +1699,9 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
         w_wait_ge(&X->trkSeq, j + 1);
         const int sj = j & (AFFC_RING - 1);
         const KCollResult cj = X->res[sj];
-        fold(j, cj, X->pendIk[sj], X->pendId0[sj], X->pendEv[sj], X->pendEk[sj]);
+        const int sing = X->pendIk[sj];
+        fold(j, cj, sing ? sing : X->pendChk[sj], sing ? -1 : X->pendChkId0[sj], X->pendEv[sj], X->pendEk[sj]);
+        jlSum = X->pendJl[sj];
         if (lane == 0) X->need = r_minDist;
       }
     }
@@ -1712,7 +1718,9 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
       w_wait_ge(&X->trkSeq, j + 1);
       const int sj = j & (AFFC_RING - 1);
       const KCollResult cj = X->res[sj];
-      fold(j, cj, X->pendIk[sj], X->pendId0[sj], X->pendEv[sj], X->pendEk[sj]);
+      const int sing = X->pendIk[sj];
+      fold(j, cj, sing ? sing : X->pendChk[sj], sing ? -1 : X->pendChkId0[sj], X->pendEv[sj], X->pendEk[sj]);
+      jlSum = X->pendJl[sj];
     }
     w_post(&X->stop, 1);
   }
@@ -1882,10 +1890,37 @@ AFF_DEV void k_cta_nullspace(const KPlan& P, int cand, double* sm0, KCtaShared* 
     w_post(&X->trkSeq, j + 1);
     return false;
   };
+  // checkState of the state after step j, collisions aside (:756-886 speed, joint limits), and its joint-limit cost (:226-227)
+  const double* qdot = sm0 + AFFK_O(P, qdot);
+  const int jl = (lane < nJ) ? lane : 0;
+  double jlSum = 0.0;
+  auto checks = [&](int j, double qv, double qdv) {
+    // (jq0, jqmin, ... : the per-joint constants of this lane, re-read through the macros of k_rollout_t)
+    const unsigned fast = w_ballot(lane < nJ && jspeed < AFFK_NO_LIMIT && fabs(qdv) > jspeed * 1.0);
+    const unsigned viol = w_ballot(lane < nJ && (qv < jqmin || qv > jqmax));
+    double term = 0.0;
+    if (lane < nJ) {
+      const double dqc = qv - jq0;
+      const double r = (dqc > 0.0) ? jqmax - jq0 : jq0 - jqmin;
+      const double u = dqc / r;
+      term = (0.5 * jwjl) * (u * u);
+    }
+    jlSum = jlSum + w_tree_sum(term);
+    const int slot = j & (AFFC_RING - 1);
+    if (lane == 0) {
+      X->pendChk[slot] = fast ? AFF_CODE_SPEED : (viol ? AFF_CODE_JOINT_LIMIT : 0);
+      X->pendChkId0[slot] = (!fast && viol) ? w_popc(viol) : -1;
+      X->pendJl[slot] = jlSum;
+    }
+  };
   for (int iter = 0; iter < nSteps; ++iter) {
-    // dH of step iter first (the step loop needs it midway through the step), then the tracking error of the step before
+    // dH of step iter first (the step loop needs it midway through the step), then the checks and the tracking error
+    // of the step before.  q / qdot of the state before step iter are taken before dH is posted: the step loop
+    // overwrites them once it has dH.
     if (w_wait_ge_or(&X->consSeq, iter + 1, &X->stop)) return;
     if (w_wait_ge_or(&X->trajSeq, iter + 1, &X->stop)) return;
+    double qv = 0.0, qdv = 0.0;
+    if (lane < nJ) { qv = q[lane]; qdv = qdot[lane]; }
     {
       const KCtaStep* rec = &X->ring[iter & (AFFC_TRING - 1)];
       KJointFrame jf;
@@ -1897,9 +1932,15 @@ AFF_DEV void k_cta_nullspace(const KPlan& P, int cand, double* sm0, KCtaShared* 
       X->dH[lane] = dHv;
       w_post(&X->nsSeq, iter + 1);
     }
-    if (iter > 0) { if (tracking(iter - 1)) return; }
+    if (iter > 0) { checks(iter - 1, qv, qdv); if (tracking(iter - 1)) return; }
   }
-  if (nSteps > 0) tracking(nSteps - 1);
+  if (nSteps > 0) {
+    if (w_wait_ge_or(&X->fkSeq, nSteps, &X->stop)) return;
+    double qv = 0.0, qdv = 0.0;
+    if (lane < nJ) { qv = q[lane]; qdv = qdot[lane]; }
+    checks(nSteps - 1, qv, qdv);
+    tracking(nSteps - 1);
+  }
 }
 
 #undef viaEnd
