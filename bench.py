@@ -19,7 +19,7 @@ one batch of ROLLOUTS_PER_GPU candidates per GPU.
           (plan compile, H2D of the tables, kernels, D2H of the verdicts), one host
           thread per variant, timed over all --steps iterations
   roofline: FP64 pipe (the path's bound); flops per rollout COUNTED by
-          running the kernel source with a counting scalar (tools/count_flops.py ->
+          running the kernel source with a counting scalar (tests/tools/count_flops.py ->
           profiles/flops_per_rollout.json); peak = DFMA rate measured on this GPU in
           this run by aff_measure_fp64_peak.  roofline_hbm: the per-thread state of the
           sweep kernel streams through HBM; measured DRAM bytes per rollout from ncu
@@ -59,7 +59,7 @@ NCU_DRAM_BYTES_PER_ROLLOUT = 29480000
 
 def algorithmic_flops_per_rollout():
     """FP64 flops of one full-length rollout (FMA = 2), mean over the three variants: COUNTED by executing
-    the kernel source with a counting scalar (tests/emu/flop_count.cpp, tools/count_flops.py), not estimated.
+    the kernel source with a counting scalar (tests/emu/flop_count.cpp, tests/tools/count_flops.py), not estimated.
     -> (flops, per-variant dict, source)"""
     path = os.path.join(ROOT, "profiles", "flops_per_rollout.json")
     with open(path) as f:

@@ -1,4 +1,4 @@
-"""Golden fixtures (tests/golden/predict_get.json, made by tools/make_golden.py from the
+"""Golden fixtures (tests/golden/predict_get.json, made by tests/tools/make_golden.py from the
 CPU oracle — the reference itself holds no numeric fixtures for this path): the
 oracle must keep reproducing them (CPU tier) and the CUDA path must reproduce
 them bit for bit (GPU tier)."""

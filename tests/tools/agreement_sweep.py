@@ -3,7 +3,7 @@ against the CPU oracle (all host threads), per grasp variant.  Prints one summar
 import os
 import sys
 import time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import affaction_b200 as ab

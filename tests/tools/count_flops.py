@@ -1,12 +1,12 @@
 """FP64 operations per rollout of the bench workload, counted by running the kernel source on the CPU
 with a counting scalar (tests/emu/flop_count.cpp).  Writes profiles/flops_per_rollout.json, which
 bench.py reads for the numerator of its FP64 roofline.
-usage: python tools/count_flops.py [candidates per variant, default 64]"""
+usage: python tests/tools/count_flops.py [candidates per variant, default 64]"""
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import affaction_b200 as ab  # noqa: E402

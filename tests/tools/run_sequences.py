@@ -7,7 +7,7 @@ with 0 failed actions" (/root/reference/examples/TestLLMSim.cpp:246, unittest.sh
 config/xml/pizza/g_scenario_pizza.xml:38-184).  The sequence texts are copied into
 tests/golden/pizza_sequences.json so this runs without /root/reference.
 
-usage: python tools/run_sequences.py [--lift-arm-speed-limits] [name ...]      (default: all)
+usage: python tests/tools/run_sequences.py [--lift-arm-speed-limits] [name ...]      (default: all)
 
 --lift-arm-speed-limits: the discriminating experiment of DESIGN.md section 2: the same sequences on a
 copy of the scene whose seven arm joints per side have no speed limit (the fingers keep theirs).
@@ -16,7 +16,7 @@ import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -1,12 +1,12 @@
 """GPU probe of the two kernels: parity of the thread-per-candidate ("sweep") kernel against the
 warp-per-candidate kernel and the CPU oracle on a sample, then kernel time over batch sizes.
-usage: python tools/sweep_probe.py [sizes ...]"""
+usage: python tests/tools/sweep_probe.py [sizes ...]"""
 import collections
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import affaction_b200 as ab  # noqa: E402
