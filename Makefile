@@ -22,7 +22,7 @@ affaction_b200/libaffpredict.so: affaction_b200/csrc/abi.cu affaction_b200/csrc/
 # the first call that predicts (affaction_b200/csrc/host/gpu_api.cpp).  -Bsymbolic: its C++ symbols bind inside the library (a process
 # that has torch loaded otherwise interposes template instantiations of another libstdc++ build: segfault)
 affaction_b200/libaffhost.so: $(HOST_SRC) affaction_b200/csrc/abi_common.cpp $(KERNEL_HDR)
-	$(CXX) -O2 -std=c++17 -fPIC -shared -ffp-contract=off -Wall -Wno-unused-variable -Wno-maybe-uninitialized $(INC) $(HOST_SRC) affaction_b200/csrc/abi_common.cpp -ldl -Wl,-Bsymbolic -o $@
+	$(CXX) -O2 -std=c++17 -fPIC -shared -ffp-contract=off -Wall -Wno-unused-variable -Wno-maybe-uninitialized $(INC) $(HOST_SRC) affaction_b200/csrc/abi_common.cpp -ldl -pthread -Wl,-Bsymbolic -o $@
 
 oracle:
 	$(MAKE) -C oracle

@@ -8,6 +8,9 @@
 #include <memory>
 #include <sstream>
 #include <string>
+#include <thread>
+#include <algorithm>
+#include <cstdlib>
 
 #include "ActionBase.h"
 #include "ActionComposite.h"
@@ -232,22 +235,59 @@ int aff_host_batch_add_perturbed(aff_host_batch* b, aff_host_scene* s, const cha
     if (!ob.rigid_body_joints) { g_hostError = "object has no rigid body joints"; return AFF_ERR_INVALID; }
     double q6[6];
     for (int k = 0; k < 6; ++k) q6[k] = s->graph.joints[ob.firstJoint + k].q_init;
-    b->batch.candidates.reserve(b->batch.candidates.size() + n);
-    for (size_t i = 0; i < n; ++i) {
-      uint64_t st = seed0 + i;
-      ActionGet local(*static_cast<ActionGet*>(sols[i % nSol].get()));
-      double p6[6];
-      for (int k = 0; k < 6; ++k) p6[k] = q6[k];
-      p6[0] += uni(st, -0.05, 0.05);
-      p6[1] += uni(st, -0.05, 0.05);
-      const double dz = uni(st, 0.0, 0.02);
-      p6[2] += dz;
-      p6[5] += uni(st, -30.0, 30.0) * (M_PI / 180.0);
-      local.preGraspDist *= uni(st, 0.8, 1.2);
-      local.liftHeight += dz + uni(st, -0.03, 0.03);
-      const double delay = 5.0 * dt;
-      b->batch.append(s->graph, local.createTasks(), local.createTrajectory(delay, local.getDurationHint() + delay), obj, p6);
-      b->commands.push_back(local.getActionCommand());
+    // candidate i depends on (seed0 + i, i mod nSol) only: slices of the index range are described by host
+    // threads into private batches and appended in index order (AFF_HOST_THREADS, default: the hardware
+    // threads, at most 16; below 2048 candidates one thread)
+    auto describe = [&](size_t lo, size_t hi, CandidateBatch& out, std::vector<std::string>& cmds) {
+      out.candidates.reserve(out.candidates.size() + (hi - lo));
+      for (size_t i = lo; i < hi; ++i) {
+        uint64_t st = seed0 + i;
+        ActionGet local(*static_cast<ActionGet*>(sols[i % nSol].get()));
+        double p6[6];
+        for (int k = 0; k < 6; ++k) p6[k] = q6[k];
+        p6[0] += uni(st, -0.05, 0.05);
+        p6[1] += uni(st, -0.05, 0.05);
+        const double dz = uni(st, 0.0, 0.02);
+        p6[2] += dz;
+        p6[5] += uni(st, -30.0, 30.0) * (M_PI / 180.0);
+        local.preGraspDist *= uni(st, 0.8, 1.2);
+        local.liftHeight += dz + uni(st, -0.03, 0.03);
+        const double delay = 5.0 * dt;
+        out.append(s->graph, local.createTasks(), local.createTrajectory(delay, local.getDurationHint() + delay), obj, p6);
+        cmds.push_back(local.getActionCommand());
+      }
+    };
+    size_t nThreads = 1;
+    if (n >= 2048) {
+      const char* env = getenv("AFF_HOST_THREADS");
+      nThreads = env ? (size_t)std::max(1, atoi(env)) : std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency()));
+      nThreads = std::min(nThreads, n / 1024);
+    }
+    if (nThreads <= 1) { describe(0, n, b->batch, b->commands); return (int)n; }
+    std::vector<CandidateBatch> part(nThreads);
+    std::vector<std::vector<std::string>> partCmds(nThreads);
+    std::vector<std::string> errs(nThreads);
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < nThreads; ++t)
+      pool.emplace_back([&, t]() {
+        try { describe(n * t / nThreads, n * (t + 1) / nThreads, part[t], partCmds[t]); }
+        catch (const std::exception& e) { errs[t] = e.what(); if (errs[t].empty()) errs[t] = "error"; }
+      });
+    for (std::thread& th : pool) th.join();
+    for (size_t t = 0; t < nThreads; ++t) if (!errs[t].empty()) { g_hostError = errs[t]; return AFF_ERR_INVALID; }
+    CandidateBatch& B = b->batch;
+    size_t addT = 0, addK = 0;
+    for (const CandidateBatch& p : part) { addT += p.tasks.size(); addK += p.constraints.size(); }
+    B.tasks.reserve(B.tasks.size() + addT); B.constraints.reserve(B.constraints.size() + addK);
+    B.candidates.reserve(B.candidates.size() + n); B.taskNames.reserve(B.taskNames.size() + n); b->commands.reserve(b->commands.size() + n);
+    for (size_t t = 0; t < nThreads; ++t) {
+      const int32_t t0 = (int32_t)B.tasks.size(), k0 = (int32_t)B.constraints.size();
+      B.tasks.insert(B.tasks.end(), part[t].tasks.begin(), part[t].tasks.end());
+      B.constraints.insert(B.constraints.end(), part[t].constraints.begin(), part[t].constraints.end());
+      for (aff_candidate c : part[t].candidates) { c.first_task += t0; c.first_constraint += k0; B.candidates.push_back(c); }
+      for (auto& nm : part[t].taskNames) B.taskNames.push_back(std::move(nm));
+      for (auto& cm : partCmds[t]) b->commands.push_back(std::move(cm));
+      part[t] = CandidateBatch();
     }
     return (int)n;
   } catch (const std::exception& e) {

@@ -373,3 +373,23 @@ def test_graph_from_desc_roundtrip(built):
     for f in ("pizza.affscene", "unittest_predict_many.affscene"):
         s = ab.HostScene(os.path.join(ab.DATA_DIR, f))
         assert ab.lib().aff_host_scene_desc_roundtrip(s.h) == 1
+
+
+def test_perturbed_candidates_do_not_depend_on_the_host_threads(monkeypatch):
+    """aff_host_batch_add_perturbed describes slices of the index range on host threads and appends them in
+    index order: the task / constraint / candidate tables are byte-identical to the single-threaded ones."""
+    import ctypes as C
+    scene = ab.HostScene()
+
+    def tables(threads):
+        monkeypatch.setenv("AFF_HOST_THREADS", str(threads))
+        b = ab.HostBatch(scene)
+        b.add_perturbed("get tomato_sauce_bottle", 7)          # something in front, so that the offsets matter
+        assert b.add_perturbed("get fresh_tomatoes", 5000, seed0=77) == 5000
+        return (b.n_candidates,
+                C.string_at(b.tasks_ptr, b.n_tasks * C.sizeof(ab.TaskDesc)),
+                C.string_at(b.constraints_ptr, b.n_constraints * C.sizeof(ab.Constraint)),
+                C.string_at(b.candidate_ptr(0), b.n_candidates * C.sizeof(ab.Candidate)),
+                [b.command(i) for i in (0, 6, 7, 2600, 5006)] if hasattr(b, "command") else None)
+
+    assert tables(1) == tables(4)
