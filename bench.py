@@ -17,7 +17,8 @@ one batch of ROLLOUTS_PER_GPU candidates per GPU.
           (148 SMs x 1024 rollouts), back to back on one stream.
   e2e   : the same metric through aff_predict_batch with HOST buffers in and out
           (plan compile, H2D of the tables, kernels, D2H of the verdicts), one host
-          thread per variant, timed over all --steps iterations
+          thread per variant running its variant for all --steps iterations back to back
+          (the host work of a call overlaps the kernels of the calls before it)
   roofline: FP64 pipe (the path's bound); flops per rollout COUNTED by
           running the kernel source with a counting scalar (tests/tools/count_flops.py ->
           profiles/flops_per_rollout.json); peak = DFMA rate measured on this GPU in
@@ -244,11 +245,21 @@ def run_cuda(args, rank, local_rank, world):
         for t in th:
             t.join()
 
+    def e2e_stream(i):
+        # one variant, all steps back to back: the host work of a step (plan compile, upload) overlaps the
+        # kernels of the calls before it, as a sweep service that keeps the GPU fed would run it.  Every
+        # step still copies its inputs from host memory and reads its verdicts back, all inside the timed region.
+        for _ in range(args.steps):
+            e2e_call(i)
+
     e2e_step()   # warm-up
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    th = [threading.Thread(target=e2e_stream, args=(i,)) for i in range(len(VARIANTS))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -310,7 +321,7 @@ def run_cuda(args, rank, local_rank, world):
                        "parallelism": "candidates sharded statically over %d GPU(s); NCCL gather of verdicts to rank 0" % world,
                        "verdict_mix_rank0": mix},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": args.steps, "records_equal_resident_arm": bool(e2e_equal),
+                    "steps": args.steps, "steps_overlap": True, "records_equal_resident_arm": bool(e2e_equal),
                     "call": "aff_predict_batch (plan compile + H2D + kernels + D2H, pageable host buffers), one host thread per variant"},
             "gpu_launches": launches * world,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None,
