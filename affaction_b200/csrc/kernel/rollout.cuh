@@ -1160,17 +1160,20 @@ template <class Ctx> AFF_DEV double k_null_space_dH(const Ctx& c, const KJointFr
   return dHv;
 }
 
+AFF_DEV bool k_geo_helper_kind(int kind) { return kind == AFF_TASK_POLAR || kind == AFF_TASK_INCLINATION; }
+
 // ----------------------------------------------------------- the rollout
 // Control block of the block-per-candidate kernel (cta.cuh), in shared memory: warp 0 walks the step
 // loop, the other warps evaluate the collision model of the steps it has finished, a few steps behind.
 #define AFFC_WORKERS 2
 #define AFFC_RING 4
 #define AFFC_TRING 8       // steps the trajectory warp may run ahead
-// warp roles: 0 step loop | 1 .. AFFC_WORKERS collision | AFFC_WORKERS + 1 trajectories | 4 idle | 5 null space.
-// Warps w and w + 4 share a scheduler: the step loop keeps its scheduler to itself (the null-space warp, which
-// also spins on flags, sits beside a collision worker instead).
+// warp roles: 0 step loop | 1 .. AFFC_WORKERS collision | AFFC_WORKERS + 1 trajectories | 5 null space | 7 geometry | 4, 6 idle.
+// Warps w and w + 4 share a scheduler: the step loop keeps its own to itself (a helper spinning on a flag
+// beside it costs it 3 % - measured with the geometry warp as warp 4).
+#define AFFC_GEO_WARP 7
 #define AFFC_NS_WARP 5
-#define AFFC_WARPS 6
+#define AFFC_WARPS 8
 // What the step loop needs from the time-driven part of a step (trajectories, activation points, blending):
 // produced by the trajectory warp, which depends on the rollout only where a task switches on (its
 // trajectory then starts from the current task value).
@@ -1187,6 +1190,7 @@ struct KCtaShared
   int consSeq;               // steps whose graph constraints are applied (chains, object state) and whose start state is final
   int nsSeq;                 // steps whose dH is posted by the null-space warp
   int trkSeq;                // steps whose tracking error is posted by the null-space warp
+  int geoHelpSeq;            // steps whose orientation-task values are written by the geometry warp
   double dH[32];
   double trkDx[32];          // scratch of the tracking error
   KCtaStep ring[AFFC_TRING];
@@ -1670,7 +1674,9 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
     // ---- geometry of the new state; tracking error (:297-337)
     const long long tgeo_ = K_NOW();
     if (CTA) { if (iter > 0) w_wait_ge(&X->trkSeq, iter); }      // the tracking error of the step before has been taken from geo / xcur
-    if (lane < nTasks) k_task_geo(c, c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur);
+    // block-per-candidate: the orientation tasks (acos / atan2 / normalisations: the long branches) are the geometry warp's
+    if (lane < nTasks && !(CTA && k_geo_helper_kind(c.tdesc[8 * lane + TD_KIND]))) k_task_geo(c, c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur);
+    if (CTA) w_wait_ge(&X->geoHelpSeq, iter + 1);
     w_sync();
     K_SUB(12, tgeo_);
     if (CTA) w_post(&X->geoSeq, iter + 2);      // task values of this state are final
@@ -1845,6 +1851,33 @@ AFF_DEV void k_cta_traj(const KPlan& P, int cand, double* sm, const double* xcur
     if (lane < xdim) rec->xdes[lane] = xdes[lane];
     if (lane == 0) { rec->activeMask = activeMask; rec->alphaEff = blending * alpha; rec->phaseScale = aff_sin(AFF_PI * phase); rec->qFilt = qFilt; }
     w_post(&X->trajSeq, iter + 1);
+  }
+}
+
+// Geometry warp of a block-per-candidate launch: the task values of the orientation tasks of the state after
+// step k (frames final once fkSeq > k; geo / xcur rows of the step before free once trkSeq >= k), written into
+// warp 0's slab next to the rows warp 0 computes meanwhile.
+AFF_DEV void k_cta_geometry(const KPlan& P, int cand, double* sm0, KCtaShared* X)
+{
+  KCtx c;
+  c.P = &P; c.C = P.cands + cand; c.sm = sm0; c.lane = w_lane();
+  c.nodes = sm0 + P.o_node;
+  c.chain = (unsigned*)(sm0 + AFFK_O(P, chain));
+  c.tdesc = (int*)(sm0 + AFFK_O(P, tdesc));
+  c.objHasRel = 0u;
+  c.objParentSlot0 = c.objParentSlot1 = 0; c.objParentDynamic0 = c.objParentDynamic1 = 0; c.objChain0 = c.objChain1 = 0u;
+  c.objTree0 = c.objTree1 = -1; c.objMode0 = c.objMode1 = 0;
+  const KCand& C = *c.C;
+  const int lane = c.lane;
+  const int nTasks = ldg(&C.n_tasks);
+  const int taskBase = ldg(&C.first_task);
+  double* geo = sm0 + AFFK_O(P, geo); double* xcur = sm0 + AFFK_O(P, xcur);
+  const int nSteps = ldg(&C.n_steps);
+  for (int iter = 0; iter < nSteps; ++iter) {
+    if (w_wait_ge_or(&X->fkSeq, iter + 1, &X->stop)) return;
+    if (iter > 0) { if (w_wait_ge_or(&X->trkSeq, iter, &X->stop)) return; }
+    if (lane < nTasks && k_geo_helper_kind(c.tdesc[8 * lane + TD_KIND])) k_task_geo(c, c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur);
+    w_post(&X->geoHelpSeq, iter + 1);
   }
 }
 
