@@ -1,4 +1,4 @@
-// One candidate rollout on one warp: the whole of
+// One candidate rollout on one warp (or on one block: see below): the whole of
 //   TrajectoryPredictor::predict     (reference src/TrajectoryPredictor.cpp:79-406)
 //   TrajectoryPredictor::computeIK   (:573-753)
 //   TrajectoryPredictor::checkState  (:756-886)
@@ -11,6 +11,10 @@
 //   J W^-1 J^T ........ one lane per matrix entry; Cholesky one lane per row
 //   forward kinematics  12 lanes per node (one per HTr element), two nodes per round
 //   collision model ... one lane per shape / body pair
+// Block-per-candidate launches (batches of a handful of candidates: k_rollout_t<1>, k_cta_* below) run the
+// same step loop on warp 0 of a block and move what is not on the chain FK -> task values -> Jacobian ->
+// solve -> FK to helper warps (collision model, trajectories, null-space terms and checks, orientation-task
+// values): same expressions, same values, a third of the time per step.
 // Every floating-point expression is written in the order the CPU checker uses
 // (explicit fma(), compiled with -fmad=false), and the few reductions over
 // lanes are order-independent (min / max / ballot) or use the fixed butterfly
