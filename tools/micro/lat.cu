@@ -1,3 +1,4 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -o tools/micro/lat tools/micro/lat.cu ; output of one run: profiles/r2_b200_instruction_latencies.txt
 // Dependent-issue latencies of the instructions the rollout's critical path is made of (one warp, B200).
 #include <cstdio>
 #include <cuda_runtime.h>
