@@ -101,13 +101,14 @@ AFF_ROLLOUT_KERNEL(aff_rollout_kernel_generic, kgeneric)  // anything larger
     NS::KCtaShared* X = (NS::KCtaShared*)(smem + (size_t)(AFFC_WORKERS + 2) * P.warp_doubles);                           \
     for (int cand = blockIdx.x; cand < P.nCands; cand += gridDim.x) {                                                    \
       if (threadIdx.x == 0) {                                                                                            \
-        X->fkSeq = 0; X->stop = 0; X->trajSeq = 0; X->geoSeq = 0; X->consSeq = 0; X->nsSeq = 0; X->trkSeq = 0; X->geoHelpSeq = 0;              \
+        X->fkSeq = 0; X->fk2Seq = 0; X->stop = 0; X->trajSeq = 0; X->geoSeq = 0; X->consSeq = 0; X->nsSeq = 0; X->trkSeq = 0; X->geoHelpSeq = 0;              \
         for (int w = 0; w < AFFC_WORKERS; ++w) { X->copied[w] = 0; X->done[w] = 0; }                                     \
       }                                                                                                                  \
       __syncthreads();                                                                                                   \
       if (warp == 0) NS::template k_rollout_t<1>(P, cand, sm, X);                                                        \
       else if (warp <= AFFC_WORKERS) NS::k_cta_worker(P, cand, sm, smem + P.o_node, X, warp);                            \
       else if (warp == AFFC_WORKERS + 1) NS::k_cta_traj(P, cand, sm, smem + NS::k_xcur_offset(P), X);                    \
+      else if (warp == AFFC_FK_WARP) NS::k_cta_fk(P, cand, smem, X);                                                     \
       else if (warp == AFFC_GEO_WARP) NS::k_cta_geometry(P, cand, smem, X);                                              \
       else if (warp == AFFC_NS_WARP) NS::k_cta_nullspace(P, cand, smem, X);                                              \
       __syncthreads();                                                                                                   \

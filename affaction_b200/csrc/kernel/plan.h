@@ -160,6 +160,7 @@ enum {
 struct KPlan
 {
   int32_t nJ, nDyn, nStatic, nRounds, nObj;
+  int32_t nRoundsCrit;             // FK rounds [0, nRoundsCrit) hold every node the step loop itself reads (plan_build.cpp: critB)
   int32_t nStatNear;               // static bodies [0, nStatNear) take part in the per-step AABB test (not explicit, active)
   uint32_t fk_obj_rounds[2], fk_const_rounds[2];   // bit r: FK round r holds an object node / a constant joint (rounds <= 64)
   int32_t nDynShapes, nDynBodies, nStatShapes, nStatBodies, nTrees;

@@ -142,6 +142,21 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     if (any) { shapeBody[b] = 1; need(b); }
   }
 
+  // ---- bodies whose frames the step loop itself reads (task effectors / reference bodies / frames, null-space
+  // bodies, objects with everything below them, the bodies objects get connected to) and their ancestors: their
+  // nodes come first in the FK schedule, so that the block-per-candidate kernel can leave the rest (fingers, the
+  // parts of the robot no task refers to: only the collision model reads those) to a helper warp.
+  std::vector<char> critB(nB, 0);
+  {
+    auto crit = [&](int b) { for (int a = b; a >= 0 && !critB[a]; a = S.parent[a]) critB[a] = 1; };
+    for (int b : {S.ns_base, S.ns_upperarm[0], S.ns_upperarm[1], S.ns_forearm[0], S.ns_forearm[1], S.ns_hand[0], S.ns_hand[1]}) if (b >= 0) crit(b);
+    for (size_t i = 0; i < nTasksIn; ++i) for (int b : {tasksIn[i].effector, tasksIn[i].ref_body, tasksIn[i].ref_frame}) if (b >= 0 && b < nB) crit(b);
+    for (size_t i = 0; i < nConsIn; ++i) if (consIn[i].kind == AFF_CON_CONNECT && consIn[i].body_b >= 0 && consIn[i].body_b < nB) crit(consIn[i].body_b);
+    for (int b : objBodies) crit(b);
+    for (int b = 0; b < nB; ++b) if (underObj[b]) crit(b);
+  }
+  std::vector<char> nodeCrit;     // per dynamic node
+
   // ---- nodes
   std::vector<int> bodyRef(nB, AFFK_WORLD), jointRef(S.nQ, AFFK_WORLD);
   H.j_node.assign(S.nJ, -1); H.j_type.assign(S.nJ, 0);
@@ -177,7 +192,7 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
       static const double I[12] = {0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1};
       KNode n = mkNode(pRef, AFFK_NODE_OBJECT, I);
       n.qidx = objSlotOfBody[b]; n.under_obj = uo; n.chain = 0u; n.tree = -1;
-      H.dyn.push_back(n);
+      H.dyn.push_back(n); nodeCrit.push_back(1);
       bodyRef[b] = (int)H.dyn.size() - 1;
       continue;
     }
@@ -192,7 +207,7 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
       for (int kk = 0; kk <= k; ++kk) { const int cc = S.jacobi[S.firstJoint[b] + kk]; if (cc >= 0) ch |= 1u << cc; }
       n.chain = uo ? 0u : ch;
       n.tree = uo ? -1 : treeB[b];
-      H.dyn.push_back(n);
+      H.dyn.push_back(n); nodeCrit.push_back(critB[b]);
       cur = (int)H.dyn.size() - 1;
       jointRef[j] = cur;
       if (c >= 0) { H.j_node[c] = cur; H.j_type[c] = S.jtype[j]; }
@@ -204,7 +219,7 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
     if (!alias) {
       KNode n = mkNode(cur, AFFK_NODE_FIXED, &S.A_BP[12 * b]);
       n.under_obj = uo; n.chain = uo ? 0u : chainB[b]; n.tree = uo ? -1 : treeB[b];
-      H.dyn.push_back(n);
+      H.dyn.push_back(n); nodeCrit.push_back(critB[b]);
       cur = (int)H.dyn.size() - 1;
     }
     bodyRef[b] = cur;
@@ -216,19 +231,28 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   {
     const int nD = (int)H.dyn.size();
     std::vector<int> roundOf(nD, 0), fill;
-    for (int n = 0; n < nD; ++n) {
-      int r = 0;
-      const int p = H.dyn[n].parent;
-      if (p >= 0) r = roundOf[p] + 1;
-      // an object may later hang on any dynamic node: schedule it after everything that is not below it
-      if (H.dyn[n].kind == AFFK_NODE_OBJECT) for (int k = 0; k < n; ++k) if (!H.dyn[k].under_obj) r = std::max(r, roundOf[k] + 1);
-      while (true) {
-        if ((int)fill.size() <= r) fill.resize(r + 1, 0);
-        if (fill[r] < 2) break;
-        ++r;
+    // two passes: the nodes the step loop reads (a node's parent is one of them if the node is), then the rest,
+    // which may fill free places of the early rounds
+    int nCritRounds = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int n = 0; n < nD; ++n) {
+        if ((nodeCrit[n] != 0) != (pass == 0)) continue;
+        int r = 0;
+        const int p = H.dyn[n].parent;
+        if (p >= 0) r = roundOf[p] + 1;
+        // an object may later hang on any of the nodes objects get connected to (all in the first pass; a
+        // parent the schedule still computes later makes KPlan::warp_ok zero): after everything earlier that is not below an object
+        if (H.dyn[n].kind == AFFK_NODE_OBJECT) for (int k = 0; k < n; ++k) if (!H.dyn[k].under_obj && nodeCrit[k]) r = std::max(r, roundOf[k] + 1);
+        while (true) {
+          if ((int)fill.size() <= r) fill.resize(r + 1, 0);
+          if (fill[r] < 2) break;
+          ++r;
+        }
+        roundOf[n] = r; fill[r]++;
       }
-      roundOf[n] = r; fill[r]++;
+      if (pass == 0) nCritRounds = (int)fill.size();
     }
+    P.nRoundsCrit = nCritRounds;
     const int nR = (int)fill.size();
     if (nR > AFFK_MAX_ROUNDS) { err = "FK schedule too deep"; return AFF_ERR_CAPACITY; }
     H.rounds.assign(2 * (size_t)nR, -1);

@@ -197,7 +197,8 @@ AFF_DEV void k_object_from_q6(const KCtx& c, int n, int slot)
 
 // RcsGraph_setState for the dynamic nodes: 12 lanes per node (one per HTr element), two nodes
 // per round on the host-built schedule; all parents are shared-memory slots.
-template <int PREFETCH> AFF_DEV void k_fk_t(const KCtx& c, bool init)
+// rounds [r0, r1) of the schedule; r0 == 0 also refreshes sin / cos of the IK joints
+template <int PREFETCH> AFF_DEV void k_fk_t(const KCtx& c, bool init, int r0, int r1)
 {
   const KPlan& P = *c.P;
   double* sn = c.sm + AFFK_O(P, sn); double* cs = c.sm + AFFK_O(P, cs);
@@ -205,19 +206,23 @@ template <int PREFETCH> AFF_DEV void k_fk_t(const KCtx& c, bool init)
   double* nodes = c.nodes;
   const int lane = c.lane;
   const long long tfk_ = K_NOW();
-  if (lane < P.nJ) { double s, co; aff_sincos(q[lane], &s, &co); sn[lane] = s; cs[lane] = co; }
-  w_sync();
+  if (r0 == 0) {
+    if (lane < P.nJ) { double s, co; aff_sincos(q[lane], &s, &co); sn[lane] = s; cs[lane] = co; }
+    w_sync();
+  }
   K_SUB(11, tfk_);
   const int e = lane % 12;
   const int col = (e < 3) ? e : (e - 3) % 3, eo = (e < 3) ? e : 0;
-  const KFkEntry* tab = P.fktab + lane;
-  unsigned constRounds = P.fk_const_rounds[0], objRounds = P.fk_obj_rounds[0];   // bit 0 = this round
+  const KFkEntry* tab = P.fktab + lane + 32 * r0;
+  // bit 0 = this round
+  unsigned constRounds = (r0 < 32) ? P.fk_const_rounds[0] >> r0 : P.fk_const_rounds[1] >> (r0 - 32);
+  unsigned objRounds = (r0 < 32) ? P.fk_obj_rounds[0] >> r0 : P.fk_obj_rounds[1] >> (r0 - 32);
   const int scratchDst = 12 * (P.nDyn + P.nStatPar);      // one spare element behind the node array
   // PREFETCH (block-per-candidate kernel: registers to spare): the entry of the next round is in flight
   // while this round computes (the table has one spare round behind its end)
   KFkEntry nxt;
   if (PREFETCH) nxt = ldg_fk(tab);
-  for (int r = 0; r < P.nRounds; ++r, tab += 32) {
+  for (int r = r0; r < r1; ++r, tab += 32) {
     KFkEntry en;
 #if defined(AFFK_PROFILE) && !defined(AFF_EMULATE)
     const long long tld_ = K_NOW();
@@ -287,7 +292,7 @@ template <int PREFETCH> AFF_DEV void k_fk_t(const KCtx& c, bool init)
   }
 }
 
-AFF_DEV void k_fk(const KCtx& c, bool init) { k_fk_t<0>(c, init); }
+AFF_DEV void k_fk(const KCtx& c, bool init) { k_fk_t<0>(c, init, 0, c.P->nRounds); }
 
 // ------------------------------------------------------------ via-point step
 // One receding-horizon step of a 1-D via-point trajectory (the oracle's
@@ -1172,9 +1177,10 @@ AFF_DEV bool k_geo_helper_kind(int kind) { return kind == AFF_TASK_POLAR || kind
 #define AFFC_WORKERS 2
 #define AFFC_RING 4
 #define AFFC_TRING 8       // steps the trajectory warp may run ahead
-// warp roles: 0 step loop | 1 .. AFFC_WORKERS collision | AFFC_WORKERS + 1 trajectories | 5 null space | 7 geometry | 4, 6 idle.
+// warp roles: 0 step loop | 1 .. AFFC_WORKERS collision | AFFC_WORKERS + 1 trajectories | 5 null space | 6 late FK rounds | 7 geometry | 4 idle.
 // Warps w and w + 4 share a scheduler: the step loop keeps its own to itself (a helper spinning on a flag
 // beside it costs it 3 % - measured with the geometry warp as warp 4).
+#define AFFC_FK_WARP 6
 #define AFFC_GEO_WARP 7
 #define AFFC_NS_WARP 5
 #define AFFC_WARPS 8
@@ -1198,7 +1204,8 @@ struct KCtaShared
   double dH[32];
   double trkDx[32];          // scratch of the tracking error
   KCtaStep ring[AFFC_TRING];
-  int fkSeq;                 // number of steps whose frames are final in warp 0's node array
+  int fkSeq;                 // number of steps whose frames of the rounds [0, nRoundsCrit) are final in warp 0's node array
+  int fk2Seq;                // ... and of the remaining rounds (FK warp): all frames final
   int stop;                  // warp 0 has left the step loop
   int copied[AFFC_WORKERS];  // per worker: steps whose frames it has taken over
   int done[AFFC_WORKERS];    // per worker: steps whose result is posted
@@ -1641,11 +1648,9 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
       }
       w_sync();
       K_MARK(6);
-#if defined(AFFK_PROFILE) && !defined(AFF_EMULATE)
-      if (iter == 100) { const long long tr_ = K_NOW(); for (int rep = 0; rep < 64; ++rep) k_fk_t<CTA>(c, false); K_SUB(14, tr_); K_MARK(15); }
-#endif
-      // integration, FK, collision model, checkState (:730-752)
-      k_fk_t<CTA>(c, false);
+      // integration, FK, collision model, checkState (:730-752); block-per-candidate: the rounds with the frames the
+      // step loop reads, the FK warp does the rest
+      k_fk_t<CTA>(c, false, 0, CTA ? P.nRoundsCrit : P.nRounds);
       K_MARK(7);
       if (!CTA) cm = k_collision(c, r_minDist > 0.001 ? r_minDist : 0.001);
       if (!CTA) {     // (block-per-candidate: the null-space warp checks the new state and adds up its joint-limit cost)
@@ -1764,7 +1769,7 @@ AFF_DEV void k_cta_worker(const KPlan& P, int cand, double* sm, const double* no
   const int nEl = 12 * (P.nDyn + P.nStatPar);
   const int nSteps = ldg(&c.C->n_steps);
   for (int k = w - 1; k < nSteps; k += AFFC_WORKERS) {
-    if (w_wait_ge_or(&X->fkSeq, k + 1, &X->stop)) return;
+    if (w_wait_ge_or(&X->fk2Seq, k + 1, &X->stop)) return;
     for (int i = lane; i < nEl; i += 32) c.nodes[i] = nodes0[i];
     c.objMode0 = X->objState[0]; c.objMode1 = X->objState[1]; c.objTree0 = X->objState[2]; c.objTree1 = X->objState[3];
     w_post(&X->copied[w - 1], k + 1);
@@ -1855,6 +1860,28 @@ AFF_DEV void k_cta_traj(const KPlan& P, int cand, double* sm, const double* xcur
     if (lane < xdim) rec->xdes[lane] = xdes[lane];
     if (lane == 0) { rec->activeMask = activeMask; rec->alphaEff = blending * alpha; rec->phaseScale = aff_sin(AFF_PI * phase); rec->qFilt = qFilt; }
     w_post(&X->trajSeq, iter + 1);
+  }
+}
+
+// FK warp of a block-per-candidate launch: the rounds [nRoundsCrit, nRounds) of the FK schedule (frames only the
+// collision model reads: fingers, parts of the robot no task refers to), in warp 0's node array, once warp 0
+// has the early rounds of the step and the collision worker of the step before has taken its copy.
+AFF_DEV void k_cta_fk(const KPlan& P, int cand, double* sm0, KCtaShared* X)
+{
+  KCtx c;
+  c.P = &P; c.C = P.cands + cand; c.sm = sm0; c.lane = w_lane();
+  c.nodes = sm0 + P.o_node;
+  c.chain = (unsigned*)(sm0 + AFFK_O(P, chain));
+  c.tdesc = (int*)(sm0 + AFFK_O(P, tdesc));
+  c.objHasRel = 0u;      // (objects and what hangs below them are in the early rounds)
+  c.objParentSlot0 = c.objParentSlot1 = 0; c.objParentDynamic0 = c.objParentDynamic1 = 0; c.objChain0 = c.objChain1 = 0u;
+  c.objTree0 = c.objTree1 = -1; c.objMode0 = c.objMode1 = 0;
+  const int nSteps = ldg(&c.C->n_steps);
+  for (int iter = 0; iter < nSteps; ++iter) {
+    if (w_wait_ge_or(&X->fkSeq, iter + 1, &X->stop)) return;
+    if (iter > 0) { if (w_wait_ge_or(&X->copied[(iter - 1) % AFFC_WORKERS], iter, &X->stop)) return; }
+    k_fk_t<1>(c, false, P.nRoundsCrit, P.nRounds);
+    w_post(&X->fk2Seq, iter + 1);
   }
 }
 

@@ -149,6 +149,7 @@ static int emu_run(int sweep, const aff_scene_desc* scene, const aff_task_desc* 
         if (w == 0) k_rollout_t<1>(P, (int)i, slab, &X);
         else if (w <= AFFC_WORKERS) k_cta_worker(P, (int)i, slab, sm.data() + P.o_node, &X, w);
         else if (w == AFFC_WORKERS + 1) k_cta_traj(P, (int)i, slab, sm.data() + k_xcur_offset(P), &X);
+        else if (w == AFFC_FK_WARP) k_cta_fk(P, (int)i, sm.data(), &X);
         else if (w == AFFC_GEO_WARP) k_cta_geometry(P, (int)i, sm.data(), &X);
         else if (w == AFFC_NS_WARP) k_cta_nullspace(P, (int)i, sm.data(), &X);
       });
@@ -163,8 +164,8 @@ static int emu_run(int sweep, const aff_scene_desc* scene, const aff_task_desc* 
     out[i] = results[i];
   }
   if (getenv("AFF_EMU_VERBOSE"))
-    std::fprintf(stderr, "emu: nDyn %d nStatic %d rounds %d dynShapes %d dynBodies %d statBodies %d pairs SS %d SB %d warp smem %zu B\n",
-                 P.nDyn, P.nStatic, P.nRounds, P.nDynShapes, P.nDynBodies, P.nStatBodies, P.nSS, P.nSB, H.smemBytesPerWarp);
+    std::fprintf(stderr, "emu: nDyn %d nStatic %d rounds %d (%d for the step loop) dynShapes %d dynBodies %d statBodies %d pairs SS %d SB %d warp smem %zu B\n",
+                 P.nDyn, P.nStatic, P.nRounds, P.nRoundsCrit, P.nDynShapes, P.nDynBodies, P.nStatBodies, P.nSS, P.nSB, H.smemBytesPerWarp);
   return AFF_OK;
 }
 
