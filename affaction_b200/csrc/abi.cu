@@ -51,9 +51,79 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(AFF_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
 // ------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(32) aff_prologue_kernel(const KPlan P)
+// Once per batch: world transforms of the static nodes, world frames / segments / AABBs of the static
+// shapes, sin / cos of the constant joints.  One block; the static nodes go a tree level at a time, two nodes per
+// warp and pass (12 lanes per node, as the FK of the step loop), the rest one item per thread.  Same
+// operations per node as k_prologue (rollout.cuh: one warp, node after node; the CPU emulator runs that one).
+#define AFF_PROLOGUE_THREADS 512
+__global__ void __launch_bounds__(AFF_PROLOGUE_THREADS) aff_prologue_kernel(const KPlan P)
 {
-  kgeneric::k_prologue(P);
+  const int tid = threadIdx.x, nT = blockDim.x, lane = tid & 31, warp = tid >> 5, nW = nT >> 5;
+  for (int n = tid; n < P.nStatic; n += nT) {
+    double s = 0.0, co = 1.0;
+    if (P.stat[n].kind == AFFK_NODE_JOINT_CONST && P.stat[n].jtype >= AFF_JNT_ROT_X) aff_sincos(P.stat[n].qconst, &s, &co);
+    P.statSC[2 * n] = s; P.statSC[2 * n + 1] = co;
+  }
+  for (int n = tid; n < P.nDyn; n += nT) {
+    double s = 0.0, co = 1.0;
+    if (P.dyn[n].kind == AFFK_NODE_JOINT_CONST && P.dyn[n].jtype >= AFF_JNT_ROT_X) aff_sincos(P.dyn[n].qconst, &s, &co);
+    P.dynSC[2 * n] = s; P.dynSC[2 * n + 1] = co;
+  }
+  if (tid < 12) P.statA[12 * P.nStatic + tid] = (tid == 3 || tid == 7 || tid == 11) ? 1.0 : 0.0;
+  __syncthreads();
+  const int grp = lane / 12, e = lane % 12;      // lanes 24 .. 31 idle (they take part in the shuffle only)
+  for (int l = 0; l < P.nStatLevels; ++l) {
+    const int lo = P.stat_level_off[l], hi = P.stat_level_off[l + 1];
+    for (int base = lo + 2 * warp; base < hi; base += 2 * nW) {
+      const int idx = base + grp;
+      const bool on = grp < 2 && idx < hi;
+      const int n = P.stat_order[on ? idx : lo];
+      const KNode* nd = P.stat + n;
+      const int par = nd->parent;
+      const double* Pp = (par == AFFK_WORLD) ? P.statA + 12 * P.nStatic : P.statA + 12 * AFFK_STATIC_IDX(par);
+      double val = nd->identityT ? Pp[e] : kgeneric::k_compose_elem(nd->T, Pp, e);
+      int partner = e, isA = 0, isB = 0;
+      const int kind = nd->kind, jt = nd->jtype;
+      if (kind == AFFK_NODE_JOINT_CONST) {
+        if (jt >= AFF_JNT_ROT_X && e >= 3) {
+          const int d = jt - AFF_JNT_ROT_X, a = (d + 1) % 3, b = (d + 2) % 3, row = (e - 3) / 3, col = (e - 3) % 3;
+          if (row == a) { isA = 1; partner = 3 + 3 * b + col; } else if (row == b) { isB = 1; partner = 3 + 3 * a + col; }
+        } else if (jt < AFF_JNT_ROT_X && e < 3) partner = 3 + 3 * jt + e;
+      }
+      const double other = __shfl_sync(0xffffffffu, val, (grp < 2 ? 12 * grp : 0) + partner);
+      if (kind == AFFK_NODE_JOINT_CONST) {
+        const double s = P.statSC[2 * n], co = P.statSC[2 * n + 1];
+        if (jt >= AFF_JNT_ROT_X) { if (isA) val = fma(s, other, co * val); else if (isB) val = fma(co, val, -(s * other)); }
+        else if (e < 3) val = fma(nd->qconst, other, val);
+      }
+      if (on) P.statA[12 * n + e] = val;
+    }
+    __syncthreads();
+  }
+  for (int s = tid; s < P.nStatShapes; s += nT) {
+    const KShape* sh = P.sshape + s;
+    const int ref = sh->node;
+    const double* An = (ref == AFFK_WORLD) ? P.statA + 12 * P.nStatic : P.statA + 12 * AFFK_STATIC_IDX(ref);
+    double W[12];
+    kgeneric::k_compose(W, sh->A_CB, An);
+    for (int k = 0; k < 12; ++k) P.sshapeA[12 * s + k] = W[k];
+    const bool ssl = sh->type == AFF_SHAPE_SSL;
+    for (int k = 0; k < 3; ++k) { P.sseg[8 * s + k] = W[k]; P.sseg[8 * s + 3 + k] = ssl ? sh->ext[2] * W[9 + k] : 0.0; }
+    P.sseg[8 * s + 6] = sh->ext[0]; P.sseg[8 * s + 7] = sh->bound;
+  }
+  __syncthreads();
+  for (int b = tid; b < P.nStatBodies; b += nT) {
+    const KShapeBody* sb = P.sbody + b;
+    double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    for (int k = 0; k < sb->n_shapes; ++k) {
+      const KShape* sh = P.sshape + sb->first_shape + k;
+      if (!sh->active0) continue;
+      double smn[3], smx[3];
+      kgeneric::k_shape_aabb(sh->type, sh->ext, P.sshapeA + 12 * (sb->first_shape + k), smn, smx);
+      for (int q = 0; q < 3; ++q) { if (smn[q] < mn[q]) mn[q] = smn[q]; if (smx[q] > mx[q]) mx[q] = smx[q]; }
+    }
+    for (int q = 0; q < 3; ++q) { P.sbodyAABB[6 * b + q] = mn[q]; P.sbodyAABB[6 * b + 3 + q] = mx[q]; }
+  }
 }
 
 // Persistent rollout kernel: one warp per candidate, warps stride over the batch.
@@ -184,7 +254,7 @@ struct aff_batch
   KPlan plan{};
   DevBuf<double> jq_init, jq0, jq_min, jq_max, jspeed, jacc, jwjl, jwmetric, obj_q6, statA, statSC, dynSC, sshapeA, sbodyAABB, qlog;
   DevBuf<KFkEntry> fktab;
-  DevBuf<int32_t> j_node, j_type, statpar_ref, obj_parent_slot, obj_parent_tree, dyn_under, obj_node, obj_body, dyn_pslot, sweep_order, node_shape_off, node_shape_idx, dyn_store;
+  DevBuf<int32_t> j_node, j_type, statpar_ref, obj_parent_slot, obj_parent_tree, dyn_under, obj_node, obj_body, dyn_pslot, sweep_order, node_shape_off, node_shape_idx, dyn_store, stat_order, stat_level_off;
   DevBuf<uint32_t> dyn_chain;
   DevBuf<double> dynT, dynQ;
   DevBuf<KPair> pairsSS, pairsSB;
@@ -205,7 +275,7 @@ struct aff_batch
     jq_init.release(); jq0.release(); jq_min.release(); jq_max.release(); jspeed.release(); jacc.release(); jwjl.release();
     jwmetric.release(); obj_q6.release(); statA.release(); statSC.release(); dynSC.release(); sshapeA.release();
     sbodyAABB.release(); qlog.release(); j_node.release(); j_type.release(); fktab.release(); statpar_ref.release(); obj_parent_slot.release(); obj_parent_tree.release(); dyn_under.release(); dyn_chain.release(); dynT.release(); dynQ.release(); pairsSS.release(); pairsSB.release(); sseg.release();
-    obj_node.release(); obj_body.release(); dyn_pslot.release(); sweep_order.release(); node_shape_off.release(); node_shape_idx.release(); dyn_store.release(); dyn.release(); stat.release(); dshape.release(); sshape.release();
+    obj_node.release(); obj_body.release(); dyn_pslot.release(); sweep_order.release(); node_shape_off.release(); node_shape_idx.release(); dyn_store.release(); stat_order.release(); stat_level_off.release(); dyn.release(); stat.release(); dshape.release(); sshape.release();
     dbody.release(); sbody.release(); tasks.release(); vias.release(); acts.release(); gcons.release(); cands.release();
     results.release();
   }
@@ -257,7 +327,7 @@ static int uploadBatch(aff_batch* b, cudaStream_t st)
   P = H.plan;
 #define UP(name) do { CUDA_TRY(b->name.upload(H.name, st)); b->h2dBytes += H.name.size() * sizeof(H.name[0]); } while (0)
   UP(jq_init); UP(jq0); UP(jq_min); UP(jq_max); UP(jspeed); UP(jacc); UP(jwjl); UP(jwmetric); UP(obj_q6);
-  UP(j_node); UP(j_type); UP(fktab); UP(statpar_ref); UP(obj_parent_slot); UP(obj_parent_tree); UP(dyn_under); UP(dyn_chain); UP(dynT); UP(dynQ); UP(pairsSS); UP(pairsSB); UP(obj_node); UP(obj_body); UP(dyn_pslot); UP(sweep_order); UP(node_shape_off); UP(node_shape_idx); UP(dyn_store);
+  UP(j_node); UP(j_type); UP(fktab); UP(statpar_ref); UP(obj_parent_slot); UP(obj_parent_tree); UP(dyn_under); UP(dyn_chain); UP(dynT); UP(dynQ); UP(pairsSS); UP(pairsSB); UP(obj_node); UP(obj_body); UP(dyn_pslot); UP(sweep_order); UP(node_shape_off); UP(node_shape_idx); UP(dyn_store); UP(stat_order); UP(stat_level_off);
   UP(dyn); UP(stat); UP(dshape); UP(sshape); UP(dbody); UP(sbody);
   UP(tasks); UP(vias); UP(acts); UP(gcons); UP(cands);
 #undef UP
@@ -280,7 +350,7 @@ static int uploadBatch(aff_batch* b, cudaStream_t st)
   P.jacc = b->jacc.p; P.jwjl = b->jwjl.p; P.jwmetric = b->jwmetric.p; P.j_node = b->j_node.p; P.j_type = b->j_type.p;
   P.dyn = b->dyn.p; P.stat = b->stat.p; P.statA = b->statA.p; P.statSC = b->statSC.p; P.dynSC = b->dynSC.p; P.fktab = b->fktab.p; P.statpar_ref = b->statpar_ref.p; P.obj_parent_slot = b->obj_parent_slot.p; P.obj_parent_tree = b->obj_parent_tree.p; P.dyn_under = b->dyn_under.p; P.dyn_chain = b->dyn_chain.p; P.dynT = b->dynT.p; P.dynQ = b->dynQ.p;
   P.dshape = b->dshape.p; P.dbody = b->dbody.p; P.sshape = b->sshape.p; P.sbody = b->sbody.p; P.sshapeA = b->sshapeA.p;
-  P.sbodyAABB = b->sbodyAABB.p; P.pairsSS = b->pairsSS.p; P.pairsSB = b->pairsSB.p; P.sseg = b->sseg.p; P.obj_node = b->obj_node.p; P.obj_body = b->obj_body.p; P.obj_q6 = b->obj_q6.p; P.dyn_pslot = b->dyn_pslot.p; P.sweep_order = b->sweep_order.p; P.node_shape_off = b->node_shape_off.p; P.node_shape_idx = b->node_shape_idx.p; P.dyn_store = b->dyn_store.p;
+  P.sbodyAABB = b->sbodyAABB.p; P.pairsSS = b->pairsSS.p; P.pairsSB = b->pairsSB.p; P.sseg = b->sseg.p; P.obj_node = b->obj_node.p; P.obj_body = b->obj_body.p; P.obj_q6 = b->obj_q6.p; P.dyn_pslot = b->dyn_pslot.p; P.sweep_order = b->sweep_order.p; P.node_shape_off = b->node_shape_off.p; P.node_shape_idx = b->node_shape_idx.p; P.dyn_store = b->dyn_store.p; P.stat_order = b->stat_order.p; P.stat_level_off = b->stat_level_off.p;
   P.tasks = b->tasks.p; P.vias = b->vias.p; P.acts = b->acts.p; P.gcons = b->gcons.p; P.cands = b->cands.p;
   P.results = b->results.p;
   return AFF_OK;
@@ -423,7 +493,7 @@ int aff_batch_launch(aff_batch* b, void* stream)
   b->launches = 0;
   b->lastStream = st; b->launched = true;
   if (!b->prologueDone) {
-    aff_prologue_kernel<<<1, 32, 0, st>>>(b->plan);
+    aff_prologue_kernel<<<1, AFF_PROLOGUE_THREADS, 0, st>>>(b->plan);
     CUDA_TRY(cudaGetLastError());
     b->prologueDone = true;
     b->launches++;

@@ -183,6 +183,9 @@ struct KPlan
   const double* dynT;              // [nDyn*12] fixed transform of each dynamic node
   const double* dynQ;              // [nDyn] value of constant joints
   const int32_t* statpar_ref;      // [nStatPar] static nodes copied into shared memory as parents
+  const int32_t* stat_order;       // [nStatic] static nodes sorted by depth below the world frame (prologue: one level at a time)
+  const int32_t* stat_level_off;   // [nStatLevels + 1] level l = stat_order[stat_level_off[l] .. stat_level_off[l + 1])
+  int32_t nStatLevels;
   const int32_t* obj_parent_slot;  // [nObj] initial parent slot of each object
   const int32_t* obj_parent_tree;  // [nObj] broad-phase tree of that parent
   const uint32_t* dyn_chain;       // [nDyn] IK joints moving each dynamic node by construction

@@ -703,6 +703,24 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
 
   // ---- scalars
   P.nJ = S.nJ; P.nDyn = (int)H.dyn.size(); P.nStatic = (int)H.stat.size(); P.nObj = nObj;
+  {
+    // static nodes by depth (parents come first in H.stat): the prologue computes a level at a time
+    const int nS = (int)H.stat.size();
+    std::vector<int> level(nS, 0);
+    int nLev = nS ? 1 : 0;
+    for (int n = 0; n < nS; ++n) {
+      const int par = H.stat[n].parent;
+      level[n] = (par == AFFK_WORLD) ? 0 : level[AFFK_STATIC_IDX(par)] + 1;
+      nLev = std::max(nLev, level[n] + 1);
+    }
+    H.stat_level_off.assign((size_t)nLev + 1, 0);
+    for (int n = 0; n < nS; ++n) H.stat_level_off[(size_t)level[n] + 1]++;
+    for (int l = 0; l < nLev; ++l) H.stat_level_off[(size_t)l + 1] += H.stat_level_off[(size_t)l];
+    H.stat_order.assign((size_t)std::max(nS, 1), 0);
+    std::vector<int> fillAt(H.stat_level_off.begin(), H.stat_level_off.end() - (nLev ? 1 : 0));
+    for (int n = 0; n < nS; ++n) H.stat_order[(size_t)fillAt[(size_t)level[n]]++] = n;
+    P.nStatLevels = nLev;
+  }
   P.nDynShapes = (int)H.dshape.size(); P.nDynBodies = (int)H.dbody.size();
   P.nStatShapes = (int)H.sshape.size(); P.nStatBodies = (int)H.sbody.size();
   P.nTrees = (int)S.bpTree.size(); P.nSS = (int)H.pairsSS.size(); P.nSB = (int)H.pairsSB.size();

@@ -33,7 +33,7 @@ struct HostPlan
   KPlan plan{};
   std::vector<double> jq_init, jq0, jq_min, jq_max, jspeed, jacc, jwjl, jwmetric, obj_q6;
   std::vector<KFkEntry> fktab;
-  std::vector<int32_t> j_node, j_type, rounds, statpar_ref, obj_parent_slot, obj_parent_tree, dyn_under, obj_node, obj_body, dyn_pslot, sweep_order, roundOf, node_shape_off, node_shape_idx, dyn_store;
+  std::vector<int32_t> j_node, j_type, rounds, statpar_ref, obj_parent_slot, obj_parent_tree, dyn_under, obj_node, obj_body, dyn_pslot, sweep_order, roundOf, node_shape_off, node_shape_idx, dyn_store, stat_order, stat_level_off;
   std::vector<uint32_t> dyn_chain;
   std::vector<double> dynT, dynQ;
   std::vector<KPair> pairsSS, pairsSB;
