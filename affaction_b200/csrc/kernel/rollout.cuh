@@ -58,9 +58,6 @@ __device__ unsigned long long g_kClocks[16];
 #define K_SUB(i, t0_) do { } while (0)
 #define K_NOW() 0ll
 #endif
-#ifndef AFFK_ABL
-#define AFFK_ABL 0
-#endif
 #define AFFK_TRACK_MAX 0.05      // MAX_TRACKING_ERROR, src/TrajectoryPredictor.cpp:50
 #define AFFK_TRAJ_EPS 1.0e-8
 #define AFFK_NO_LIMIT 1.0e300
@@ -224,15 +221,8 @@ template <int PREFETCH> AFF_DEV void k_fk_t(const KCtx& c, bool init, int r0, in
   if (PREFETCH) nxt = ldg_fk(tab);
   for (int r = r0; r < r1; ++r, tab += 32) {
     KFkEntry en;
-#if defined(AFFK_PROFILE) && !defined(AFF_EMULATE)
-    const long long tld_ = K_NOW();
-#endif
     if (PREFETCH) { en = nxt; nxt = ldg_fk(tab + 32); }
     else en = ldg_fk(tab);
-#if defined(AFFK_PROFILE) && !defined(AFF_EMULATE)
-    asm volatile("" :: "r"(en.w0), "r"(en.w1));
-    K_SUB(13, tld_);
-#endif
     const int op = (int)((en.w0 >> 24) & 7u);
     const int pbase = (int)(en.w0 & 4095u);               // parent node (0 for lanes that do not compose)
     int dst = (int)((en.w0 >> 12) & 4095u);                // idle lanes: the spare element
@@ -251,7 +241,6 @@ template <int PREFETCH> AFF_DEV void k_fk_t(const KCtx& c, bool init, int r0, in
     double val = (op == FKOP_COPY) ? x : (compose ? comp : 0.0);
     double s = x, co = cs[qi];
     if (r == 32) { constRounds = P.fk_const_rounds[1]; objRounds = P.fk_obj_rounds[1]; }
-#if AFFK_ABL != 1
     if (constRounds & 1u) {
       if (op > FKOP_FIXED && op <= FKOP_TRANS && (en.w1 & 0x80u)) {
         const int n = (int)((en.w1 >> 8) & 255u);
@@ -259,8 +248,6 @@ template <int PREFETCH> AFF_DEV void k_fk_t(const KCtx& c, bool init, int r0, in
         co = ldg(&P.dynSC[2 * n + 1]);
       }
     }
-#endif
-#if AFFK_ABL != 2
     if (objRounds & 1u) {
       if (op == FKOP_OBJECT) {
         const int slot = (int)(en.w1 & 3u), n = (int)((en.w1 >> 8) & 255u);
@@ -276,19 +263,12 @@ template <int PREFETCH> AFF_DEV void k_fk_t(const KCtx& c, bool init, int r0, in
         }
       }
     }
-#endif
-#if AFFK_ABL == 3
-    const double other = val;
-#else
     const double other = w_shfl(val, partner);
-#endif
     const double rotA = fma(s, other, co * val), rotB = fma(co, val, -(s * other)), trn = fma(s, other, val);
     val = (op == FKOP_ROT_A) ? rotA : ((op == FKOP_ROT_B) ? rotB : ((op == FKOP_TRANS) ? trn : val));
     nodes[dst] = val;
     constRounds >>= 1; objRounds >>= 1;
-#if AFFK_ABL != 4
     w_sync();
-#endif
   }
 }
 

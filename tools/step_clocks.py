@@ -28,6 +28,5 @@ tot = sum(out[i] for i in range(11))
 print("%s kernel %s n=%d: %.1f ms, %d steps, %.0f cycles/step" % (cmd, dev.kernel, n, ms, steps, tot / steps))
 for i, nm in enumerate(names):
     print("  %-36s %6.1f %%   %8.0f cycles/step" % (nm, 100.0 * out[i] / tot, out[i] / steps))
-for i, nm in ((11, "  FK: sincos"), (12, "  task geo only"), (13, "  FK: table loads")):
+for i, nm in ((11, "  FK: sincos"), (12, "  task geo only")):
     print("  %-36s %6.1f %%   %8.0f cycles/step" % (nm, 100.0 * out[i] / tot, out[i] / steps))
-print("  FK repeated 64 times back to back at step 100: %.0f cycles per call" % (out[14] / 64.0))
