@@ -483,6 +483,54 @@ template <class Ctx> AFF_DEV void k_task_geo(const Ctx& c, const int* td, const 
   }
 }
 
+// The two orientation kinds of k_task_geo for a whole warp at once (geometry warp of the block-per-candidate
+// kernel): lanes gather their vectors, then every lane runs ONE normalisation (sqrt, three divisions) and ONE
+// acos together instead of one branch after the other; expression by expression the same as k_task_geo.
+// on: this lane has a POLAR or Inclination task (td valid).
+template <class Ctx> AFF_DEV void k_task_geo_orient(const Ctx& c, const int* td, double* geo, double* xcur, bool on)
+{
+  const int kind = on ? td[TD_KIND] : -1;
+  const bool polar = kind == AFF_TASK_POLAR, incl = kind == AFF_TASK_INCLINATION;
+  const int eff = on ? td[TD_EFF] : 0, ref = on ? td[TD_REF] : -1, axis = on ? td[TD_AXIS] : 0, xoff = on ? td[TD_XOFF] : 0;
+  const double* Ae = k_slot(c, eff);
+  const double* aI = Ae + 3 + 3 * axis;
+  double a[3] = {0.0, 0.0, 1.0}, v[3] = {0.0, 0.0, 1.0}, w[3] = {1.0, 0.0, 0.0};
+  double acArg = 0.0;
+  if (polar) {
+    if (ref >= 0) k_mulv(a, k_slot(c, ref) + 3, aI);
+    else { a[0] = aI[0]; a[1] = aI[1]; a[2] = aI[2]; }
+    // k_tangent_basis up to its normalisation
+    int k = 0;
+    double m = fabs(a[0]);
+    if (fabs(a[1]) < m) { k = 1; m = fabs(a[1]); }
+    if (fabs(a[2]) < m) { k = 2; }
+    const double ak = k_sel3(a, k);
+    for (int i = 0; i < 3; ++i) { const double ti = -(ak * a[i]); w[i] = (i == k) ? ti + 1.0 : ti; }
+    acArg = a[2];
+  } else if (incl) {
+    for (int i = 0; i < 3; ++i) a[i] = aI[i];
+    if (ref >= 0) { const double* z = k_slot(c, ref) + 3 + 6; v[0] = z[0]; v[1] = z[1]; v[2] = z[2]; }
+    k_cross(w, v, a);
+    acArg = k_dot(a, v);
+  }
+  const double nn = sqrt(k_dot(w, w));
+  const double w0 = w[0] / nn, w1 = w[1] / nn, w2 = w[2] / nn;
+  const double ac = aff_acos(acArg);
+  if (polar) {
+    const double e1[3] = {w0, w1, w2};
+    double e2[3];
+    k_cross(e2, a, e1);
+    for (int i = 0; i < 3; ++i) { geo[i] = a[i]; geo[3 + i] = e1[i]; geo[6 + i] = e2[i]; geo[9 + i] = Ae[i]; }
+    xcur[xoff] = ac;
+    xcur[xoff + 1] = aff_atan2(a[1], a[0]);
+  } else if (incl) {
+    const bool ok = nn > 1.0e-8;
+    const double n[3] = {ok ? w0 : 0.0, ok ? w1 : 0.0, ok ? w2 : 0.0};
+    for (int i = 0; i < 3; ++i) { geo[i] = a[i]; geo[3 + i] = v[i]; geo[6 + i] = n[i]; geo[9 + i] = Ae[i]; }
+    xcur[xoff] = ac;
+  }
+}
+
 AFF_DEV double k_region_dx(const KTask* tk, double e)
 {
   if (!ldg(&tk->has_region)) return e;
@@ -1887,7 +1935,10 @@ AFF_DEV void k_cta_geometry(const KPlan& P, int cand, double* sm0, KCtaShared* X
   for (int iter = 0; iter < nSteps; ++iter) {
     if (w_wait_ge_or(&X->fkSeq, iter + 1, &X->stop)) return;
     if (iter > 0) { if (w_wait_ge_or(&X->trkSeq, iter, &X->stop)) return; }
-    if (lane < nTasks && k_geo_helper_kind(c.tdesc[8 * lane + TD_KIND])) k_task_geo(c, c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur);
+    {
+      const bool on = lane < nTasks && k_geo_helper_kind(c.tdesc[8 * (lane < nTasks ? lane : 0) + TD_KIND]);
+      k_task_geo_orient(c, c.tdesc + 8 * (on ? lane : 0), geo + AFFK_GEO * (on ? lane : 0), xcur, on);
+    }
     w_post(&X->geoHelpSeq, iter + 1);
   }
 }
