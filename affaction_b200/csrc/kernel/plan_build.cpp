@@ -728,6 +728,21 @@ int buildPlan(const SceneModel& S, const aff_task_desc* tasksIn, size_t nTasksIn
   for (const KNode& nd : H.dyn) { H.dyn_chain.push_back(nd.chain); H.dyn_under.push_back(nd.under_obj); }
   P.ns_base = refOf(S.ns_base);
   for (int k = 0; k < 2; ++k) { P.ns_upperarm[k] = refOf(S.ns_upperarm[k]); P.ns_forearm[k] = refOf(S.ns_forearm[k]); P.ns_hand[k] = refOf(S.ns_hand[k]); }
+  {
+    // Guard of the FK split of the block-per-candidate kernel: every frame the step loop reads (task effector /
+    // reference / frame slots, null-space bodies, objects, the nodes objects get connected to) must come out of
+    // the early rounds; if one does not, the step loop keeps all rounds (correct, only slower).
+    const int nD = (int)H.dyn.size();
+    auto late = [&](int slot) { return slot >= 0 && slot < nD && H.roundOf[slot] >= P.nRoundsCrit; };
+    bool ok = true;
+    for (const KTask& t : H.tasks) ok = ok && !late(t.eff) && !late(t.ref) && !late(t.frame);
+    for (const KGraphCon& g : H.gcons) ok = ok && !late(g.parent_slot);
+    for (int32_t on : H.obj_node) ok = ok && !late(on);
+    for (int n = 0; n < nD; ++n) if (H.dyn[n].under_obj) ok = ok && !late(n);
+    ok = ok && !late(P.ns_base);
+    for (int k = 0; k < 2; ++k) ok = ok && !late(P.ns_upperarm[k]) && !late(P.ns_forearm[k]) && !late(P.ns_hand[k]);
+    if (!ok) P.nRoundsCrit = P.nRounds;
+  }
   P.rbj_static_chain = rbjStatic;
   P.bp_threshold = S.bpThreshold;
   P.nCands = (int)nCands;
