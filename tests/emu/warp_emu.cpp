@@ -176,6 +176,22 @@ extern "C" int emu_predict_batch(const aff_scene_desc* scene, const aff_task_des
   return emu_run(0, scene, tasks, nTasks, cons, nCons, cands, nCands, opts, out, qlog, qlogRows, errbuf, errlen);
 }
 
+// plan compiler only: {nDyn, nRounds, nRoundsCrit, warp_ok, sweep_ok, nStatLevels}; and, per dynamic node, its FK round
+extern "C" int emu_plan_info(const aff_scene_desc* scene, const aff_task_desc* tasks, size_t nTasks,
+                             const aff_constraint* cons, size_t nCons, const aff_candidate* cands, size_t nCands,
+                             const aff_opts* opts, int* info, int* roundOf, size_t nRoundOf, int* parentOf)
+{
+  affk::SceneModel model;
+  std::string e = model.init(scene);
+  affk::HostPlan H;
+  if (!e.empty()) return AFF_ERR_INVALID;
+  const int rc = affk::buildPlan(model, tasks, nTasks, cons, nCons, cands, nCands, *opts, H, e);
+  if (rc != AFF_OK) return rc;
+  info[0] = H.plan.nDyn; info[1] = H.plan.nRounds; info[2] = H.plan.nRoundsCrit; info[3] = H.plan.warp_ok; info[4] = H.plan.sweep_ok; info[5] = H.plan.nStatLevels;
+  for (size_t n = 0; n < H.roundOf.size() && n < nRoundOf; ++n) { roundOf[n] = H.roundOf[n]; parentOf[n] = H.dyn[n].parent; }
+  return AFF_OK;
+}
+
 // the block-per-candidate arrangement (warp 0 + collision workers) on the CPU
 extern "C" int emu_predict_batch_cta(const aff_scene_desc* scene, const aff_task_desc* tasks, size_t nTasks,
                                      const aff_constraint* cons, size_t nCons, const aff_candidate* cands, size_t nCands,

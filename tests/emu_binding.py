@@ -25,6 +25,8 @@ def emu_lib():
         _lib.emu_predict_batch_sweep.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, vp, vp, sz, vp, sz]
         _lib.emu_predict_batch_cta.restype = C.c_int
         _lib.emu_predict_batch_cta.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, vp, vp, sz, vp, sz]
+        _lib.emu_plan_info.restype = C.c_int
+        _lib.emu_plan_info.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, vp, vp, sz, vp]
         _lib.emu_count_flops.restype = C.c_int
         _lib.emu_count_flops.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp, sz]
     return _lib
@@ -64,3 +66,18 @@ def count_flops(scene, batch, opts, first=0, count=None):
     if rc != 0:
         raise RuntimeError("emu_count_flops failed (%d): %s" % (rc, err.value.decode()))
     return list(res), counts
+
+
+def plan_info(scene, batch, opts):
+    """What the plan compiler made of a batch: dict(n_dyn, n_rounds, n_rounds_crit, warp_ok, sweep_ok,
+    n_stat_levels, round_of=[...], parent_of=[...]) (FK schedule of the warp / block kernels)."""
+    info = (C.c_int * 8)()
+    rnd = (C.c_int * 256)()
+    par = (C.c_int * 256)()
+    rc = emu_lib().emu_plan_info(scene.desc, batch.tasks_ptr, batch.n_tasks, batch.constraints_ptr, batch.n_constraints,
+                                 batch.candidate_ptr(0), batch.n_candidates, C.byref(opts), info, rnd, 256, par)
+    if rc != 0:
+        raise RuntimeError("emu_plan_info failed (%d)" % rc)
+    n = info[0]
+    return dict(n_dyn=n, n_rounds=info[1], n_rounds_crit=info[2], warp_ok=info[3], sweep_ok=info[4], n_stat_levels=info[5],
+                round_of=list(rnd[:n]), parent_of=list(par[:n]))

@@ -120,3 +120,26 @@ def test_plan_compiler_threads_do_not_change_the_plan(scene, monkeypatch):
     assert out[0] == out[1]
     ref, _ = ob.predict(scene, b, 2099, opts)
     assert out[1][2099] == ref.as_tuple()
+
+
+def test_fk_schedule_puts_the_step_loops_frames_first(scene):
+    """FK schedule of the warp / block kernels: parents in earlier rounds, at most two nodes per round, and for a
+    one-object `get` the frames the step loop reads fill only the first rounds (the block-per-candidate kernel
+    leaves the others to its FK warp); the static tree is cut into levels for the prologue."""
+    b = ab.HostBatch(scene)
+    b.add_action("get fresh_tomatoes")
+    info = eb.plan_info(scene, b, ab.default_opts())
+    assert info["warp_ok"] == 1 and info["sweep_ok"] == 1
+    assert 0 < info["n_rounds_crit"] < info["n_rounds"]
+    assert info["n_stat_levels"] >= 2
+    rounds = info["round_of"]
+    for n, p in enumerate(info["parent_of"]):
+        if p >= 0:
+            assert rounds[p] < rounds[n]
+    for r in range(info["n_rounds"]):
+        assert 1 <= sum(1 for x in rounds if x == r) <= 2
+    # two objects (double_get): both hang on hands that come last in their chains; whatever the split, it is sane
+    b2 = ab.HostBatch(scene)
+    b2.add_action("double_get tomato_sauce_bottle bbq_sauce_bottle")
+    info2 = eb.plan_info(scene, b2, ab.default_opts())
+    assert 0 < info2["n_rounds_crit"] <= info2["n_rounds"]
