@@ -1712,7 +1712,12 @@ template <int CTA> AFF_DEV void k_rollout_t(const KPlan& P, int cand, double* sm
     const long long tgeo_ = K_NOW();
     if (CTA) { if (iter > 0) w_wait_ge(&X->trkSeq, iter); }      // the tracking error of the step before has been taken from geo / xcur
     // block-per-candidate: the orientation tasks (acos / atan2 / normalisations: the long branches) are the geometry warp's
-    if (lane < nTasks && !(CTA && k_geo_helper_kind(c.tdesc[8 * lane + TD_KIND]))) k_task_geo(c, c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur);
+    {
+      const bool orient = lane < nTasks && k_geo_helper_kind(c.tdesc[8 * (lane < nTasks ? lane : 0) + TD_KIND]);
+      if (lane < nTasks && !orient) k_task_geo(c, c.tdesc + 8 * lane, tasks + lane, geo + AFFK_GEO * lane, xcur);
+      // one warp: the orientation tasks share one normalisation and one acos instead of a branch each
+      if (!CTA) k_task_geo_orient(c, c.tdesc + 8 * (orient ? lane : 0), geo + AFFK_GEO * (orient ? lane : 0), xcur, orient);
+    }
     if (CTA) w_wait_ge(&X->geoHelpSeq, iter + 1);
     w_sync();
     K_SUB(12, tgeo_);
