@@ -129,6 +129,31 @@ void CandidateBatch::append(const Graph& graph, const std::vector<TaskSpec>& spe
     names.push_back(s.name);
   }
   c.n_tasks = (int32_t)names.size();
+  appendConstraints(graph, names, tSet, c);
+  candidates.push_back(c);
+  taskNames.push_back(names);
+}
+
+void CandidateBatch::appendLike(const Graph& graph, const CandidateBatch& proto, size_t like, const ActivationSet& tSet,
+                                int poseBody, const double* poseQ6)
+{
+  const aff_candidate& pc = proto.candidates[like];
+  aff_candidate c;
+  std::memset(&c, 0, sizeof(c));
+  c.first_task = (int32_t)tasks.size();
+  c.first_constraint = (int32_t)constraints.size();
+  c.pose_body = poseBody;
+  if (poseBody >= 0 && poseQ6) for (int k = 0; k < 6; ++k) c.pose_q6[k] = poseQ6[k];
+  tasks.insert(tasks.end(), proto.tasks.begin() + pc.first_task, proto.tasks.begin() + pc.first_task + pc.n_tasks);
+  c.n_tasks = pc.n_tasks;
+  const std::vector<std::string>& names = proto.taskNames[like];
+  appendConstraints(graph, names, tSet, c);
+  candidates.push_back(c);
+  taskNames.push_back(names);
+}
+
+void CandidateBatch::appendConstraints(const Graph& graph, const std::vector<std::string>& names, const ActivationSet& tSet, aff_candidate& c)
+{
   for (const ActivationSet::Entry& e : tSet.entries) {
     aff_constraint k;
     std::memset(&k, 0, sizeof(k));
@@ -146,8 +171,6 @@ void CandidateBatch::append(const Graph& graph, const std::vector<TaskSpec>& spe
     constraints.push_back(k);
   }
   c.n_constraints = (int32_t)constraints.size() - c.first_constraint;
-  candidates.push_back(c);
-  taskNames.push_back(names);
 }
 
 // --------------------------------------------------------------- ActionBase

@@ -77,6 +77,16 @@ struct CandidateBatch
   std::vector<std::vector<std::string>> taskNames;   // per candidate, for messages
   void append(const Graph& graph, const std::vector<TaskSpec>& tasks, const ActivationSet& tSet,
               int poseBody = -1, const double* poseQ6 = nullptr);
+  // Same as append() for a candidate whose task list is that of candidate `like` of `proto` (sweeps: the tasks of
+  // a command and hand do not change with the perturbation): the task records and names are copied, only the
+  // trajectory is converted.
+  void appendLike(const Graph& graph, const CandidateBatch& proto, size_t like, const ActivationSet& tSet,
+                  int poseBody = -1, const double* poseQ6 = nullptr);
+
+private:
+  void appendConstraints(const Graph& graph, const std::vector<std::string>& names, const ActivationSet& tSet, aff_candidate& c);
+
+public:
 };
 
 class ActionBase

@@ -238,6 +238,14 @@ int aff_host_batch_add_perturbed(aff_host_batch* b, aff_host_scene* s, const cha
     // candidate i depends on (seed0 + i, i mod nSol) only: slices of the index range are described by host
     // threads into private batches and appended in index order (AFF_HOST_THREADS, default: the hardware
     // threads, at most 16; below 2048 candidates one thread)
+    // the task list of a command and hand does not depend on the perturbation: one prototype per solution
+    // (AFF_HOST_PERTURBED_GENERIC=1: every candidate through the generic append(), for the equality test)
+    CandidateBatch proto;
+    const bool generic = getenv("AFF_HOST_PERTURBED_GENERIC") != nullptr;
+    for (size_t r = 0; r < nSol; ++r) {
+      const ActionGet& g = *static_cast<ActionGet*>(sols[r].get());
+      proto.append(s->graph, g.createTasks(), ActivationSet());
+    }
     auto describe = [&](size_t lo, size_t hi, CandidateBatch& out, std::vector<std::string>& cmds) {
       out.candidates.reserve(out.candidates.size() + (hi - lo));
       for (size_t i = lo; i < hi; ++i) {
@@ -253,7 +261,8 @@ int aff_host_batch_add_perturbed(aff_host_batch* b, aff_host_scene* s, const cha
         local.preGraspDist *= uni(st, 0.8, 1.2);
         local.liftHeight += dz + uni(st, -0.03, 0.03);
         const double delay = 5.0 * dt;
-        out.append(s->graph, local.createTasks(), local.createTrajectory(delay, local.getDurationHint() + delay), obj, p6);
+        if (generic) out.append(s->graph, local.createTasks(), local.createTrajectory(delay, local.getDurationHint() + delay), obj, p6);
+        else out.appendLike(s->graph, proto, i % nSol, local.createTrajectory(delay, local.getDurationHint() + delay), obj, p6);
         cmds.push_back(local.getActionCommand());
       }
     };

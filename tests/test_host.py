@@ -393,3 +393,24 @@ def test_perturbed_candidates_do_not_depend_on_the_host_threads(monkeypatch):
                 [b.command(i) for i in (0, 6, 7, 2600, 5006)] if hasattr(b, "command") else None)
 
     assert tables(1) == tables(4)
+
+
+def test_perturbed_candidates_from_prototype_tasks_equal_the_generic_path(monkeypatch):
+    """add_perturbed copies the task records of a command and hand from one prototype per solution (they do not
+    depend on the perturbation) and converts only the trajectory: byte-identical to the generic append()."""
+    import ctypes as C
+    scene = ab.HostScene()
+
+    def tables(generic):
+        if generic:
+            monkeypatch.setenv("AFF_HOST_PERTURBED_GENERIC", "1")
+        else:
+            monkeypatch.delenv("AFF_HOST_PERTURBED_GENERIC", raising=False)
+        b = ab.HostBatch(scene)
+        for cmd, n in (("get tomato_sauce_bottle", 301), ("get italian_seasoning_bowl", 3000)):
+            assert b.add_perturbed(cmd, n, seed0=11) == n
+        return (C.string_at(b.tasks_ptr, b.n_tasks * C.sizeof(ab.TaskDesc)),
+                C.string_at(b.constraints_ptr, b.n_constraints * C.sizeof(ab.Constraint)),
+                C.string_at(b.candidate_ptr(0), b.n_candidates * C.sizeof(ab.Candidate)))
+
+    assert tables(True) == tables(False)
